@@ -1,0 +1,509 @@
+"""Host-side configuration compiler: the reference's JSON surface -> flat POD `fw_config_t` (include/fwgym.h).
+
+Mirrors, on the host and once per (re)configuration:
+  * the config loader and recursive override of FixedWingAircraft.__init__ (fixed_wing.py:24-35) and the PyFly
+    overrides it forces (fixed_wing.py:37-46);
+  * observation bounds / normalisation defaults (fixed_wing.py:57-134), action scaling vectors and bounds
+    (fixed_wing.py:136-191);
+  * set_curriculum_level (fixed_wing.py:224-285);
+  * PyFly's own config/parameter parsing (pyfly_config.json variables -> limits in radians, actuator coefficients,
+    inertia Gammas) and the Dryden filter discretisation that scipy.signal.lsim performs per reset
+    (scipy/signal/_ltisys.py:2254-2277), done here once.
+No simulation happens here; everything per-step runs in the CUDA kernels.
+"""
+import copy
+import json
+import math
+import os
+
+import numpy as np
+
+from . import _capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_SIM_CONFIG = os.path.join(_HERE, "params", "pyfly_config.json")
+DEFAULT_SIM_PARAMS = os.path.join(_HERE, "params", "x8_param.json")
+DEFAULT_ENV_CONFIG = os.path.join(_HERE, "params", "fixed_wing_config.json")
+F32_MAX = float(np.finfo(np.float32).max)
+
+FCLASS = {"linear": 0, "exponential": 1, "quadratic": 2}
+TCLASS = {"constant": 0, "linear": 1, "sinusoidal": 2, "compensate": 3}
+ACT_NAMES = ["elevator", "aileron", "throttle"]
+
+
+class ConfigError(ValueError):
+    pass
+
+
+def set_config_attrs(parent, kws):
+    """fixed_wing.py:24-29: dict values recurse; so do values addressed into a list (int keys)."""
+    for attr, val in kws.items():
+        if isinstance(val, dict) or isinstance(parent[attr], list):
+            set_config_attrs(parent[attr], val)
+        else:
+            parent[attr] = val
+
+
+def _set_sim_config_attrs(parent, kws):
+    """PyFly's own override: recurse on dict values only."""
+    for attr, val in kws.items():
+        if isinstance(val, dict):
+            _set_sim_config_attrs(parent[attr], val)
+        else:
+            parent[attr] = val
+
+
+class SimVariable:
+    """Limits of one PyFly Variable (value_min/max, init_min/max, constraint_min/max, wrap), radians applied."""
+    LIMITS = ("value_min", "value_max", "init_min", "init_max", "constraint_min", "constraint_max", "dot_max")
+
+    def __init__(self, spec):
+        self.name = spec["name"]
+        self.value_min = spec.get("value_min")
+        self.value_max = spec.get("value_max")
+        self.init_min = spec.get("init_min") if spec.get("init_min") is not None else self.value_min
+        self.init_max = spec.get("init_max") if spec.get("init_max") is not None else self.value_max
+        self.constraint_min = spec.get("constraint_min")
+        self.constraint_max = spec.get("constraint_max")
+        self.dot_max = spec.get("dot_max")
+        if spec.get("convert_to_radians", False):
+            for a in self.LIMITS:
+                if getattr(self, a) is not None:
+                    setattr(self, a, getattr(self, a) * (np.pi / 180))
+        self.wrap = bool(spec.get("wrap", False))
+        self.order = spec.get("order")
+        self.tau = spec.get("tau")
+        self.omega_0 = spec.get("omega_0")
+        self.zeta = spec.get("zeta")
+        self.disabled = bool(spec.get("disabled", False))
+
+    @property
+    def coefs(self):
+        if self.order == 1:
+            return [[-1 / self.tau, 0, 1 / self.tau], [0, 0, 0]]
+        if self.order == 2:
+            return [[0, 1, 0], [-self.omega_0 ** 2, -2 * self.zeta * self.omega_0, self.omega_0 ** 2]]
+        raise ConfigError("actuator %s needs order 1 or 2" % self.name)
+
+
+def dryden_transfer_functions(b, intensity, h=100.0, V_a=25.0):
+    """(num, den, noise stream) of the six MIL-F-8785C shaping filters as PyFly's DrydenGustModel builds them
+    (SURVEY App. D); feet units."""
+    ft = 3.28084
+    h, b, V_a = h * ft, b * ft, V_a * ft
+    if intensity is None or intensity == "light":
+        W_20 = 15 * ft
+    elif intensity == "moderate":
+        W_20 = 30 * ft
+    elif intensity == "severe":
+        W_20 = 45 * ft
+    else:
+        raise ConfigError("Unsupported turbulence intensity %r" % (intensity,))
+    L_u = h / (0.177 + 0.000823 * h) ** 1.2
+    L_v, L_w = L_u, h
+    sigma_w = 0.1 * W_20
+    sigma_u = sigma_w / (0.177 + 0.000823 * h) ** 0.4
+    sigma_v = sigma_u
+    K_u = sigma_u * math.sqrt((2 * L_u) / (math.pi * V_a))
+    K_v = sigma_v * math.sqrt(L_v / (math.pi * V_a))
+    K_w = sigma_w * math.sqrt(L_w / (math.pi * V_a))
+    T_u = L_u / V_a
+    T_v1, T_v2 = math.sqrt(3.0) * L_v / V_a, L_v / V_a
+    T_w1, T_w2 = math.sqrt(3.0) * L_w / V_a, L_w / V_a
+    K_p = sigma_w * math.sqrt(0.8 / V_a) * ((math.pi / (4 * b)) ** (1 / 6)) / (L_w ** (1 / 3))
+    K_q = K_r = 1 / V_a
+    T_p = 4 * b / (math.pi * V_a)
+    T_q, T_r = T_p, 3 * b / (math.pi * V_a)
+    return [
+        ([K_u], [T_u, 1], 0),
+        ([K_v * T_v1, K_v], [T_v2 ** 2, 2 * T_v2, 1], 1),
+        ([K_w * T_w1, K_w], [T_w2 ** 2, 2 * T_w2, 1], 2),
+        ([K_p], [T_p, 1], 3),
+        ([-K_w * K_q * T_w1, -K_w * K_q, 0], [T_q * T_w2 ** 2, T_w2 ** 2 + 2 * T_q * T_w2, T_q + 2 * T_w2, 1], 1),
+        ([K_v * K_r * T_v1, K_v * K_r, 0], [T_r * T_v2 ** 2, T_v2 ** 2 + 2 * T_r * T_v2, T_r + 2 * T_v2, 1], 2),
+    ]
+
+
+def discretise_filter(num, den, dt):
+    """The (Ad, Bd0, Bd1, C, D) that scipy.signal.lsim(interp=True) builds from a transfer function."""
+    import scipy.linalg
+    import scipy.signal
+    A, B, C, D = scipy.signal.tf2ss(num, den)
+    n, m = A.shape[0], 1
+    M = np.vstack([np.hstack([A * dt, B * dt, np.zeros((n, m))]),
+                   np.hstack([np.zeros((m, n + m)), np.identity(m)]),
+                   np.zeros((m, n + 2 * m))])
+    E = scipy.linalg.expm(M.T)
+    Ad = E[:n, :n]
+    Bd1 = E[n + m:, :n]
+    Bd0 = E[n:n + m, :n] - Bd1
+    return Ad, Bd0[0], Bd1[0], C[0], float(D[0, 0])
+
+
+class CompiledConfig:
+    """Holds the (mutable) parsed JSON configs, mirrors FixedWingAircraft's derived attributes and produces the POD."""
+
+    def __init__(self, config_path=None, sim_config_path=None, sim_parameter_path=None, config_kw=None,
+                 sim_config_kw=None, precision="fp64"):
+        config_path = config_path or DEFAULT_ENV_CONFIG
+        with open(config_path) as f:
+            self.cfg = json.load(f)
+        if config_kw is not None:
+            set_config_attrs(self.cfg, copy.deepcopy(config_kw))
+        sim_config_kw = dict(sim_config_kw or {})
+        sim_config_kw.update({"actuation": {"inputs": [a["name"] for a in self.cfg["action"]["states"]]}})
+        sim_config_kw["turbulence_sim_length"] = self.cfg["steps_max"]
+        with open(sim_config_path or DEFAULT_SIM_CONFIG) as f:
+            self.sim_cfg = json.load(f)
+        _set_sim_config_attrs(self.sim_cfg, copy.deepcopy(sim_config_kw))
+        with open(sim_parameter_path or DEFAULT_SIM_PARAMS) as f:
+            self.params = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        self.precision = {"fp64": 0, "fp32": 1}[precision]
+        self.state = {v["name"]: SimVariable(v) for v in self.sim_cfg["variables"]}
+        self.dt = self.sim_cfg["dt"]
+        self._check_supported()
+        self.steps_max = self.cfg["steps_max"]
+        self.integration_window = self.cfg.get("integration_window", 0)
+        self._build_spaces()
+        self._rew_factors_init = copy.deepcopy(self.cfg["reward"]["factors"])
+        self._curriculum_level = None
+        self._target_props_init = None
+        self.set_curriculum_level(1)
+
+    # ------------------------------------------------------------------------------------------------ validation
+    def _check_supported(self):
+        if [a["name"] for a in self.cfg["action"]["states"]] != ACT_NAMES:
+            raise ConfigError("action.states must be elevator, aileron, throttle (in this order)")
+        act = self.sim_cfg["actuation"]
+        if act["dynamics"] != ["elevon_left", "elevon_right", "throttle"]:
+            raise ConfigError("only elevon dynamics [elevon_left, elevon_right, throttle] are supported")
+        for n in ("roll", "pitch", "yaw"):
+            v = self.state[n]
+            if any(getattr(v, a) is not None for a in ("value_min", "value_max", "constraint_min", "constraint_max")):
+                raise ConfigError("value limits / constraints on attitude state %s are not supported" % n)
+        if self.cfg["reward"].get("randomize_scaling", False):
+            raise ConfigError("reward.randomize_scaling is not supported yet (SURVEY §8f)")
+        for key in self.cfg["simulator"]:
+            if key != "states":
+                raise ConfigError("simulator.%s randomisation is not supported yet (SURVEY §8f #4)" % key)
+        if self.sim_cfg["turbulence"] and not self.cfg["steps_max"] > 0:
+            raise ConfigError("turbulence needs steps_max > 0 (turbulence_sim_length = steps_max, fixed_wing.py:40)")
+
+    # ------------------------------------------------------------------------- fixed_wing.py:57-191 (spaces etc.)
+    def _build_spaces(self):
+        cfg = self.cfg
+        self.obs_norm = cfg["observation"].get("normalize", False)
+        obs_low, obs_high = [], []
+        for obs_var in cfg["observation"]["states"]:
+            high = obs_var.get("high", None)
+            if high is None:
+                st = self.state[obs_var["name"]]
+                high = st.value_max if st.value_max is not None else (
+                    st.constraint_max if st.constraint_max is not None else F32_MAX)
+            elif obs_var.get("convert_to_radians", False):
+                high = np.radians(high)
+            low = obs_var.get("low", None)
+            if low is None:
+                st = self.state[obs_var["name"]]
+                low = st.value_min if st.value_min is not None else (
+                    st.constraint_min if st.constraint_min is not None else -F32_MAX)
+            elif obs_var.get("convert_to_radians", False):
+                low = np.radians(low)
+            bounded = high != F32_MAX and low != -F32_MAX
+            if obs_var["type"] == "target" and obs_var["value"] == "relative":
+                obs_high.append(high - low if bounded else F32_MAX)
+                obs_low.append(low - high if bounded else -F32_MAX)
+            else:
+                obs_high.append(high)
+                obs_low.append(low)
+            if self.obs_norm:
+                if obs_var.get("mean", None) is None:
+                    obs_var["mean"] = high - low if bounded else 0
+                if obs_var.get("var", None) is None:
+                    obs_var["var"] = (high - low) / (4 ** 2) if bounded else 1
+        length, shape = cfg["observation"]["length"], cfg["observation"]["shape"]
+        if length > 1:
+            if shape == "vector":
+                obs_low, obs_high = obs_low * length, obs_high * length
+            elif shape == "matrix":
+                obs_low, obs_high = [obs_low] * length, [obs_high] * length
+            else:
+                raise ConfigError("observation.shape must be vector or matrix")
+        self.observation_low = np.array(obs_low, dtype=np.float64)
+        self.observation_high = np.array(obs_high, dtype=np.float64)
+
+        a_low, a_high, s_low, s_high = [], [], [], []
+        for av in cfg["action"]["states"]:
+            st = self.state[av["name"]]
+            state_high = st.value_max if st.value_max is not None else (
+                st.constraint_max if st.constraint_max is not None else F32_MAX)
+            state_low = st.value_min if st.value_min is not None else (
+                st.constraint_min if st.constraint_min is not None else -F32_MAX)
+            sh, sl = av.get("high", None), av.get("low", None)
+            s_high.append(F32_MAX if sh == "max" else (state_high if sh is None else sh))
+            s_low.append(-F32_MAX if sl == "max" else (state_low if sl is None else sl))
+            a_high.append(state_high)
+            a_low.append(state_low)
+        self.action_scale_to_low = np.array(a_low, dtype=np.float64)
+        self.action_scale_to_high = np.array(a_high, dtype=np.float64)
+        self.action_space_low = np.array(s_low, dtype=np.float64)
+        self.action_space_high = np.array(s_high, dtype=np.float64)
+        self.scale_actions = cfg["action"].get("scale_space", False)
+        self.action_bounds_max = self.action_bounds_min = None
+        if cfg["action"].get("bounds_multiplier", None) is not None:
+            m = cfg["action"]["bounds_multiplier"]
+            self.action_bounds_max = np.full(3, cfg["action"].get("scale_high", 1)) * m
+            self.action_bounds_min = np.full(3, cfg["action"].get("scale_low", -1)) * m
+        self.goal_enabled = cfg["target"]["success_streak_req"] > 0
+
+    # ------------------------------------------------------------------------------------ fixed_wing.py:224-285
+    def set_curriculum_level(self, level):
+        assert 0 <= level <= 1
+        self._curriculum_level = level
+        if "states" in self.cfg["simulator"]:
+            for state in self.cfg["simulator"]["states"]:
+                state = copy.copy(state)
+                state_name = state.pop("name")
+                to_rad = state.pop("convert_to_radians", False)
+                for prop, val in state.items():
+                    if val is not None:
+                        if "constraint" not in prop and any(m in prop for m in ["min", "max"]):
+                            midpoint = (state[prop[:-3] + "max"] + state[prop[:-3] + "min"]) / 2
+                            val = midpoint - level * (midpoint - val)
+                        if to_rad:
+                            val = np.radians(val)
+                    setattr(self.state[state_name], prop, val)
+        tp = {"states": {}}
+        for attr, val in self.cfg["target"].items():
+            if attr == "states":
+                for state in val:
+                    name = state.get("name")
+                    tp["states"][name] = {}
+                    for k, v in state.items():
+                        if k == "name":
+                            continue
+                        if k not in ["bound", "class"] and v is not None and not isinstance(v, bool):
+                            if k == "low":
+                                midpoint = (state["high"] + v) / 2
+                            elif k == "high":
+                                midpoint = (v + state["low"]) / 2
+                            else:
+                                midpoint = 0
+                            v = midpoint - level * (midpoint - v)
+                        tp["states"][name][k] = v
+            elif isinstance(val, list):
+                tp[attr] = val[round(len(val) * level)]
+            else:
+                tp[attr] = val
+        self._target_props_init = tp
+
+    # -------------------------------------------------------------------------------------------------- to POD
+    @property
+    def obs_dim(self):
+        return self.cfg["observation"]["length"] * len(self.cfg["observation"]["states"])
+
+    @property
+    def obs_shape(self):
+        o = self.cfg["observation"]
+        n = len(o["states"])
+        if o["length"] > 1 and o["shape"] == "matrix":
+            return (o["length"], n)
+        return (o["length"] * n,)
+
+    def pod(self):
+        c = _capi.fw_config_t()
+        c.abi_version = _capi.DEFINES["FW_ABI_VERSION"]
+        c.precision = self.precision
+        self._fill_sim(c.sim)
+        self._fill_env(c.env)
+        return c
+
+    def _fill_sim(self, s):
+        P, sc = self.params, self.sim_cfg
+        s.dt, s.rho, s.g = sc["dt"], sc["rho"], sc["g"]
+        s.rtol, s.atol = 1e-3, 1e-6
+        for k in ("mass", "S_wing", "b", "c", "S_prop", "k_motor", "k_T_P", "k_Omega", "C_prop", "e", "M", "a_0",
+                  "C_L_0", "C_L_alpha", "C_L_q", "C_L_delta_e", "C_D_p", "C_D_0", "C_D_alpha1", "C_D_alpha2",
+                  "C_D_beta1", "C_D_beta2", "C_D_q", "C_D_delta_e", "C_m_0", "C_m_alpha", "C_m_q", "C_m_delta_e",
+                  "C_m_fp", "C_Y_0", "C_Y_beta", "C_Y_p", "C_Y_r", "C_Y_delta_a", "C_Y_delta_r", "C_l_0", "C_l_beta",
+                  "C_l_p", "C_l_r", "C_l_delta_a", "C_l_delta_r", "C_n_0", "C_n_beta", "C_n_p", "C_n_r",
+                  "C_n_delta_a", "C_n_delta_r"):
+            setattr(s, k, float(P[k]))
+        s.ar = P["b"] ** 2 / P["S_wing"]
+        I = np.array([[P["Jx"], 0, -P["Jxz"]], [0, P["Jy"], 0], [-P["Jxz"], 0, P["Jz"]]])
+        g0 = I[0, 0] * I[2, 2] - I[0, 2] ** 2
+        gam = [g0, (np.abs(I[0, 2]) * (I[0, 0] - I[1, 1] + I[2, 2])) / g0,
+               (I[2, 2] * (I[2, 2] - I[1, 1]) + I[0, 2] ** 2) / g0, I[2, 2] / g0, np.abs(I[0, 2]) / g0,
+               (I[2, 2] - I[0, 0]) / I[1, 1], I[0, 2] / I[1, 1],
+               ((I[0, 0] - I[1, 1]) * I[0, 0] + I[0, 2] ** 2) / g0, I[0, 0] / g0]
+        for i, v in enumerate(gam):
+            s.gammas[i] = float(v)
+        s.Jy = float(I[1, 1])
+        s.drag_model = {"induced": 0, "polynomial": 1}[sc.get("drag_model", "induced")]
+        s.turbulence = 1 if sc["turbulence"] else 0
+        s.wind_mag_min, s.wind_mag_max = sc["wind_magnitude_min"], sc["wind_magnitude_max"]
+        s.wind_enabled = 1 if (sc["wind_magnitude_max"] != 0 or sc["wind_magnitude_min"] != 0
+                               or sc.get("allow_wind_injection", False)) else 0
+        s.turb_noise_scale = math.sqrt(math.pi / sc["dt"])
+        if sc["turbulence"]:
+            length = sc.get("turbulence_sim_length", 250)
+            # PyFly simulates `length` samples on t = linspace(0, length*dt, length): spacing length*dt/(length-1)
+            dt_eff = float(np.diff(np.linspace(0, length * sc["dt"], length))[0]) if length > 1 else sc["dt"]
+            for i, (num, den, stream) in enumerate(dryden_transfer_functions(P["b"], sc["turbulence_intensity"])):
+                Ad, Bd0, Bd1, C, D = discretise_filter(num, den, dt_eff)
+                f = s.filt[i]
+                f.n, f.stream = Ad.shape[0], stream
+                for a in range(f.n):
+                    for b_ in range(f.n):
+                        f.Ad[a * 3 + b_] = float(Ad[a, b_])
+                    f.Bd0[a], f.Bd1[a], f.C[a] = float(Bd0[a]), float(Bd1[a]), float(C[a])
+                f.D = D
+        for name, var in self.state.items():
+            v = s.var[_capi.sv_id(name)]
+            flags = 0
+            for attr, bit in (("value_min", "FW_VC_VMIN"), ("value_max", "FW_VC_VMAX"),
+                              ("constraint_min", "FW_VC_CMIN"), ("constraint_max", "FW_VC_CMAX")):
+                val = getattr(var, attr)
+                if val is not None:
+                    flags |= _capi.DEFINES[bit]
+                    setattr(v, {"value_min": "vmin", "value_max": "vmax", "constraint_min": "cmin",
+                                "constraint_max": "cmax"}[attr], float(val))
+            if var.wrap:
+                flags |= _capi.DEFINES["FW_VC_WRAP"]
+            v.flags = flags
+            v.init_min = float(var.init_min) if var.init_min is not None else 0.0
+            v.init_max = float(var.init_max) if var.init_max is not None else 0.0
+        for i, name in enumerate(sc["actuation"]["dynamics"]):
+            var = self.state[name]
+            co = var.coefs
+            for j in range(3):
+                s.act_coef[i][j] = float(co[0][j])
+                s.act_coef[i][3 + j] = float(co[1][j])
+            s.act_has_dot_max[i] = 1 if var.dot_max is not None else 0
+            s.act_dot_max[i] = float(var.dot_max) if var.dot_max is not None else 0.0
+        a = self.cfg["action"]
+        s.scale_actions = 1 if self.scale_actions else 0
+        s.has_scale_low = 1 if a.get("scale_low") is not None else 0
+        s.has_scale_high = 1 if a.get("scale_high") is not None else 0
+        s.scale_low = float(a.get("scale_low")) if a.get("scale_low") is not None else 0.0
+        s.scale_high = float(a.get("scale_high")) if a.get("scale_high") is not None else 0.0
+        if self.scale_actions and not (s.has_scale_low and s.has_scale_high):
+            raise ConfigError("action.scale_space needs scale_low and scale_high")
+        for j in range(3):
+            s.act_to_low[j] = float(self.action_scale_to_low[j])
+            s.act_to_high[j] = float(self.action_scale_to_high[j])
+
+    def _fill_env(self, e):
+        cfg = self.cfg
+        o = cfg["observation"]
+        e.steps_max = int(cfg["steps_max"])
+        e.integration_window = int(self.integration_window)
+        e.obs_len, e.obs_step = int(o["length"]), int(o.get("step", 1))
+        e.obs_nvar = len(o["states"])
+        if e.obs_nvar > _capi.DEFINES["FW_MAX_OBS_VARS"]:
+            raise ConfigError("too many observation variables")
+        e.obs_shape = {"vector": 0, "matrix": 1}[o["shape"]]
+        e.obs_norm = 1 if self.obs_norm else 0
+        noise = o.get("noise", None)
+        e.obs_noise = 1 if noise is not None else 0
+        if noise is not None:
+            e.obs_noise_mean, e.obs_noise_std = float(noise["mean"]), float(noise["var"])   # "var" is used as a std
+        tnames = list(self._target_props_init["states"].keys())
+        for i, ov in enumerate(o["states"]):
+            v = e.obs[i]
+            v.type = {"state": 0, "target": 1, "action": 2}[ov["type"]]
+            if ov["type"] == "state":
+                v.ref = _capi.sv_id(ov["name"])
+            elif ov["type"] == "target":
+                v.ref = tnames.index(ov["name"])
+                v.value_kind = {"relative": 0, "absolute": 1, "integrator": 2}[ov["value"]]
+            else:
+                v.ref = ACT_NAMES.index(ov["name"])
+                v.window = int(ov.get("window_size", 1))
+                if v.window > 9:
+                    raise ConfigError("action observation window_size > 9 not supported (float32 pairwise order)")
+            v.norm = 1 if ov.get("norm", True) else 0
+            if self.obs_norm and v.norm:
+                v.mean, v.var = float(ov["mean"]), float(ov["var"])
+        if self.action_bounds_max is not None:
+            e.has_bounds = 1
+            for j in range(3):
+                e.bounds_min[j], e.bounds_max[j] = float(self.action_bounds_min[j]), float(self.action_bounds_max[j])
+        tp = self._target_props_init
+        e.n_targets = len(tnames)
+        if e.n_targets > _capi.DEFINES["FW_MAX_TARGETS"]:
+            raise ConfigError("at most %d target states are supported" % _capi.DEFINES["FW_MAX_TARGETS"])
+        e.resample_every = int(tp.get("resample_every", 0) or 0)
+        e.streak_req = int(tp["success_streak_req"])
+        e.streak_fraction = float(tp["success_streak_fraction"])
+        e.on_success = {"none": 0, "done": 1, "new": 2}[tp["on_success"]]
+        for k, name in enumerate(tnames):
+            props, t = tp["states"][name], e.tgt[k]
+            cls = props.get("class", "constant")
+            if cls not in TCLASS:
+                raise ConfigError("target class %r is not supported" % cls)
+            if cls == "compensate" and name != "Va":
+                raise ConfigError("target class compensate is only defined for Va (fixed_wing.py:944-976)")
+            t.sv, t.cls = _capi.sv_id(name), TCLASS[cls]
+            t.wrap = 1 if self.state[name].wrap else 0
+            rad = bool(props.get("convert_to_radians", False))
+            t.to_radians = 1 if rad else 0
+            conv = (lambda x: float(np.radians(x))) if rad else float
+            t.low, t.high = conv(props["low"]), conv(props["high"])
+            if props.get("delta", None) is not None:
+                t.has_delta, t.delta = 1, conv(props["delta"])
+            if props.get("bound", None) is not None:
+                t.has_bound, t.bound = 1, conv(props["bound"])
+            if cls == "linear":
+                t.slope_low, t.slope_high = float(props["slope_low"]), float(props["slope_high"])
+            if cls == "sinusoidal":
+                t.amp_low, t.amp_high = float(props["amplitude_low"]), float(props["amplitude_high"])
+                t.period_low, t.period_high = float(props.get("period_low", 250)), float(props.get("period_high", 500))
+        r = cfg["reward"]
+        e.potential = 1 if r.get("form", "absolute") == "potential" else 0
+        sf = r.get("step_fail", 0)
+        e.step_fail_timesteps = 1 if sf == "timesteps" else 0
+        e.step_fail_value = 0.0 if sf == "timesteps" else float(sf)
+        e.n_terms = len(r["terms"])
+        seen = set()
+        for i, term in enumerate(r["terms"]):
+            fc = FCLASS[term["function_class"]]
+            if fc in seen:
+                raise ConfigError("duplicate reward term function_class")
+            seen.add(fc)
+            e.term_fclass[i], e.term_weight[i] = fc, float(term["weight"])
+        e.n_factors = len(r["factors"])
+        if e.n_factors > _capi.DEFINES["FW_MAX_FACTORS"]:
+            raise ConfigError("too many reward factors")
+        for i, comp in enumerate(r["factors"]):
+            F = e.fac[i]
+            F.cls = {"action": 0, "state": 1, "success": 2, "step": 3, "goal": 4}[comp["class"]]
+            F.fclass = FCLASS[comp["function_class"]]
+            if F.fclass not in seen:
+                raise ConfigError("reward factor %s uses function_class without a term" % comp.get("name"))
+            if comp["class"] == "action":
+                F.type = {"value": 0, "delta": 1, "bound": 2}[comp["type"]]
+                if comp["type"] == "delta":
+                    if comp["name"] != "action":
+                        raise ConfigError("action delta reward must be named 'action' (fixed_wing.py:689)")
+                    F.window = int(comp["window_size"])
+                if comp["type"] == "bound" and self.action_bounds_max is None:
+                    raise ConfigError("action bound reward needs action.bounds_multiplier")
+            elif comp["class"] == "state":
+                F.type = {"value": 0, "error": 1, "int_error": 2}[comp["type"]]
+                F.ref = _capi.sv_id(comp["name"]) if comp["type"] == "value" else tnames.index(comp["name"])
+            elif comp["class"] == "success":
+                if comp["value"] == "timesteps":
+                    F.value_timesteps = 1
+                else:
+                    F.value = float(comp["value"])
+            elif comp["class"] == "step":
+                F.value = float(comp["value"])
+            elif comp["class"] == "goal":
+                F.type = {"per_state": 0, "all": 1}[comp["type"]]
+                F.value = float(comp["value"])
+            F.scaling = float(comp["scaling"])
+            F.shaping = 1 if comp.get("shaping", False) else 0
+            if comp.get("max", None) is not None:
+                F.has_max, F.max = 1, float(comp["max"])
+            F.sign = float(np.sign(comp.get("sign", -1)))

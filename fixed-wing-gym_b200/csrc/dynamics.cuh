@@ -1,0 +1,336 @@
+// 6-DOF Skywalker-X8 right-hand side and scipy-RK45-equivalent adaptive dopri5 driver, one thread per aircraft.
+//
+// What it replaces: PyFly.step / PyFly._dynamics / _forces / _f_* (pyfly 0.1.2, restated in
+// oracle/pyfly_restated.py) and scipy.integrate.solve_ivp(RK45) (scipy/integrate/_ivp/rk.py:14-176,
+// common.py:63-134, base.py:179-210) as called once per env step from fixed_wing.py:358.
+#pragma once
+#include <math_constants.h>
+#include "layout.h"
+
+#define FW_STATUS_RUNNING 0
+#define FW_STATUS_FINISHED 1
+#define FW_STATUS_TOO_SMALL 2
+
+template <typename T> struct FwMath;
+template <> struct FwMath<double> {
+  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+  static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+  static __device__ __forceinline__ double asin_(double x) { return asin(x); }
+  static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+  static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
+  static __device__ __forceinline__ double next_up(double x) { return nextafter(x, CUDART_INF); }
+  static __device__ __forceinline__ double exp_arg(double x) { return x; }
+};
+template <> struct FwMath<float> {
+  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+  static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+  static __device__ __forceinline__ float asin_(float x) { return asinf(x); }
+  static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+  static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+  static __device__ __forceinline__ float next_up(float x) { return nextafterf(x, CUDART_INF_F); }
+  // keep exp() finite in fp32: (1+e1)(1+e2) stays below FLT_MAX (e1*e2 = exp(2*M*a_0) is constant)
+  static __device__ __forceinline__ float exp_arg(float x) { return fminf(x, 80.0f); }
+};
+
+// PyFly Variable.apply_conditions: constraint check -> clip -> (wrap).  `fail` keeps the FIRST violated variable.
+template <typename T>
+__device__ __forceinline__ T fw_cond(const fw_var_t& v, int sv, T x, int& fail) {
+  const uint32_t fl = v.flags;
+  if ((fl & FW_VC_CMIN) && x < (T)v.cmin && !fail) fail = FW_TERM_FAIL_BASE + sv;
+  if ((fl & FW_VC_CMAX) && x > (T)v.cmax && !fail) fail = FW_TERM_FAIL_BASE + sv;
+  if (fl & FW_VC_VMIN) x = x < (T)v.vmin ? (T)v.vmin : x;
+  if (fl & FW_VC_VMAX) x = x > (T)v.vmax ? (T)v.vmax : x;
+  if (fl & FW_VC_WRAP) {
+    T ax = fabs(x);
+    if (ax > (T)CUDART_PI) {   // np.sign(v) * (|v| % pi - pi)
+      T s = x > 0 ? (T)1 : (T)-1;
+      x = s * (fmod(ax, (T)CUDART_PI) - (T)CUDART_PI);
+    }
+  }
+  return x;
+}
+
+// per-step inputs that are constant during one env step
+template <typename T> struct FwStepIn {
+  T cmd[3];      // constrained setpoints for elevon_left, elevon_right, throttle
+  T gl[3];       // linear gust (body)
+  T ga[3];       // angular gust
+  T wind[3];     // steady wind NED
+};
+
+// d/dt of the 19-state vector.  y is the RAW trial state; PyFly conditions every component (clip / constraint) before
+// use except the quaternion, which is used un-normalised (oracle/pyfly_restated.py: _dynamics, _forces).
+template <typename T>
+__device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in, const T (&y)[FW_N_ODE],
+                                       T (&dy)[FW_N_ODE], int& fail) {
+  typedef FwMath<T> Mt;
+  const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
+  const T p = fw_cond<T>(P.var[FW_SV_OMEGA_P], FW_SV_OMEGA_P, y[4], fail);
+  const T q = fw_cond<T>(P.var[FW_SV_OMEGA_Q], FW_SV_OMEGA_Q, y[5], fail);
+  const T r = fw_cond<T>(P.var[FW_SV_OMEGA_R], FW_SV_OMEGA_R, y[6], fail);
+  (void)fw_cond<T>(P.var[FW_SV_POS_N], FW_SV_POS_N, y[7], fail);
+  (void)fw_cond<T>(P.var[FW_SV_POS_E], FW_SV_POS_E, y[8], fail);
+  (void)fw_cond<T>(P.var[FW_SV_POS_D], FW_SV_POS_D, y[9], fail);
+  const T u = fw_cond<T>(P.var[FW_SV_VEL_U], FW_SV_VEL_U, y[10], fail);
+  const T v = fw_cond<T>(P.var[FW_SV_VEL_V], FW_SV_VEL_V, y[11], fail);
+  const T w = fw_cond<T>(P.var[FW_SV_VEL_W], FW_SV_VEL_W, y[12], fail);
+  // actuators: value conditions + rate clip (ControlVariable.apply_conditions)
+  const T el = fw_cond<T>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, y[13], fail);
+  const T er = fw_cond<T>(P.var[FW_SV_ELEVON_R], FW_SV_ELEVON_R, y[14], fail);
+  const T th = fw_cond<T>(P.var[FW_SV_THROTTLE], FW_SV_THROTTLE, y[15], fail);
+  T ad[3] = {y[16], y[17], y[18]};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (P.act_has_dot_max[i]) {
+      const T m = (T)P.act_dot_max[i];
+      ad[i] = ad[i] < -m ? -m : (ad[i] > m ? m : ad[i]);
+    }
+  const T ail = fw_cond<T>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-er + el) / (T)2, fail);
+  const T elev = fw_cond<T>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (er + el) / (T)2, fail);
+  const T rud = (T)0;
+
+  // ---- airspeed factors (PyFly._calculate_airspeed_factors with the quaternion rotation) ----
+  T ur = u, vr = v, wr = w;
+  if (P.wind_enabled) {
+    const T wn = in.wind[0], we = in.wind[1], wd = in.wind[2];
+    ur -= ((T)-1 + 2 * (e0 * e0 + e1 * e1)) * wn + 2 * (e1 * e2 + e3 * e0) * we + 2 * (e1 * e3 - e2 * e0) * wd;
+    vr -= 2 * (e1 * e2 - e3 * e0) * wn + ((T)-1 + 2 * (e0 * e0 + e2 * e2)) * we + 2 * (e2 * e3 + e1 * e0) * wd;
+    wr -= 2 * (e1 * e3 + e2 * e0) * wn + 2 * (e2 * e3 - e1 * e0) * we + ((T)-1 + 2 * (e0 * e0 + e3 * e3)) * wd;
+  }
+  T pa = p, qa = q, ra = r;
+  if (P.turbulence) {
+    ur -= in.gl[0]; vr -= in.gl[1]; wr -= in.gl[2];
+    pa -= in.ga[0]; qa -= in.ga[1]; ra -= in.ga[2];
+  }
+  T Va = Mt::sqrt_(ur * ur + vr * vr + wr * wr);
+  T alpha = Mt::atan2_(wr, ur);
+  T beta = Mt::asin_(vr / Va);
+  Va = fw_cond<T>(P.var[FW_SV_VA], FW_SV_VA, Va, fail);
+  alpha = fw_cond<T>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, fail);
+  beta = fw_cond<T>(P.var[FW_SV_BETA], FW_SV_BETA, beta, fail);
+
+  // ---- forces and moments (PyFly._forces) ----
+  const T pre = (T)0.5 * (T)P.rho * Va * Va * (T)P.S_wing;
+  const T mg = (T)P.mass * (T)P.g;
+  const T fgx = mg * (2 * (e1 * e3 - e2 * e0));
+  const T fgy = mg * (2 * (e2 * e3 + e1 * e0));
+  const T fgz = mg * (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2);
+
+  const T CLlin = (T)P.C_L_0 + (T)P.C_L_alpha * alpha;
+  const T ex1 = Mt::exp_(Mt::exp_arg(-(T)P.M * (alpha - (T)P.a_0)));
+  const T ex2 = Mt::exp_(Mt::exp_arg((T)P.M * (alpha + (T)P.a_0)));
+  const T sigma = (1 + ex1 + ex2) / ((1 + ex1) * (1 + ex2));
+  T sa, ca, sb, cb;
+  Mt::sincos_(alpha, &sa, &ca);
+  Mt::sincos_(beta, &sb, &cb);
+  const T sgn = alpha > 0 ? (T)1 : (alpha < 0 ? (T)-1 : (T)0);
+  const T CL = (1 - sigma) * CLlin + sigma * (2 * sgn * sa * sa * ca);
+  const T inv2Va = (T)1 / (2 * Va);
+  const T c2Va = (T)P.c * inv2Va, b2Va = (T)P.b * inv2Va;
+  const T lift = pre * (CL + (T)P.C_L_q * c2Va * qa + (T)P.C_L_delta_e * elev);
+  T CDa;
+  if (P.drag_model == 0)
+    CDa = (T)P.C_D_p + (1 - sigma) * CLlin * CLlin / ((T)CUDART_PI * (T)P.e * (T)P.ar) + sigma * (2 * sgn * sa * sa * sa);
+  else
+    CDa = (T)P.C_D_0 + (T)P.C_D_alpha1 * alpha + (T)P.C_D_alpha2 * alpha * alpha;
+  const T CDb = (T)P.C_D_beta1 * beta + (T)P.C_D_beta2 * beta * beta;
+  const T drag = pre * (CDa + CDb + (T)P.C_D_q * c2Va * qa + (T)P.C_D_delta_e * elev * elev);
+  const T Cm = (1 - sigma) * ((T)P.C_m_0 + (T)P.C_m_alpha * alpha) + sigma * ((T)P.C_m_fp * sgn * sa * sa);
+  const T mm = pre * (T)P.c * (Cm + (T)P.C_m_q * b2Va * qa + (T)P.C_m_delta_e * elev);
+  const T fy = pre * ((T)P.C_Y_0 + (T)P.C_Y_beta * beta + (T)P.C_Y_p * b2Va * pa + (T)P.C_Y_r * b2Va * ra +
+                      (T)P.C_Y_delta_a * ail + (T)P.C_Y_delta_r * rud);
+  const T ll = pre * (T)P.b * ((T)P.C_l_0 + (T)P.C_l_beta * beta + (T)P.C_l_p * b2Va * pa + (T)P.C_l_r * b2Va * ra +
+                               (T)P.C_l_delta_a * ail + (T)P.C_l_delta_r * rud);
+  const T nn = pre * (T)P.b * ((T)P.C_n_0 + (T)P.C_n_beta * beta + (T)P.C_n_p * b2Va * pa + (T)P.C_n_r * b2Va * ra +
+                               (T)P.C_n_delta_a * ail + (T)P.C_n_delta_r * rud);
+  // f_aero = R(0, alpha, beta) * [-D, Y, -L]
+  const T fax = ca * cb * (-drag) + ca * sb * fy + sa * lift;
+  const T fay = sb * drag + cb * fy;
+  const T faz = sa * cb * (-drag) + sa * sb * fy - ca * lift;
+  const T Vd = Va + th * ((T)P.k_motor - Va);
+  const T fprop = (T)0.5 * (T)P.rho * (T)P.S_prop * (T)P.C_prop * Vd * (Vd - Va);
+  const T kot = (T)P.k_Omega * th;
+  const T tprop = -(T)P.k_T_P * kot * kot;
+  const T fx = fprop + fgx + fax, fyy = fgy + fay, fz = fgz + faz;
+  const T tl = ll + tprop, tm = mm, tn = nn;
+
+  // ---- kinematics / rigid body ----
+  dy[0] = (T)0.5 * (-p * e1 - q * e2 - r * e3);
+  dy[1] = (T)0.5 * (p * e0 + r * e2 - q * e3);
+  dy[2] = (T)0.5 * (q * e0 - r * e1 + p * e3);
+  dy[3] = (T)0.5 * (r * e0 + q * e1 - p * e2);
+  const double* G = P.gammas;
+  dy[4] = (T)G[1] * p * q - (T)G[2] * q * r + (T)G[3] * tl + (T)G[4] * tn;
+  dy[5] = (T)G[5] * p * r - (T)G[6] * (p * p - r * r) + tm / (T)P.Jy;
+  dy[6] = (T)G[7] * p * q - (T)G[1] * q * r + (T)G[4] * tl + (T)G[8] * tn;
+  dy[7] = (e1 * e1 + e0 * e0 - e2 * e2 - e3 * e3) * u + 2 * (e1 * e2 - e3 * e0) * v + 2 * (e1 * e3 + e2 * e0) * w;
+  dy[8] = 2 * (e1 * e2 + e3 * e0) * u + (e2 * e2 + e0 * e0 - e1 * e1 - e3 * e3) * v + 2 * (e2 * e3 - e1 * e0) * w;
+  dy[9] = 2 * (e1 * e3 - e2 * e0) * u + 2 * (e2 * e3 + e1 * e0) * v + (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2) * w;
+  const T im = (T)1 / (T)P.mass;
+  dy[10] = r * v - q * w + fx * im;
+  dy[11] = p * w - r * u + fyy * im;
+  dy[12] = q * u - p * v + fz * im;
+  const T av[3] = {el, er, th};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double* c = P.act_coef[i];
+    dy[13 + i] = av[i] * (T)c[0] + in.cmd[i] * (T)c[2] + ad[i] * (T)c[1];
+    dy[16 + i] = av[i] * (T)c[3] + in.cmd[i] * (T)c[5] + ad[i] * (T)c[4];
+  }
+}
+
+// Dormand-Prince 5(4) tableau (scipy/integrate/_ivp/rk.py:541-552).  Row 6 of A is B (FSAL).
+__constant__ double c_dpA[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+__constant__ double c_dpE[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+
+// K-stage storage: shared memory, [slot][component][thread] so a warp's access to one (slot, component) is 32
+// consecutive words -> conflict-free.
+template <typename T, int BLOCK> struct FwKStore {
+  T* base;
+  __device__ __forceinline__ T& at(int slot, int c) { return base[(slot * FW_N_ODE + c) * BLOCK + threadIdx.x]; }
+};
+
+// One env step of PyFly's integration: solve_ivp(fun, (0, dt), y0) with RK45 defaults.  On return y holds
+// sol.y[:, -1]; attempts/accepted count dopri5 step attempts; `fail` != 0 if a ConstraintException was raised by any
+// RHS evaluation (the integration is abandoned immediately, as the exception does in PyFly).
+template <typename T, int BLOCK>
+__device__ __forceinline__ int fw_integrate_step(const fw_sim_t& P, const FwStepIn<T>& in, T (&y)[FW_N_ODE],
+                                                 FwKStore<T, BLOCK> K, int& attempts, int& accepted, int& fail) {
+  typedef FwMath<T> Mt;
+  const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
+  const T sqrtn = (T)4.358898943540674;   // 19 ** 0.5
+  T f[FW_N_ODE], ys[FW_N_ODE];
+  attempts = 0;
+  accepted = 0;
+
+  // RK45.__init__: f = fun(t0, y0) ; h_abs = select_initial_step(...)   (rk.py:94-100, common.py:109-134)
+  fw_rhs<T>(P, in, y, f, fail);
+  if (fail) return FW_STATUS_FINISHED;
+  T h_abs;
+  {
+    T s0 = 0, s1 = 0;
+#pragma unroll
+    for (int c = 0; c < FW_N_ODE; ++c) {
+      const T sc = atol + fabs(y[c]) * rtol;
+      const T a = y[c] / sc, b = f[c] / sc;
+      s0 += a * a;
+      s1 += b * b;
+      K.at(0, c) = f[c];
+    }
+    const T d0 = Mt::sqrt_(s0) / sqrtn, d1 = Mt::sqrt_(s1) / sqrtn;
+    T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
+    h0 = h0 < tb ? h0 : tb;
+#pragma unroll
+    for (int c = 0; c < FW_N_ODE; ++c) ys[c] = y[c] + h0 * f[c];
+    T f1[FW_N_ODE];
+    fw_rhs<T>(P, in, ys, f1, fail);
+    if (fail) return FW_STATUS_FINISHED;
+    T s2 = 0;
+#pragma unroll
+    for (int c = 0; c < FW_N_ODE; ++c) {
+      const T sc = atol + fabs(y[c]) * rtol;
+      const T a = (f1[c] - f[c]) / sc;
+      s2 += a * a;
+    }
+    const T d2 = Mt::sqrt_(s2) / sqrtn / h0;
+    T h1;
+    if (d1 <= (T)1e-15 && d2 <= (T)1e-15) {
+      h1 = h0 * (T)1e-3;
+      h1 = h1 > (T)1e-6 ? h1 : (T)1e-6;
+    } else {
+      h1 = Mt::pow_((T)0.01 / (d1 > d2 ? d1 : d2), (T)0.2);
+    }
+    h_abs = 100 * h0;
+    h_abs = h_abs < h1 ? h_abs : h1;
+    h_abs = h_abs < tb ? h_abs : tb;
+  }
+
+  // solve_ivp loop of RK45._step_impl (rk.py:111-176); one iteration of this loop == one step attempt
+  T t = 0, min_step = 0;
+  bool newstep = true, rejected = false;
+  int status = FW_STATUS_RUNNING;
+  while (status == FW_STATUS_RUNNING) {
+    if (newstep) {
+      min_step = 10 * fabs(Mt::next_up(t) - t);
+      if (h_abs < min_step) h_abs = min_step;
+      rejected = false;
+      newstep = false;
+    }
+    if (h_abs < min_step) { status = FW_STATUS_TOO_SMALL; break; }
+    T t_new = t + h_abs;
+    if (t_new - tb > 0) t_new = tb;
+    const T h = t_new - t;
+    h_abs = fabs(h);
+    ++attempts;
+
+    // rk_step: stages 1..5 then the FSAL stage (row 6 == B) which gives y_new and f_new
+    for (int s = 1; s <= 6; ++s) {
+#pragma unroll
+      for (int c = 0; c < FW_N_ODE; ++c) ys[c] = 0;
+      for (int j = 0; j < s; ++j) {
+        const T a = (T)c_dpA[s][j];
+#pragma unroll
+        for (int c = 0; c < FW_N_ODE; ++c) ys[c] += a * K.at(j, c);
+      }
+#pragma unroll
+      for (int c = 0; c < FW_N_ODE; ++c) ys[c] = y[c] + ys[c] * h;
+      fw_rhs<T>(P, in, ys, f, fail);
+      if (fail) return FW_STATUS_FINISHED;
+      if (s < 6) {
+#pragma unroll
+        for (int c = 0; c < FW_N_ODE; ++c) K.at(s, c) = f[c];
+      }
+    }
+    // ys == y_new, f == f_new.  error = (K^T . E) * h ; scale = atol + max(|y|,|y_new|)*rtol
+    T se = 0;
+#pragma unroll
+    for (int c = 0; c < FW_N_ODE; ++c) {
+      T e = (T)c_dpE[6] * f[c];
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j != 1) e += (T)c_dpE[j] * K.at(j, c);
+      e *= h;
+      const T ay = fabs(y[c]), an = fabs(ys[c]);
+      const T sc = atol + (ay > an ? ay : an) * rtol;
+      const T q = e / sc;
+      se += q * q;
+    }
+    const T err = Mt::sqrt_(se) / sqrtn;
+    if (err < (T)1) {
+      T factor;
+      if (err == (T)0) factor = (T)10;
+      else {
+        factor = (T)0.9 * Mt::pow_(err, (T)-0.2);
+        factor = factor < (T)10 ? factor : (T)10;
+      }
+      if (rejected) factor = factor < (T)1 ? factor : (T)1;
+      h_abs *= factor;
+      // accept
+      t = t_new;
+#pragma unroll
+      for (int c = 0; c < FW_N_ODE; ++c) {
+        y[c] = ys[c];
+        K.at(0, c) = f[c];
+      }
+      ++accepted;
+      newstep = true;
+      if (t - tb >= 0) status = FW_STATUS_FINISHED;
+    } else {
+      // NaN error norms land here too: Python's max(0.2, nan) == 0.2
+      T fac = (T)0.9 * Mt::pow_(err, (T)-0.2);
+      fac = fac > (T)0.2 ? fac : (T)0.2;
+      h_abs *= fac;
+      rejected = true;
+    }
+  }
+  return status;
+}

@@ -1,0 +1,499 @@
+// Env-side work of FixedWingAircraft.step / reset, one thread per env over coalesced SoA rows.
+//
+// What it replaces: fixed_wing.py:338-437 (step orchestration), :287-336 (reset), :461-521
+// (sample_target), :674-774 (get_reward), :776-846 (get_observation), :890-931 (_get_error, _get_goal_status),
+// :933-991 (_get_next_target) and PyFly.reset (oracle/pyfly_restated.py: PyFly.reset) for the auto-reset.
+#pragma once
+#include <math_constants.h>
+#include "layout.h"
+#include "philox.cuh"
+#include "dynamics.cuh"
+
+#define FW_TWO_PI 6.283185307179586
+
+struct FwEnvCtx {
+  double* __restrict__ d;
+  int32_t* __restrict__ i;
+  int64_t stride;
+  int64_t env;
+  __device__ __forceinline__ double& D(int row) const { return d[(int64_t)row * stride + env]; }
+  __device__ __forceinline__ int32_t& I(int row) const { return i[(int64_t)row * stride + env]; }
+};
+
+struct FwEnvRng {
+  FwRng g;
+  uint32_t n_u, n_n;        // uniform / normal draws consumed in this tick
+  double z_cached;
+  __device__ __forceinline__ double uniform(double lo, double hi) { return fw_uniform(g, FW_RS_ENV_U, n_u++, lo, hi); }
+  __device__ __forceinline__ double uniform01() { return fw_uniform01(g, FW_RS_ENV_U, n_u++); }
+  __device__ __forceinline__ double normal(double mean, double std) {
+    double z;
+    if (n_n & 1u) z = z_cached;
+    else { double z1; fw_normal2(g, FW_RS_ENV_N, n_n >> 1, z, z1); z_cached = z1; }
+    ++n_n;
+    return mean + std * z;
+  }
+};
+
+// current value of a PyFly state variable (`simulator.state[name].value`)
+__device__ __forceinline__ double fw_sv_value(const FwEnvCtx& c, int sv) {
+  switch (sv) {
+    case FW_SV_ROLL: return c.D(D_ROLL);
+    case FW_SV_PITCH: return c.D(D_PITCH);
+    case FW_SV_YAW: return c.D(D_YAW);
+    case FW_SV_OMEGA_P: return c.D(D_OMEGA + 0);
+    case FW_SV_OMEGA_Q: return c.D(D_OMEGA + 1);
+    case FW_SV_OMEGA_R: return c.D(D_OMEGA + 2);
+    case FW_SV_POS_N: return c.D(D_POS + 0);
+    case FW_SV_POS_E: return c.D(D_POS + 1);
+    case FW_SV_POS_D: return c.D(D_POS + 2);
+    case FW_SV_VEL_U: return c.D(D_VEL + 0);
+    case FW_SV_VEL_V: return c.D(D_VEL + 1);
+    case FW_SV_VEL_W: return c.D(D_VEL + 2);
+    case FW_SV_VA: return c.D(D_VA);
+    case FW_SV_ALPHA: return c.D(D_ALPHA);
+    case FW_SV_BETA: return c.D(D_BETA);
+    case FW_SV_ELEVATOR: return c.D(D_ELEV);
+    case FW_SV_AILERON: return c.D(D_AIL);
+    case FW_SV_RUDDER: return 0.0;
+    case FW_SV_THROTTLE: return c.D(D_ACT + 2);
+    case FW_SV_ELEVON_L: return c.D(D_ACT + 0);
+    case FW_SV_ELEVON_R: return c.D(D_ACT + 1);
+  }
+  return 0.0;
+}
+
+// python float floor-mod x % m for m > 0
+__device__ __forceinline__ double fw_pymod(double x, double m) {
+  double r = fmod(x, m);
+  if (r != 0.0 && r < 0.0) r += m;
+  return r;
+}
+
+// fixed_wing.py:890-914
+__device__ __forceinline__ double fw_error(const fw_target_t& t, double target, double value) {
+  if (t.wrap) return fw_pymod(value - target + CUDART_PI, FW_TWO_PI) - CUDART_PI;
+  return target - value;
+}
+
+__device__ __forceinline__ int fw_tcls(uint32_t flags, int k) { return (flags >> (FWF_TCLS_SHIFT + 2 * k)) & 3u; }
+
+// fixed_wing.py:916-931 : bit k = |err_k| <= bound_k for targets with a bound; bit 31 = all()
+__device__ __forceinline__ uint32_t fw_goal_status(const fw_env_t& E, const FwEnvCtx& c) {
+  uint32_t bits = 0;
+  bool all = true;
+  for (int k = 0; k < E.n_targets; ++k) {
+    if (!E.tgt[k].has_bound) continue;
+    const double err = fw_error(E.tgt[k], c.D(D_TARGET + k), fw_sv_value(c, E.tgt[k].sv));
+    const bool ok = fabs(err) <= E.tgt[k].bound;
+    if (ok) bits |= 1u << k;
+    all = all && ok;
+  }
+  if (all) bits |= 1u << 31;
+  return bits;
+}
+
+// fixed_wing.py:461-521
+__device__ __forceinline__ void fw_sample_target(const fw_env_t& E, const FwEnvCtx& c, FwEnvRng& rng,
+                                                 uint32_t& flags, int steps_count) {
+  c.I(I_STEPS_TGT) = 0;
+  for (int k = 0; k < E.n_targets; ++k) {
+    const fw_target_t& t = E.tgt[k];
+    double low = t.low, high = t.high;
+    if (t.has_delta) {
+      const double v = fw_sv_value(c, t.sv);
+      low = fmax(low, v - t.delta);
+      high = fmax(fmin(high, v + t.delta), low);
+    }
+    const double initial = rng.uniform(low, high);
+    flags = (flags & ~(3u << (FWF_TCLS_SHIFT + 2 * k))) | ((uint32_t)t.cls << (FWF_TCLS_SHIFT + 2 * k));
+    if (t.cls == 1) {   // linear
+      double slope = rng.uniform(t.slope_low, t.slope_high);
+      if (rng.uniform01() < 0.5) slope *= -1.0;
+      if (t.to_radians) slope = slope * (CUDART_PI / 180.0);
+      c.D(D_TSLOPE + k) = slope;
+    } else if (t.cls == 2) {   // sinusoidal
+      double amp = rng.uniform(t.amp_low, t.amp_high);
+      if (t.to_radians) amp = amp * (CUDART_PI / 180.0);
+      const double period = rng.uniform(t.period_low, t.period_high);
+      const double phase = rng.uniform(0.0, FW_TWO_PI) / (FW_TWO_PI / period);
+      c.D(D_TAMP + k) = amp;
+      c.D(D_TPERIOD + k) = period;
+      c.D(D_TPHASE + k) = phase;
+      c.D(D_TBIAS + k) = initial - amp * sin(FW_TWO_PI / period * ((double)steps_count + phase));
+    }
+    c.D(D_TARGET + k) = initial;
+  }
+}
+
+// fixed_wing.py:933-991 (all next targets are computed from the CURRENT targets, then assigned)
+__device__ __forceinline__ void fw_next_targets(const fw_env_t& E, const fw_sim_t& P, const FwEnvCtx& c,
+                                                uint32_t flags, int steps_count, int steps_tgt, double (&out)[FW_MAX_TARGETS]) {
+  int pitch_k = -1;
+  for (int k = 0; k < E.n_targets; ++k)
+    if (E.tgt[k].sv == FW_SV_PITCH) pitch_k = k;
+  for (int k = 0; k < E.n_targets; ++k) {
+    const fw_target_t& t = E.tgt[k];
+    const int cls = fw_tcls(flags, k);
+    const double cur = c.D(D_TARGET + k);
+    double res = cur;
+    if (cls == 3 && pitch_k >= 0) {   // compensate (Va)
+      const int pc = fw_tcls(flags, pitch_k);
+      const double pitch_cur = c.D(D_TARGET + pitch_k);
+      const double pitch_tar = (pc == 2) ? c.D(D_TBIAS + pitch_k) : pitch_cur;
+      if (pitch_tar <= -2.5 * (CUDART_PI / 180.0)) {
+        const double va_end = 28.434 - 40.0841 * pitch_tar;
+        double slope = 0.0;
+        if (cur <= va_end) slope = 7.0 * fmax(0.0, cur < va_end * 0.95 ? 1.0 : 1.0 - cur / (va_end * 1.5));
+        res = cur + (slope * (-pitch_cur) - 0.25) * P.dt;
+      } else if (pitch_tar >= 5.0 * (CUDART_PI / 180.0)) {
+        const double va_end = 26.27 - 41.2529 * pitch_tar;
+        if (cur > va_end) res = (steps_tgt < 750) ? cur + (va_end - cur) * 1.0 / 150.0 : va_end;
+      }
+    } else if (cls == 1) {
+      res = cur + c.D(D_TSLOPE + k) * P.dt;
+    } else if (cls == 2) {
+      res = c.D(D_TAMP + k) * sin(FW_TWO_PI / c.D(D_TPERIOD + k) * ((double)steps_count + c.D(D_TPHASE + k))) + c.D(D_TBIAS + k);
+    }
+    if (t.wrap && fabs(res) > CUDART_PI) {
+      const double s = res > 0 ? 1.0 : -1.0;
+      res = s * (fmod(fabs(res), CUDART_PI) - CUDART_PI);
+    }
+    out[k] = res;
+  }
+}
+
+// ---- history rings.  Entry e (0 = the reset entry) lives in slot e % depth. -------------------------------------
+__device__ __forceinline__ double fw_ring_get(const FwEnvCtx& c, int row0, int depth, int ncol, int col, int e) {
+  return c.D(row0 + (e % depth) * ncol + col);
+}
+__device__ __forceinline__ void fw_ring_put(const FwEnvCtx& c, int row0, int depth, int ncol, int col, int e, double v) {
+  c.D(row0 + (e % depth) * ncol + col) = v;
+}
+
+// fixed_wing.py:776-846.  hist_len = len(history["error"][k]) = len(PyFly Variable.history); steps_count as in the
+// reference; `stale` selects the reset-time behaviour where the integrator reads the previous episode's history
+// (fixed_wing.py:317 runs before :318).
+template <typename OutF>
+__device__ __forceinline__ void fw_observation(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
+                                               const FwEnvCtx& c, FwEnvRng& rng, uint32_t flags, int steps_count,
+                                               int hist_len, bool at_reset, OutF out) {
+  const int nv = E.obs_nvar, len = E.obs_len, step = E.obs_step;
+  const int W = E.integration_window;
+  for (int row = 0; row < len; ++row) {
+    int i = 1 + row * step;
+    double init_noise = 0.0;
+    bool has_init_noise = false;
+    if (i > steps_count) {
+      i = steps_count + 1;
+      if (len > 1) { init_noise = rng.uniform(-1.0, 1.0) * P.dt; has_init_noise = true; }
+    }
+    // index into PyFly / env histories; clamp for the failure step, where nothing was appended
+    int ih = i < hist_len ? i : hist_len;
+    for (int v = 0; v < nv; ++v) {
+      const fw_obs_var_t& ov = E.obs[v];
+      double val;
+      if (ov.type == 0) {
+        if (L.sv_depth <= 1 || ih == 1) val = fw_sv_value(c, ov.ref);
+        else val = fw_ring_get(c, L.sv_row, L.sv_depth, L.n_sv_obs, L.sv_slot[v], hist_len - ih);
+      } else if (ov.type == 1) {
+        const int k = ov.ref;
+        if (ov.value_kind == 0) {
+          if (i == 1) val = fw_error(E.tgt[k], c.D(D_TARGET + k), fw_sv_value(c, E.tgt[k].sv));
+          else val = fw_ring_get(c, L.err_row, L.err_depth, E.n_targets, k, hist_len - ih);
+        } else if (ov.value_kind == 1) {
+          if (i == 1) val = c.D(D_TARGET + k);
+          else val = fw_ring_get(c, L.tgt_row, L.tgt_depth, E.n_targets, k, hist_len - ih);
+        } else {
+          if (at_reset && !(flags & FWF_HIST_VALID)) {
+            val = fw_error(E.tgt[k], c.D(D_TARGET + k), fw_sv_value(c, E.tgt[k].sv)) * (double)W;
+          } else {
+            // np.sum(history["error"][k][-W-i:-i]) : entries [max(0, n-W-i), n-i)
+            const int n = hist_len;
+            int hi = n - i, lo = n - W - i;
+            if (lo < 0) lo = 0;
+            double s = 0.0;
+            for (int e = lo; e < hi; ++e) s += fw_ring_get(c, L.err_row, L.err_depth, E.n_targets, k, e);
+            val = s;
+            if (steps_count - i < W) val += (double)(W - (steps_count - i)) * c.D(D_ERR0 + k);
+          }
+        }
+      } else {
+        const int a = ov.ref;
+        if (steps_count - i < 0) {
+          const int sv = a == 0 ? FW_SV_ELEVATOR : (a == 1 ? FW_SV_AILERON : FW_SV_THROTTLE);
+          val = fw_sv_value(c, sv);
+          if (P.scale_actions) {
+            // linear_action_scaling(direction="backward") applied to a vector that is zero except at a
+            const double omin = P.act_to_low[a], omax = P.act_to_high[a];
+            val = (P.scale_high - P.scale_low) * (val - omin) / (omax - omin) + P.scale_low;
+          }
+        } else {
+          // sum |diff| over the `window` entries of the action (or command) history ending i-1 steps ago,
+          // accumulated in float32 (np.sum(..., dtype=np.float32))
+          const int n = steps_count;            // len(history["action"])
+          const int hi = n - (i - 1);           // exclusive
+          int lo = n - ov.window - i + 1;
+          if (lo < 0) lo = 0;
+          const int row0 = P.scale_actions ? L.act_row : L.cmd_row;
+          const int depth = P.scale_actions ? L.act_depth : L.cmd_depth;
+          float acc = 0.0f;
+          for (int e = lo + 1; e < hi; ++e) {
+            const double d1 = fw_ring_get(c, row0, depth, FW_N_ACT, a, e);
+            const double d0 = fw_ring_get(c, row0, depth, FW_N_ACT, a, e - 1);
+            acc += (float)fabs(d1 - d0);
+          }
+          val = (double)acc;
+        }
+      }
+      if (has_init_noise) val += init_noise;
+      if (E.obs_norm && ov.norm) { val -= ov.mean; val /= ov.var; }
+      if (E.obs_noise) val += rng.normal(E.obs_noise_mean, E.obs_noise_std);
+      out(row * nv + v, val);
+    }
+  }
+}
+
+// fixed_wing.py:674-774.  a = raw action of this step; steps_count already incremented; error history not yet
+// extended with this step's entry (hist_len entries).
+__device__ __forceinline__ double fw_reward(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
+                                            uint32_t& flags, const double (&a)[FW_N_ACT], bool success,
+                                            int steps_count, int hist_len, uint32_t goal_bits) {
+  double val_t[FW_N_FCLASS] = {0, 0, 0}, shp_t[FW_N_FCLASS] = {0, 0, 0};
+  for (int f = 0; f < E.n_factors; ++f) {
+    const fw_factor_t& F = E.fac[f];
+    double val = 0.0;
+    if (F.cls == 0) {
+      if (F.type == 0) {
+        val = fabs(a[0]) + fabs(a[1]) + fabs(a[2]);
+      } else if (F.type == 1) {
+        if (steps_count > 1) {
+          int lo = steps_count - F.window;
+          if (lo < 0) lo = 0;
+          for (int e = lo + 1; e < steps_count; ++e)
+            for (int j = 0; j < FW_N_ACT; ++j)
+              val += fabs(fw_ring_get(c, L.act_row, L.act_depth, FW_N_ACT, j, e) -
+                          fw_ring_get(c, L.act_row, L.act_depth, FW_N_ACT, j, e - 1));
+        }
+      } else {
+        double hi = 0.0, lo = 0.0;
+        for (int j = 0; j < FW_N_ACT; ++j) {
+          if (a[j] > E.bounds_max[j]) hi += fabs(a[j] - E.bounds_max[j]);
+          if (a[j] < E.bounds_min[j]) lo += fabs(a[j] - E.bounds_min[j]);
+        }
+        val = hi + lo;
+      }
+    } else if (F.cls == 1) {
+      if (F.type == 0) {
+        val = fw_sv_value(c, F.ref);
+      } else if (F.type == 1) {
+        val = fw_error(E.tgt[F.ref], c.D(D_TARGET + F.ref), fw_sv_value(c, E.tgt[F.ref].sv));
+      } else {
+        const int W = E.integration_window;
+        int lo = hist_len - W;
+        if (lo < 0) lo = 0;
+        if (W == 0) lo = 0;   // python: list[-0:] is the whole list
+        for (int e = lo; e < hist_len; ++e) val += fw_ring_get(c, L.err_row, L.err_depth, E.n_targets, F.ref, e);
+        if (steps_count < W) val += (double)(W - steps_count) * c.D(D_ERR0 + F.ref);
+      }
+    } else if (F.cls == 2) {
+      if (success) val = F.value_timesteps ? (double)(E.steps_max - steps_count) : F.value;
+    } else if (F.cls == 3) {
+      val = F.value;
+    } else {
+      if (F.type == 0) {
+        for (int k = 0; k < E.n_targets; ++k)
+          if (E.tgt[k].has_bound && ((goal_bits >> k) & 1u)) val += F.value / (double)E.n_targets;
+      } else {
+        if (goal_bits >> 31) val += F.value;
+      }
+    }
+    if (F.fclass == 0) {
+      val = fabs(val) / F.scaling;
+      if (val < 0.0) val = 0.0;
+      if (F.has_max && val > F.max) val = F.max;
+    } else {
+      val = val * val / F.scaling;
+    }
+    if (F.shaping) shp_t[F.fclass] += val * F.sign;
+    else val_t[F.fclass] += val * F.sign;
+  }
+  double reward = 0.0;
+  for (int ti = 0; ti < E.n_terms; ++ti) {
+    const int fc = E.term_fclass[ti];
+    const bool has_prev = (flags >> (FWF_PREVSHAPE_SHIFT + fc)) & 1u;
+    const double prev = c.D(D_PREVSHAPE + fc);
+    double val;
+    if (fc == 1) {
+      if (E.potential) val = has_prev ? -1.0 + exp(val_t[fc] + (shp_t[fc] - prev)) : -1.0 + exp(val_t[fc]);
+      else val = -1.0 + exp(val_t[fc] + shp_t[fc]);
+    } else {
+      val = val_t[fc];
+      if (E.potential) { if (has_prev) val += shp_t[fc] - prev; }
+      else val += shp_t[fc];
+    }
+    c.D(D_PREVSHAPE + fc) = shp_t[fc];
+    flags |= 1u << (FWF_PREVSHAPE_SHIFT + fc);
+    reward += E.term_weight[ti] * val;
+  }
+  return reward;
+}
+
+// Euler-angle rotation body<-vehicle times a vector (PyFly._rot_b_v with 3 angles)
+__device__ __forceinline__ void fw_rot_euler(double phi, double th, double psi, const double (&w)[3], double (&o)[3]) {
+  double sphi, cphi, sth, cth, spsi, cpsi;
+  sincos(phi, &sphi, &cphi); sincos(th, &sth, &cth); sincos(psi, &spsi, &cpsi);
+  o[0] = cth * cpsi * w[0] + cth * spsi * w[1] - sth * w[2];
+  o[1] = (sphi * sth * cpsi - cphi * spsi) * w[0] + (sphi * sth * spsi + cphi * cpsi) * w[1] + sphi * cth * w[2];
+  o[2] = (cphi * sth * cpsi + sphi * spsi) * w[0] + (cphi * sth * spsi - sphi * cpsi) * w[1] + cphi * cth * w[2];
+}
+
+// Dryden white noise for sim step s of the episode keyed by eptick (4 streams, already scaled)
+__device__ __forceinline__ void fw_turb_noise(const fw_sim_t& P, uint32_t k0, uint32_t k1, uint32_t genv, uint32_t eptick,
+                                              int s, double (&u)[4]) {
+  FwRng g{k0, k1, genv, eptick};
+  fw_normal2(g, FW_RS_TURB, 2u * (uint32_t)s, u[0], u[1]);
+  fw_normal2(g, FW_RS_TURB, 2u * (uint32_t)s + 1u, u[2], u[3]);
+  for (int j = 0; j < 4; ++j) u[j] *= P.turb_noise_scale;
+}
+
+// advance the six shaping filters by one sample (scipy lsim recurrence) and refresh the gust rows
+__device__ __forceinline__ void fw_turb_advance(const fw_sim_t& P, const FwEnvCtx& c, const double (&unew)[4]) {
+  for (int f = 0; f < FW_N_FILT; ++f) {
+    const fw_filter_t& F = P.filt[f];
+    const double up = c.D(D_TU + F.stream), un = unew[F.stream];
+    double x[FW_FILT_MAXN], xn[FW_FILT_MAXN];
+    for (int a = 0; a < F.n; ++a) x[a] = c.D(D_TX + 3 * f + a);
+    double yv = F.D * un;
+    for (int b = 0; b < F.n; ++b) {
+      double s = up * F.Bd0[b] + un * F.Bd1[b];
+      for (int a = 0; a < F.n; ++a) s += x[a] * F.Ad[a * FW_FILT_MAXN + b];
+      xn[b] = s;
+      yv += s * F.C[b];
+    }
+    for (int b = 0; b < F.n; ++b) c.D(D_TX + 3 * f + b) = xn[b];
+    c.D(D_GUST + f) = yv;
+  }
+  for (int j = 0; j < 4; ++j) c.D(D_TU + j) = unew[j];
+}
+
+// PyFly.reset + FixedWingAircraft.reset for one env.  init_state rows: FW_N_SV + 3 (wind n,e,d); NaN = sample.
+template <typename OutF>
+__device__ __forceinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
+                                             uint32_t k0, uint32_t k1, uint32_t genv, const double* __restrict__ init_state,
+                                             const double* __restrict__ init_target, int64_t in_stride, OutF out) {
+  const uint32_t tick = (uint32_t)c.I(I_TICK);
+  c.I(I_TICK) = (int32_t)(tick + 1u);
+  c.I(I_EPTICK) = (int32_t)tick;
+  FwRng g{k0, k1, genv, tick};
+  int dummy = 0;
+  auto given = [&](int r, double& v) -> bool {
+    if (!init_state) return false;
+    v = init_state[(int64_t)r * in_stride + c.env];
+    return !isnan(v);
+  };
+  auto init_var = [&](int sv) -> double {
+    double v;
+    if (given(sv, v)) return fw_cond<double>(P.var[sv], sv, v, dummy);
+    return fw_uniform(g, FW_RS_INIT, (uint32_t)sv, P.var[sv].init_min, P.var[sv].init_max);
+  };
+  // ---- PyFly.reset ----
+  const double roll = init_var(FW_SV_ROLL), pitch = init_var(FW_SV_PITCH), yaw = init_var(FW_SV_YAW);
+  c.D(D_ROLL) = roll; c.D(D_PITCH) = pitch; c.D(D_YAW) = yaw;
+  for (int j = 0; j < 3; ++j) c.D(D_OMEGA + j) = init_var(FW_SV_OMEGA_P + j);
+  for (int j = 0; j < 3; ++j) c.D(D_POS + j) = init_var(FW_SV_POS_N + j);
+  double vel[3];
+  for (int j = 0; j < 3; ++j) { vel[j] = init_var(FW_SV_VEL_U + j); c.D(D_VEL + j) = vel[j]; }
+  const int act_sv[3] = {FW_SV_ELEVON_L, FW_SV_ELEVON_R, FW_SV_THROTTLE};
+  double act[3];
+  for (int j = 0; j < 3; ++j) { act[j] = init_var(act_sv[j]); c.D(D_ACT + j) = act[j]; c.D(D_ACTDOT + j) = 0.0; }
+  c.D(D_ELEV) = fw_cond<double>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (act[1] + act[0]) / 2, dummy);
+  c.D(D_AIL) = fw_cond<double>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-act[1] + act[0]) / 2, dummy);
+  for (int j = 0; j < 3; ++j) c.D(D_CMD + j) = 0.0;
+  double wind[3] = {0, 0, 0};
+  {
+    double wv[3];
+    const bool have = given(FW_N_SV + 0, wv[0]) & given(FW_N_SV + 1, wv[1]) & given(FW_N_SV + 2, wv[2]);
+    if (have) { wind[0] = wv[0]; wind[1] = wv[1]; wind[2] = wv[2]; }
+    else {
+      const double mag = fw_uniform(g, FW_RS_WIND, 0, P.wind_mag_min, P.wind_mag_max);
+      wind[0] = fw_uniform(g, FW_RS_WIND, 1, -mag, mag);
+      const double we_max = sqrt(mag * mag - wind[0] * wind[0]);
+      wind[1] = fw_uniform(g, FW_RS_WIND, 2, -we_max, we_max);
+      wind[2] = sqrt(mag * mag - wind[0] * wind[0] - wind[1] * wind[1]);
+    }
+  }
+  for (int j = 0; j < 3; ++j) c.D(D_WIND + j) = wind[j];
+  // Dryden: x = 0, first sample drawn, gust = D*u0
+  for (int j = 0; j < 18; ++j) c.D(D_TX + j) = 0.0;
+  double gl[3] = {0, 0, 0};
+  if (P.turbulence) {
+    double u0[4];
+    fw_turb_noise(P, k0, k1, genv, tick, 0, u0);
+    for (int j = 0; j < 4; ++j) c.D(D_TU + j) = u0[j];
+    for (int f = 0; f < FW_N_FILT; ++f) c.D(D_GUST + f) = P.filt[f].D * u0[P.filt[f].stream];
+    for (int j = 0; j < 3; ++j) gl[j] = c.D(D_GUST + j);
+  } else {
+    for (int j = 0; j < 4; ++j) c.D(D_TU + j) = 0.0;
+    for (int j = 0; j < 6; ++j) c.D(D_GUST + j) = 0.0;
+  }
+  // Va, alpha, beta from the Euler-angle rotation of the steady wind + gust
+  double wb[3];
+  fw_rot_euler(roll, pitch, yaw, wind, wb);
+  const double ur = vel[0] - (wb[0] + gl[0]), vr = vel[1] - (wb[1] + gl[1]), wr = vel[2] - (wb[2] + gl[2]);
+  const double Va = sqrt(ur * ur + vr * vr + wr * wr);
+  c.D(D_VA) = fw_cond<double>(P.var[FW_SV_VA], FW_SV_VA, Va, dummy);
+  c.D(D_ALPHA) = fw_cond<double>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, atan2(wr, ur), dummy);
+  c.D(D_BETA) = fw_cond<double>(P.var[FW_SV_BETA], FW_SV_BETA, asin(vr / Va), dummy);
+  {
+    double sphi, cphi, sth, cth, spsi, cpsi;
+    sincos(roll / 2, &sphi, &cphi); sincos(pitch / 2, &sth, &cth); sincos(yaw / 2, &spsi, &cpsi);
+    c.D(D_Q + 0) = cpsi * cth * cphi + spsi * sth * sphi;
+    c.D(D_Q + 1) = cpsi * cth * sphi - spsi * sth * cphi;
+    c.D(D_Q + 2) = cpsi * sth * cphi + spsi * cth * sphi;
+    c.D(D_Q + 3) = spsi * cth * cphi - cpsi * sth * sphi;
+  }
+  // ---- FixedWingAircraft.reset ----
+  uint32_t flags = (uint32_t)c.I(I_FLAGS);
+  const int old_hist_len = c.I(I_HISTLEN);
+  c.I(I_STEPS) = 0;
+  FwEnvRng rng{g, 0u, 0u, 0.0};
+  fw_sample_target(E, c, rng, flags, 0);
+  if (init_target) {
+    for (int k = 0; k < E.n_targets; ++k) {
+      const double v = init_target[(int64_t)k * in_stride + c.env];
+      if (isnan(v)) continue;
+      const int cls = fw_tcls(flags, k);
+      if (cls != 0 && cls != 3) flags &= ~(3u << (FWF_TCLS_SHIFT + 2 * k));
+      c.D(D_TARGET + k) = v;
+    }
+  }
+  // observation BEFORE the histories are rebuilt (fixed_wing.py:317 vs :318): the PyFly state histories are new
+  // (hist_len 1) but the integrator still reads the previous episode's error history.
+  fw_observation(E, P, L, c, rng, flags, 0, (flags & FWF_HIST_VALID) ? old_hist_len : 1, true, out);
+  // rebuild histories
+  c.I(I_HISTLEN) = 1;
+  for (int k = 0; k < E.n_targets; ++k) {
+    const double err = fw_error(E.tgt[k], c.D(D_TARGET + k), fw_sv_value(c, E.tgt[k].sv));
+    c.D(D_ERR0 + k) = err;
+    if (L.err_depth > 0) fw_ring_put(c, L.err_row, L.err_depth, E.n_targets, k, 0, err);
+    if (L.tgt_depth > 0) fw_ring_put(c, L.tgt_row, L.tgt_depth, E.n_targets, k, 0, c.D(D_TARGET + k));
+  }
+  if (L.sv_depth > 1)
+    for (int v = 0; v < E.obs_nvar; ++v)
+      if (E.obs[v].type == 0) fw_ring_put(c, L.sv_row, L.sv_depth, L.n_sv_obs, L.sv_slot[v], 0, fw_sv_value(c, E.obs[v].ref));
+  if (E.streak_req > 0) {
+    for (int wd = 0; wd < L.goal_words; ++wd) c.I(I_GOALRING + wd) = 0;
+    const uint32_t gb = fw_goal_status(E, c);
+    const int all = (int)(gb >> 31);
+    if (all) c.I(I_GOALRING) = 1;
+    c.I(I_GOALCNT) = all;
+  }
+  flags |= FWF_HIST_VALID;
+  flags &= ~(7u << FWF_PREVSHAPE_SHIFT);
+  flags &= ~FWF_EP_SUCCESS;
+  c.I(I_FLAGS) = (int32_t)flags;
+  c.I(I_STATUS) = 0;
+  c.I(I_LASTK) = 0;
+  c.D(D_EPRET) = 0.0;
+}

@@ -1,0 +1,666 @@
+// libfwgym.so — kernels + C-ABI (include/fwgym.h).  sm_100a only.
+//
+//   fw_dyn_kernel  : one thread per aircraft; action scaling + command constraining, adaptive dopri5 integration of
+//                    the 6-DOF model over one env step (register-resident state, K stages in shared memory), state
+//                    commit, Dryden filter advance.  FP64-pipe bound.
+//   fw_env_kernel  : one thread per env; goal bits / streak, reward, target resample + advance, history rings,
+//                    observation (+noise), done, metric sums, auto-reset.  HBM bound.
+//   fw_reset_kernel: explicit (masked) reset with optional injected initial states / targets.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include "../../include/fwgym.h"
+#include "layout.h"
+#include "philox.cuh"
+#include "dynamics.cuh"
+#include "env.cuh"
+
+#define FW_DYN_BLOCK 64
+#define FW_ENV_BLOCK 128
+
+enum { CTR_ENV_STEPS = 0, CTR_ATTEMPTS, CTR_ACCEPTED, CTR_WARP_MAX, CTR_WARP_STEPS, CTR_FAILURES, CTR_RESETS, CTR_N };
+enum { MS_EPISODES = 0, MS_SUCCESS, MS_RETURN, MS_LENGTH, MS_FAILURES, MS_STEPS_TERM, MS_SUCCESS_TERM, MS_GOAL_STEPS };
+
+struct fw_handle_s {
+  fw_config_t cfg;
+  FwLayout L;
+  int device;
+  int64_t n, offset;
+  uint64_t seed;
+  double* d;
+  int32_t* i;
+  unsigned long long* ctr;   // CTR_N
+  double* msum;              // FW_N_METRIC_SUMS
+  cudaStream_t last_stream;
+};
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+#define CK(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess) return fail(FW_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ dynamics kernel
+struct FwDynArgs {
+  double* d;
+  int32_t* i;
+  int64_t stride, n;
+  const void* actions;
+  int actions_f64;
+  uint32_t k0, k1;
+  uint32_t env_offset;
+  unsigned long long* ctr;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(FW_DYN_BLOCK)
+fw_dyn_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwKStore<T, FW_DYN_BLOCK> K{reinterpret_cast<T*>(smem_raw)};
+  const int64_t env = (int64_t)blockIdx.x * FW_DYN_BLOCK + threadIdx.x;
+  const bool valid = env < a.n;
+  int attempts = 0, accepted = 0, failv = 0;
+  if (valid) {
+    FwEnvCtx c{a.d, a.i, a.stride, env};
+    // ---- action -> actuator commands (fixed_wing.py:349-354,439-459; Actuation.set_and_constrain_commands) ----
+    double act[3];
+    if (a.actions_f64) {
+      const double* p = reinterpret_cast<const double*>(a.actions) + env * 3;
+      act[0] = p[0]; act[1] = p[1]; act[2] = p[2];
+    } else {
+      const float* p = reinterpret_cast<const float*>(a.actions) + env * 3;
+      act[0] = p[0]; act[1] = p[1]; act[2] = p[2];
+    }
+    if (P.scale_actions) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double x = act[j];
+        if (P.has_scale_low) x = fmax(x, P.scale_low);   // np.clip propagates NaN; so do these for NaN in x? (fmax drops it)
+        if (P.has_scale_high) x = fmin(x, P.scale_high);
+        act[j] = (P.act_to_high[j] - P.act_to_low[j]) * (x - P.scale_low) / (P.scale_high - P.scale_low) + P.act_to_low[j];
+      }
+    }
+    int dummy = 0;
+    const double er_c = -1.0 * act[1] + act[0], el_c = act[1] + act[0];
+    const double cmd_el = fw_cond<double>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, el_c, dummy);
+    const double cmd_er = fw_cond<double>(P.var[FW_SV_ELEVON_R], FW_SV_ELEVON_R, er_c, dummy);
+    const double cmd_th = fw_cond<double>(P.var[FW_SV_THROTTLE], FW_SV_THROTTLE, act[2], dummy);
+    c.D(D_CMD + 0) = fw_cond<double>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (cmd_er + cmd_el) / 2, dummy);
+    c.D(D_CMD + 1) = fw_cond<double>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-cmd_er + cmd_el) / 2, dummy);
+    c.D(D_CMD + 2) = cmd_th;
+
+    FwStepIn<T> in;
+    in.cmd[0] = (T)cmd_el; in.cmd[1] = (T)cmd_er; in.cmd[2] = (T)cmd_th;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      in.gl[j] = P.turbulence ? (T)c.D(D_GUST + j) : (T)0;
+      in.ga[j] = P.turbulence ? (T)c.D(D_GUST + 3 + j) : (T)0;
+      in.wind[j] = P.wind_enabled ? (T)c.D(D_WIND + j) : (T)0;
+    }
+    T y[FW_N_ODE];
+#pragma unroll
+    for (int j = 0; j < FW_N_ODE; ++j) y[j] = (T)c.D(j);
+
+    fw_integrate_step<T, FW_DYN_BLOCK>(P, in, y, K, attempts, accepted, failv);
+
+    // ---- PyFly._set_states_from_ode_solution(save=True) + airspeed factors ----
+    double yd[FW_N_ODE];
+#pragma unroll
+    for (int j = 0; j < FW_N_ODE; ++j) yd[j] = (double)y[j];
+    double roll = 0, pitch = 0, yaw = 0, Va = 0, alpha = 0, beta = 0, elev = 0, ail = 0;
+    if (!failv) {
+      const double qn = sqrt(yd[0] * yd[0] + yd[1] * yd[1] + yd[2] * yd[2] + yd[3] * yd[3]);
+      const double e0 = yd[0] / qn, e1 = yd[1] / qn, e2 = yd[2] / qn, e3 = yd[3] / qn;
+      yd[0] = e0; yd[1] = e1; yd[2] = e2; yd[3] = e3;
+      roll = atan2(2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
+      pitch = asin(2 * (e0 * e2 - e1 * e3));
+      yaw = atan2(2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
+      roll = fw_cond<double>(P.var[FW_SV_ROLL], FW_SV_ROLL, roll, failv);
+      pitch = fw_cond<double>(P.var[FW_SV_PITCH], FW_SV_PITCH, pitch, failv);
+      yaw = fw_cond<double>(P.var[FW_SV_YAW], FW_SV_YAW, yaw, failv);
+#pragma unroll
+      for (int j = 0; j < 9; ++j) yd[4 + j] = fw_cond<double>(P.var[FW_SV_OMEGA_P + j], FW_SV_OMEGA_P + j, yd[4 + j], failv);
+      yd[13] = fw_cond<double>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, yd[13], failv);
+      yd[14] = fw_cond<double>(P.var[FW_SV_ELEVON_R], FW_SV_ELEVON_R, yd[14], failv);
+      yd[15] = fw_cond<double>(P.var[FW_SV_THROTTLE], FW_SV_THROTTLE, yd[15], failv);
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (P.act_has_dot_max[j]) yd[16 + j] = fmin(fmax(yd[16 + j], -P.act_dot_max[j]), P.act_dot_max[j]);
+      ail = fw_cond<double>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-yd[14] + yd[13]) / 2, failv);
+      elev = fw_cond<double>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (yd[14] + yd[13]) / 2, failv);
+      double wb[3] = {0, 0, 0};
+      if (P.wind_enabled) {
+        const double wv[3] = {c.D(D_WIND + 0), c.D(D_WIND + 1), c.D(D_WIND + 2)};
+        fw_rot_euler(roll, pitch, yaw, wv, wb);
+      }
+      double gl[3] = {0, 0, 0};
+      if (P.turbulence) { gl[0] = c.D(D_GUST + 0); gl[1] = c.D(D_GUST + 1); gl[2] = c.D(D_GUST + 2); }
+      const double ur = yd[10] - (wb[0] + gl[0]), vr = yd[11] - (wb[1] + gl[1]), wr = yd[12] - (wb[2] + gl[2]);
+      Va = sqrt(ur * ur + vr * vr + wr * wr);
+      alpha = atan2(wr, ur);
+      beta = asin(vr / Va);
+      Va = fw_cond<double>(P.var[FW_SV_VA], FW_SV_VA, Va, failv);
+      alpha = fw_cond<double>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, failv);
+      beta = fw_cond<double>(P.var[FW_SV_BETA], FW_SV_BETA, beta, failv);
+    }
+    if (!failv) {
+#pragma unroll
+      for (int j = 0; j < FW_N_ODE; ++j) c.D(j) = yd[j];
+      c.D(D_ROLL) = roll; c.D(D_PITCH) = pitch; c.D(D_YAW) = yaw;
+      c.D(D_VA) = Va; c.D(D_ALPHA) = alpha; c.D(D_BETA) = beta;
+      c.D(D_ELEV) = elev; c.D(D_AIL) = ail;
+      if (P.turbulence) {   // gust column for the next sim step (cur_sim_step + 1)
+        double un[4];
+        fw_turb_noise(P, a.k0, a.k1, a.env_offset + (uint32_t)env, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
+        fw_turb_advance(P, c, un);
+      }
+    }
+    c.I(I_STATUS) = failv;
+    c.I(I_LASTK) = attempts;
+  }
+  // ---- counters: one atomic per warp ----
+  const unsigned full = 0xffffffffu;
+  int sa = attempts, sc = accepted, mx = attempts, nf = failv ? 1 : 0, nv = valid ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(full, sa, o);
+    sc += __shfl_xor_sync(full, sc, o);
+    nf += __shfl_xor_sync(full, nf, o);
+    nv += __shfl_xor_sync(full, nv, o);
+    mx = max(mx, __shfl_xor_sync(full, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0 && nv) {
+    atomicAdd(a.ctr + CTR_ENV_STEPS, (unsigned long long)nv);
+    atomicAdd(a.ctr + CTR_ATTEMPTS, (unsigned long long)sa);
+    atomicAdd(a.ctr + CTR_ACCEPTED, (unsigned long long)sc);
+    atomicAdd(a.ctr + CTR_WARP_MAX, (unsigned long long)mx);
+    atomicAdd(a.ctr + CTR_WARP_STEPS, 1ull);
+    if (nf) atomicAdd(a.ctr + CTR_FAILURES, (unsigned long long)nf);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- env kernel
+struct FwEnvArgs {
+  double* d;
+  int32_t* i;
+  int64_t n;
+  const void* actions;
+  int actions_f64;
+  uint32_t k0, k1, env_offset;
+  float* obs_out;
+  float* rew_out;
+  uint8_t* done_out;
+  int32_t* term_out;
+  double* obs64_out;
+  double* rew64_out;
+  float* term_obs_out;
+  int auto_reset;
+  int obs_dim;
+  unsigned long long* ctr;
+  double* msum;
+};
+
+struct FwObsWriter {
+  float* o32;
+  double* o64;
+  int64_t base;
+  __device__ __forceinline__ void operator()(int idx, double v) const {
+    if (o32) o32[base + idx] = (float)v;
+    if (o64) o64[base + idx] = v;
+  }
+};
+
+__global__ void __launch_bounds__(FW_ENV_BLOCK)
+fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
+              const FwEnvArgs a) {
+  const int64_t env = (int64_t)blockIdx.x * FW_ENV_BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  FwEnvCtx c{a.d, a.i, L.stride, env};
+  uint32_t flags = (uint32_t)c.I(I_FLAGS);
+  int steps = c.I(I_STEPS);
+  const int status = c.I(I_STATUS);
+  double ar[3];
+  if (a.actions_f64) {
+    const double* p = reinterpret_cast<const double*>(a.actions) + env * 3;
+    ar[0] = p[0]; ar[1] = p[1]; ar[2] = p[2];
+  } else {
+    const float* p = reinterpret_cast<const float*>(a.actions) + env * 3;
+    ar[0] = p[0]; ar[1] = p[1]; ar[2] = p[2];
+  }
+  // history["action"].append(action) happens before the simulator step (fixed_wing.py:345)
+  if (L.act_depth > 0)
+    for (int j = 0; j < 3; ++j) fw_ring_put(c, L.act_row, L.act_depth, FW_N_ACT, j, steps, ar[j]);
+  if (L.cmd_depth > 0)
+    for (int j = 0; j < 3; ++j) fw_ring_put(c, L.cmd_row, L.cmd_depth, FW_N_ACT, j, steps, c.D(D_CMD + j));
+  steps += 1;
+  int steps_tgt = c.I(I_STEPS_TGT) + 1;
+  c.I(I_STEPS_TGT) = steps_tgt;
+  const uint32_t tick = (uint32_t)c.I(I_TICK);
+  c.I(I_TICK) = (int32_t)(tick + 1u);
+  const uint32_t genv = a.env_offset + (uint32_t)env;
+  FwEnvRng rng{FwRng{a.k0, a.k1, genv, tick}, 0u, 0u, 0.0};
+
+  bool done = false;
+  int term = FW_TERM_NONE;
+  if (E.steps_max > 0 && steps >= E.steps_max) { done = true; term = FW_TERM_STEPS; }
+  double reward;
+  int hist_len = c.I(I_HISTLEN);
+  FwObsWriter ow{a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim};
+  FwObsWriter tw{a.term_obs_out, nullptr, env * (int64_t)a.obs_dim};
+  if (status == 0) {
+    const uint32_t gb = fw_goal_status(E, c);
+    bool achieved_on_step = false, resample = false;
+    if (E.streak_req > 0) {
+      const int slot = hist_len % E.streak_req;
+      const int wd = slot >> 5, bit = slot & 31;
+      uint32_t word = (uint32_t)c.I(I_GOALRING + wd);
+      const int oldb = (word >> bit) & 1u, newb = (int)(gb >> 31);
+      word = (word & ~(1u << bit)) | ((uint32_t)newb << bit);
+      c.I(I_GOALRING + wd) = (int32_t)word;
+      const int cnt = c.I(I_GOALCNT) + newb - oldb;
+      c.I(I_GOALCNT) = cnt;
+      if (newb) atomicAdd(a.msum + MS_GOAL_STEPS, 1.0);
+      if (steps_tgt >= E.streak_req && (double)cnt / (double)E.streak_req >= E.streak_fraction) {
+        achieved_on_step = !(flags & FWF_GOAL_ACHIEVED);
+        flags |= FWF_GOAL_ACHIEVED | FWF_EP_SUCCESS;
+        if (E.on_success == 1) { done = true; term = FW_TERM_SUCCESS; }
+        else if (E.on_success == 2) resample = true;
+      }
+    }
+    reward = fw_reward(E, P, L, c, flags, ar, achieved_on_step, steps, hist_len, gb);
+    if (resample || (E.resample_every && steps_tgt >= E.resample_every)) {
+      fw_sample_target(E, c, rng, flags, steps);
+      steps_tgt = 0;
+    }
+    double nt[FW_MAX_TARGETS];
+    fw_next_targets(E, P, c, flags, steps, steps_tgt, nt);
+    for (int k = 0; k < E.n_targets; ++k) {
+      c.D(D_TARGET + k) = nt[k];
+      if (L.tgt_depth > 0) fw_ring_put(c, L.tgt_row, L.tgt_depth, E.n_targets, k, hist_len, nt[k]);
+      if (L.err_depth > 0)
+        fw_ring_put(c, L.err_row, L.err_depth, E.n_targets, k, hist_len,
+                    fw_error(E.tgt[k], nt[k], fw_sv_value(c, E.tgt[k].sv)));
+    }
+    if (L.sv_depth > 1)
+      for (int v = 0; v < E.obs_nvar; ++v)
+        if (E.obs[v].type == 0)
+          fw_ring_put(c, L.sv_row, L.sv_depth, L.n_sv_obs, L.sv_slot[v], hist_len, fw_sv_value(c, E.obs[v].ref));
+    hist_len += 1;
+    c.I(I_HISTLEN) = hist_len;
+  } else {
+    done = true;
+    reward = E.step_fail_timesteps ? (double)(steps - E.steps_max) : E.step_fail_value;
+    term = status;
+  }
+  c.I(I_STEPS) = steps;
+  const bool do_reset = done && a.auto_reset;
+  if (do_reset) {
+    if (a.term_obs_out) fw_observation(E, P, L, c, rng, flags, steps, hist_len, false, tw);
+  } else {
+    fw_observation(E, P, L, c, rng, flags, steps, hist_len, false, ow);
+  }
+  c.I(I_FLAGS) = (int32_t)flags;
+  const double epret = c.D(D_EPRET) + reward;
+  c.D(D_EPRET) = epret;
+  a.rew_out[env] = (float)reward;
+  if (a.rew64_out) a.rew64_out[env] = reward;
+  a.done_out[env] = done ? 1 : 0;
+  a.term_out[env] = term;
+  if (done) {
+    atomicAdd(a.msum + MS_EPISODES, 1.0);
+    atomicAdd(a.msum + MS_RETURN, epret);
+    atomicAdd(a.msum + MS_LENGTH, (double)steps);
+    if (flags & FWF_EP_SUCCESS) atomicAdd(a.msum + MS_SUCCESS, 1.0);
+    if (term >= FW_TERM_FAIL_BASE) atomicAdd(a.msum + MS_FAILURES, 1.0);
+    if (term == FW_TERM_STEPS) atomicAdd(a.msum + MS_STEPS_TERM, 1.0);
+    if (term == FW_TERM_SUCCESS) atomicAdd(a.msum + MS_SUCCESS_TERM, 1.0);
+  }
+  if (do_reset) {
+    atomicAdd(a.ctr + CTR_RESETS, 1ull);
+    fw_reset_env(E, P, L, c, a.k0, a.k1, genv, nullptr, nullptr, 0, ow);
+  }
+}
+
+struct FwResetArgs {
+  double* d;
+  int32_t* i;
+  int64_t n;
+  const uint8_t* mask;
+  const double* init_state;
+  const double* init_target;
+  uint32_t k0, k1, env_offset;
+  float* obs_out;
+  double* obs64_out;
+  int obs_dim;
+  unsigned long long* ctr;
+};
+
+__global__ void __launch_bounds__(FW_ENV_BLOCK)
+fw_reset_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
+                const FwResetArgs a) {
+  const int64_t env = (int64_t)blockIdx.x * FW_ENV_BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  if (a.mask && !a.mask[env]) return;
+  FwEnvCtx c{a.d, a.i, L.stride, env};
+  FwObsWriter ow{a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim};
+  atomicAdd(a.ctr + CTR_RESETS, 1ull);
+  fw_reset_env(E, P, L, c, a.k0, a.k1, a.env_offset + (uint32_t)env, a.init_state, a.init_target, a.n, ow);
+}
+
+// ---- state export / import: [rows_d + rows_i, N] doubles -----------------------------------------------------
+__global__ void fw_export_kernel(const double* d, const int32_t* i, int64_t stride, int64_t n, int rows_d, int rows_i,
+                                 double* out) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  for (int r = 0; r < rows_d; ++r) out[(int64_t)r * n + env] = d[(int64_t)r * stride + env];
+  for (int r = 0; r < rows_i; ++r) out[(int64_t)(rows_d + r) * n + env] = (double)i[(int64_t)r * stride + env];
+}
+__global__ void fw_import_kernel(double* d, int32_t* i, int64_t stride, int64_t n, int rows_d, int rows_i,
+                                 const double* in) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  for (int r = 0; r < rows_d; ++r) d[(int64_t)r * stride + env] = in[(int64_t)r * n + env];
+  for (int r = 0; r < rows_i; ++r) i[(int64_t)r * stride + env] = (int32_t)(long long)in[(int64_t)(rows_d + r) * n + env];
+}
+__global__ void fw_gather_i32_kernel(const int32_t* i, int64_t stride, int64_t n, int row, int32_t* out) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env < n) out[env] = i[(int64_t)row * stride + env];
+}
+
+// DFMA peak micro-benchmark: 8 independent FMA chains per thread, all SMs, 32 resident warps per SM
+__global__ void __launch_bounds__(256) fw_dfma_kernel(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, b = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+      a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------------- host side
+static int make_layout(const fw_config_t& cfg, int64_t n, FwLayout& L) {
+  const fw_env_t& E = cfg.env;
+  memset(&L, 0, sizeof(L));
+  L.n = n;
+  L.stride = (n + 31) / 32 * 32;
+  if (E.obs_len < 1 || E.obs_step < 1 || E.obs_nvar < 1 || E.obs_nvar > FW_MAX_OBS_VARS)
+    return fail(FW_ERR_CONFIG, "bad observation length/step/nvar");
+  if (E.n_targets < 0 || E.n_targets > FW_MAX_TARGETS) return fail(FW_ERR_CONFIG, "bad n_targets");
+  if (E.n_factors < 0 || E.n_factors > FW_MAX_FACTORS) return fail(FW_ERR_CONFIG, "bad n_factors");
+  if (E.streak_req > 32 * FW_MAX_GOAL_WORDS) return fail(FW_ERR_CONFIG, "success_streak_req > 256 unsupported");
+  const int imax = (E.obs_len - 1) * E.obs_step + 1;   // deepest history index used by an observation row
+  int row = D_FIXED;
+  int act_need = 0, win_obs = 0;
+  bool need_err = false, need_tgt = false, integ = false;
+  for (int v = 0; v < E.obs_nvar; ++v) {
+    L.sv_slot[v] = -1;
+    const fw_obs_var_t& ov = E.obs[v];
+    if (ov.type == 0) L.sv_slot[v] = L.n_sv_obs++;
+    if (ov.type == 1 && ov.value_kind == 0 && E.obs_len > 1) need_err = true;
+    if (ov.type == 1 && ov.value_kind == 1 && E.obs_len > 1) need_tgt = true;
+    if (ov.type == 1 && ov.value_kind == 2) { need_err = true; integ = true; }
+    if (ov.type == 2) win_obs = ov.window > win_obs ? ov.window : win_obs;
+  }
+  if (win_obs > 0) act_need = win_obs + imax;
+  bool int_err = false;
+  for (int f = 0; f < E.n_factors; ++f) {
+    const fw_factor_t& F = E.fac[f];
+    if (F.cls == 0 && F.type == 1) act_need = F.window + 1 > act_need ? F.window + 1 : act_need;
+    if (F.cls == 1 && F.type == 2) { need_err = true; int_err = true; }
+  }
+  if ((integ || int_err) && E.integration_window <= 0)
+    return fail(FW_ERR_CONFIG, "integrator observation / int_error reward need integration_window > 0");
+  if (act_need > 0) {
+    const bool raw = cfg.sim.scale_actions != 0;
+    // reward "delta" always reads the raw action history; action observations read raw actions when scale_actions
+    // and PyFly's constrained command history otherwise (fixed_wing.py:824-828)
+    L.act_depth = act_need; L.act_row = row; row += act_need * FW_N_ACT;
+    if (!raw && win_obs > 0) { L.cmd_depth = act_need; L.cmd_row = row; row += act_need * FW_N_ACT; }
+  }
+  if (E.obs_len > 1 && L.n_sv_obs > 0) { L.sv_depth = imax + 1; L.sv_row = row; row += L.sv_depth * L.n_sv_obs; }
+  else L.sv_depth = 1;
+  if (need_err) {
+    L.err_depth = ((integ || int_err) ? E.integration_window : 0) + imax + 2;
+    L.err_row = row; row += L.err_depth * E.n_targets;
+  }
+  if (need_tgt) { L.tgt_depth = imax + 1; L.tgt_row = row; row += L.tgt_depth * E.n_targets; }
+  L.d_rows = row;
+  L.i_rows = I_FIXED;
+  L.goal_words = (E.streak_req + 31) / 32;
+  return FW_OK;
+}
+
+extern "C" {
+
+const char* fw_last_error(void) { return g_err; }
+int fw_abi_version(void) { return FW_ABI_VERSION; }
+int64_t fw_config_sizeof(void) { return (int64_t)sizeof(fw_config_t); }
+
+int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset, int device, fw_handle* out) {
+  if (!cfg || !out || n_envs <= 0) return fail(FW_ERR_ARG, "fw_create: bad argument");
+  if (cfg->abi_version != FW_ABI_VERSION) return fail(FW_ERR_ABI, "fw_create: config ABI version mismatch");
+  CK(cudaSetDevice(device));
+  fw_handle_s* h = new (std::nothrow) fw_handle_s();
+  if (!h) return fail(FW_ERR_ALLOC, "out of host memory");
+  h->cfg = *cfg;
+  h->device = device;
+  h->n = n_envs;
+  h->offset = global_env_offset;
+  h->seed = 0;
+  h->last_stream = nullptr;
+  int rc = make_layout(h->cfg, n_envs, h->L);
+  if (rc) { delete h; return rc; }
+  const size_t db = (size_t)h->L.d_rows * h->L.stride * sizeof(double);
+  const size_t ib = (size_t)h->L.i_rows * h->L.stride * sizeof(int32_t);
+  if (cudaMalloc(&h->d, db) != cudaSuccess || cudaMalloc(&h->i, ib) != cudaSuccess ||
+      cudaMalloc(&h->ctr, CTR_N * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&h->msum, FW_N_METRIC_SUMS * sizeof(double)) != cudaSuccess) {
+    delete h;
+    return fail(FW_ERR_ALLOC, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  CK(cudaMemset(h->d, 0, db));
+  CK(cudaMemset(h->i, 0, ib));
+  CK(cudaMemset(h->ctr, 0, CTR_N * sizeof(unsigned long long)));
+  CK(cudaMemset(h->msum, 0, FW_N_METRIC_SUMS * sizeof(double)));
+  const int smem64 = 6 * FW_N_ODE * FW_DYN_BLOCK * (int)sizeof(double);
+  CK(cudaFuncSetAttribute(fw_dyn_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+  CK(cudaFuncSetAttribute(fw_dyn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64 / 2));
+  *out = h;
+  return FW_OK;
+}
+
+int fw_destroy(fw_handle h) {
+  if (!h) return FW_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d); cudaFree(h->i); cudaFree(h->ctr); cudaFree(h->msum);
+  delete h;
+  return FW_OK;
+}
+
+int fw_seed(fw_handle h, uint64_t seed) {
+  if (!h) return fail(FW_ERR_ARG, "null handle");
+  h->seed = seed;
+  return FW_OK;
+}
+
+int fw_set_config(fw_handle h, const fw_config_t* cfg) {
+  if (!h || !cfg) return fail(FW_ERR_ARG, "null argument");
+  if (cfg->abi_version != FW_ABI_VERSION) return fail(FW_ERR_ABI, "config ABI version mismatch");
+  FwLayout L;
+  int rc = make_layout(*cfg, h->n, L);
+  if (rc) return rc;
+  if (L.d_rows != h->L.d_rows || memcmp(&L, &h->L, sizeof(L)) != 0)
+    return fail(FW_ERR_CONFIG, "fw_set_config: new config changes the state layout; create a new handle");
+  h->cfg = *cfg;
+  return FW_OK;
+}
+
+int64_t fw_num_envs(fw_handle h) { return h ? h->n : 0; }
+int fw_obs_dim(fw_handle h) { return h ? h->cfg.env.obs_len * h->cfg.env.obs_nvar : 0; }
+int64_t fw_state_rows(fw_handle h) { return h ? h->L.d_rows + h->L.i_rows : 0; }
+
+const char* fw_state_row_name(fw_handle h, int64_t r) {
+  static const char* dn[D_FIXED] = {
+      "q0", "q1", "q2", "q3", "omega_p", "omega_q", "omega_r", "position_n", "position_e", "position_d", "velocity_u",
+      "velocity_v", "velocity_w", "elevon_left", "elevon_right", "throttle", "elevon_left_dot", "elevon_right_dot",
+      "throttle_dot", "roll", "pitch", "yaw", "Va", "alpha", "beta", "elevator", "aileron", "cmd_elevator", "cmd_aileron",
+      "cmd_throttle", "wind_n", "wind_e", "wind_d", "tx0", "tx1", "tx2", "tx3", "tx4", "tx5", "tx6", "tx7", "tx8", "tx9",
+      "tx10", "tx11", "tx12", "tx13", "tx14", "tx15", "tx16", "tx17", "tu0", "tu1", "tu2", "tu3", "gust_u", "gust_v",
+      "gust_w", "gust_p", "gust_q", "gust_r", "target0", "target1", "target2", "tslope0", "tslope1", "tslope2", "tamp0",
+      "tamp1", "tamp2", "tperiod0", "tperiod1", "tperiod2", "tphase0", "tphase1", "tphase2", "tbias0", "tbias1", "tbias2",
+      "prev_shaping0", "prev_shaping1", "prev_shaping2", "err0_0", "err0_1", "err0_2", "episode_return"};
+  static const char* in[I_GOALRING + 1] = {"steps_count", "steps_for_target", "hist_len", "rng_tick", "episode_tick",
+                                           "flags", "goal_count", "last_attempts", "sim_status", "goal_ring"};
+  if (!h || r < 0) return nullptr;
+  if (r < D_FIXED) return dn[r];
+  if (r < h->L.d_rows) return "ring";
+  r -= h->L.d_rows;
+  if (r < I_GOALRING) return in[r];
+  if (r < h->L.i_rows) return in[I_GOALRING];
+  return nullptr;
+}
+
+int fw_reset(fw_handle h, const uint8_t* mask, const double* init_state, const double* init_target, float* obs_out,
+             double* obs64_out, void* stream) {
+  if (!h) return fail(FW_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  FwResetArgs a{h->d, h->i, h->n, mask, init_state, init_target, (uint32_t)h->seed, (uint32_t)(h->seed >> 32),
+                (uint32_t)h->offset, obs_out, obs64_out, fw_obs_dim(h), h->ctr};
+  const int grid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
+  fw_reset_kernel<<<grid, FW_ENV_BLOCK, 0, s>>>(h->cfg.env, h->cfg.sim, h->L, a);
+  CK(cudaGetLastError());
+  h->last_stream = s;
+  return FW_OK;
+}
+
+int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, float* rew_out, uint8_t* done_out,
+            int32_t* term_out, double* obs64_out, double* rew64_out, float* term_obs_out, int auto_reset,
+            void* stream) {
+  if (!h || !actions || !rew_out || !done_out || !term_out) return fail(FW_ERR_ARG, "fw_step: null argument");
+  if (!obs_out && !obs64_out) return fail(FW_ERR_ARG, "fw_step: no observation buffer");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
+  FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, h->ctr};
+  const int dgrid = (int)((h->n + FW_DYN_BLOCK - 1) / FW_DYN_BLOCK);
+  if (h->cfg.precision == 0) {
+    const int smem = 6 * FW_N_ODE * FW_DYN_BLOCK * (int)sizeof(double);
+    fw_dyn_kernel<double><<<dgrid, FW_DYN_BLOCK, smem, s>>>(h->cfg.sim, da);
+  } else {
+    const int smem = 6 * FW_N_ODE * FW_DYN_BLOCK * (int)sizeof(float);
+    fw_dyn_kernel<float><<<dgrid, FW_DYN_BLOCK, smem, s>>>(h->cfg.sim, da);
+  }
+  CK(cudaGetLastError());
+  FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
+               term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum};
+  const int egrid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
+  fw_env_kernel<<<egrid, FW_ENV_BLOCK, 0, s>>>(h->cfg.env, h->cfg.sim, h->L, ea);
+  CK(cudaGetLastError());
+  h->last_stream = s;
+  return FW_OK;
+}
+
+int fw_get_state(fw_handle h, double* out, void* stream) {
+  if (!h || !out) return fail(FW_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  const int grid = (int)((h->n + 255) / 256);
+  fw_export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, h->i, h->L.stride, h->n, h->L.d_rows, h->L.i_rows, out);
+  CK(cudaGetLastError());
+  return FW_OK;
+}
+
+int fw_set_state(fw_handle h, const double* in, void* stream) {
+  if (!h || !in) return fail(FW_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  const int grid = (int)((h->n + 255) / 256);
+  fw_import_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, h->i, h->L.stride, h->n, h->L.d_rows, h->L.i_rows, in);
+  CK(cudaGetLastError());
+  return FW_OK;
+}
+
+int fw_last_attempts(fw_handle h, int32_t* out, void* stream) {
+  if (!h || !out) return fail(FW_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  const int grid = (int)((h->n + 255) / 256);
+  fw_gather_i32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->i, h->L.stride, h->n, I_LASTK, out);
+  CK(cudaGetLastError());
+  return FW_OK;
+}
+
+int fw_counters(fw_handle h, fw_counters_t* out) {
+  if (!h || !out) return fail(FW_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  unsigned long long c[CTR_N];
+  CK(cudaStreamSynchronize(h->last_stream));
+  CK(cudaMemcpy(c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost));
+  out->env_steps = c[CTR_ENV_STEPS];
+  out->attempts = c[CTR_ATTEMPTS];
+  out->accepted = c[CTR_ACCEPTED];
+  out->warp_max_attempts = c[CTR_WARP_MAX];
+  out->warp_steps = c[CTR_WARP_STEPS];
+  out->failures = c[CTR_FAILURES];
+  out->resets = c[CTR_RESETS];
+  out->rhs_evals = 2 * c[CTR_ENV_STEPS] + 6 * c[CTR_ATTEMPTS];
+  return FW_OK;
+}
+
+int fw_reset_counters(fw_handle h) {
+  if (!h) return fail(FW_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->last_stream));
+  CK(cudaMemset(h->ctr, 0, CTR_N * sizeof(unsigned long long)));
+  CK(cudaMemset(h->msum, 0, FW_N_METRIC_SUMS * sizeof(double)));
+  return FW_OK;
+}
+
+int fw_metric_sums(fw_handle h, double* out_host) {
+  if (!h || !out_host) return fail(FW_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->last_stream));
+  CK(cudaMemcpy(out_host, h->msum, FW_N_METRIC_SUMS * sizeof(double), cudaMemcpyDeviceToHost));
+  return FW_OK;
+}
+
+int fw_dfma_peak(int device, double* flops_out, double* ms_out) {
+  if (!flops_out) return fail(FW_ERR_ARG, "null argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double* d;
+  CK(cudaMalloc(&d, 8));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 4096;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  fw_dfma_kernel<<<blocks, threads>>>(d, 64, 1.0);   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0));
+    fw_dfma_kernel<<<blocks, threads>>>(d, iters, 1.0);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = ms < best ? ms : best;
+  }
+  CK(cudaGetLastError());
+  const double fl = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+  *flops_out = fl / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return FW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+// Structure-of-arrays state layout in HBM: one row per quantity, N (padded) contiguous envs per row, so that lane i
+// of a warp touches element i of a row (fully coalesced 256 B per warp per row for doubles).
+#pragma once
+#include <stdint.h>
+#include "../../include/fwgym.h"
+
+// ---- double rows (fixed part) -------------------------------------------------------------------------------
+enum {
+  D_Q = 0,          // 4  quaternion (normalised at each env step, PyFly _set_states_from_ode_solution)
+  D_OMEGA = 4,      // 3
+  D_POS = 7,        // 3
+  D_VEL = 10,       // 3
+  D_ACT = 13,       // 3  elevon_left, elevon_right, throttle values
+  D_ACTDOT = 16,    // 3
+  D_ROLL = 19, D_PITCH = 20, D_YAW = 21, D_VA = 22, D_ALPHA = 23, D_BETA = 24, D_ELEV = 25, D_AIL = 26,
+  D_CMD = 27,       // 3  constrained model commands (elevator, aileron, throttle) of the last step
+  D_WIND = 30,      // 3  steady wind NED
+  D_TX = 33,        // 18 Dryden filter states, 3 per filter
+  D_TU = 51,        // 4  previous white-noise sample per stream (already scaled by sqrt(pi/dt))
+  D_GUST = 55,      // 6  current gust: linear u,v,w then angular p,q,r
+  D_TARGET = 61,    // 3
+  D_TSLOPE = 64, D_TAMP = 67, D_TPERIOD = 70, D_TPHASE = 73, D_TBIAS = 76,   // 3 each
+  D_PREVSHAPE = 79, // 3  prev_shaping per function class
+  D_ERR0 = 82,      // 3  history["error"][k][0]
+  D_EPRET = 85,     // episode return
+  D_FIXED = 86
+};
+
+// ---- int32 rows (fixed part) --------------------------------------------------------------------------------
+enum {
+  I_STEPS = 0,      // steps_count
+  I_STEPS_TGT,      // _steps_for_current_target
+  I_HISTLEN,        // len(history["error"][k]) == len(PyFly Variable.history) (successful steps + 1)
+  I_TICK,           // rng tick (next call uses this value)
+  I_EPTICK,         // tick of the reset that started the episode (keys the turbulence stream)
+  I_FLAGS,          // FWF_* bits
+  I_GOALCNT,        // number of set bits among the last streak_req entries of the "all" goal history
+  I_LASTK,          // dopri5 attempts of the last step
+  I_STATUS,         // last sim step: 0 ok, else FW_TERM_FAIL_BASE + sv
+  I_GOALRING,       // FW_MAX_GOAL_WORDS words
+  I_FIXED = I_GOALRING + FW_MAX_GOAL_WORDS
+};
+
+#define FWF_GOAL_ACHIEVED 1u      // fixed_wing.py:51,382 latch (never cleared by reset)
+#define FWF_HIST_VALID 2u         // self.history is not None (a previous episode exists)
+#define FWF_PREVSHAPE_SHIFT 2     // 3 bits: prev_shaping[fclass] is not None
+#define FWF_TCLS_SHIFT 8          // 2 bits per target: current class (reset(target=) may force constant)
+#define FWF_EP_SUCCESS (1u << 16) // streak achieved in this episode (metric "success"["all"])
+
+// variable part, computed on the host from the config (api.cu: make_layout)
+struct FwLayout {
+  int64_t n;            // number of envs
+  int64_t stride;       // padded row length (multiple of 32)
+  int32_t d_rows, i_rows;
+  int32_t act_depth, act_row;     // raw-action ring: act_depth x 3 rows starting at act_row (double)
+  int32_t cmd_depth, cmd_row;     // constrained-command ring (only when scale_actions == 0)
+  int32_t sv_depth, sv_row;       // observed-state ring: sv_depth x n_sv_obs rows
+  int32_t n_sv_obs;
+  int32_t err_depth, err_row;     // error ring: err_depth x n_targets
+  int32_t tgt_depth, tgt_row;     // target ring: tgt_depth x n_targets
+  int32_t goal_words;
+  int32_t sv_slot[FW_MAX_OBS_VARS];   // obs var index -> column in the sv ring (-1 if not a state var)
+};

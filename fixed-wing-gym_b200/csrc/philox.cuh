@@ -1,0 +1,62 @@
+// Counter-based per-env RNG: Philox4x32-10 (Salmon et al., SC'11).  The reference draws from numpy MT19937
+// (fixed_wing.py:57,220; PyFly per-variable RandomState); this framework replaces that with a keyed counter so any
+// sharding of envs over GPUs produces identical per-env streams.  oracle/philox.py is the numpy twin.
+//
+// counter = (global env id, tick, stream, index), key = 64-bit seed.
+//   tick   : per-env count of reset()/step() calls since seeding; each call uses its own tick.
+//   stream : FW_RS_* below.
+//   index  : draw index inside (tick, stream).
+#pragma once
+#include <stdint.h>
+
+#define FW_RS_INIT 0    // PyFly Variable.reset uniform draws, index = fw_sv id
+#define FW_RS_WIND 1    // steady wind magnitude / components
+#define FW_RS_TURB 2    // Dryden white noise; tick = episode tick, index = 2*sim_step + {0,1}
+#define FW_RS_ENV_U 3   // env-side uniform draws in call order (target sampling, init noise)
+#define FW_RS_ENV_N 4   // env-side normal draws in call order (observation noise), two per block
+
+__host__ __device__ __forceinline__ void fw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct FwRng {
+  uint32_t k0, k1, env, tick;
+};
+
+// 53-bit uniform in [0,1) from two words (same construction as numpy's random_sample: (a>>5, b>>6))
+__host__ __device__ __forceinline__ double fw_u53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ double fw_uniform01(const FwRng& g, uint32_t stream, uint32_t idx) {
+  uint32_t w[4];
+  fw_philox4x32_10(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+  return fw_u53(w[0], w[1]);
+}
+
+__device__ __forceinline__ double fw_uniform(const FwRng& g, uint32_t stream, uint32_t idx, double lo, double hi) {
+  return lo + (hi - lo) * fw_uniform01(g, stream, idx);   // numpy: low + (high-low)*random_sample()
+}
+
+// two standard normals per Philox block (Box-Muller); u1 in (0,1] so the log is finite
+__device__ __forceinline__ void fw_normal2(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
+  uint32_t w[4];
+  fw_philox4x32_10(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+  double u1 = 1.0 - fw_u53(w[0], w[1]);
+  double u2 = fw_u53(w[2], w[3]);
+  double r = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}

@@ -1,0 +1,313 @@
+"""Batched VecEnv over torch CUDA tensors — the reference-facing host mirror of the hot path.
+
+`FixedWingVecEnv` steps N independent `FixedWingAircraft` (fixed_wing.py:13-437) per call through libfwgym.so.  It
+duck-types the stable-baselines VecEnv surface the reference's scripts use (train_rl_controller.py:223-225,
+evaluate_controller.py:80-154): num_envs, observation_space/action_space (shape/low/high/dtype), reset(), step(),
+step_async()/step_wait(), seed(), get_attr(), set_attr(), env_method(), close(); finished envs auto-reset and return
+the post-reset observation, the terminal one is infos[i]["terminal_observation"].  Tensors stay on the device;
+`infos` is materialised lazily.  PyTorch is plumbing here (device memory, streams); all compute is in the CUDA library.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+from .config import CompiledConfig
+
+TERM_NAMES = {0: None, 1: "steps", 2: "success"}
+N_INIT_ROWS = _capi.DEFINES["FW_N_SV"] + 3
+WIND_KEYS = ("wind_n", "wind_e", "wind_d")
+
+
+class Box:
+    """Minimal gym.spaces.Box stand-in (shape / low / high / dtype), float32 like fixed_wing.py:176-183."""
+
+    def __init__(self, low, high, dtype=np.float32):
+        self.low = np.asarray(low, dtype=dtype)
+        self.high = np.asarray(high, dtype=dtype)
+        self.shape = self.low.shape
+        self.dtype = np.dtype(dtype)
+
+    def sample(self, rng=None):
+        rng = rng or np.random
+        lo = np.clip(self.low, -1, 1)
+        hi = np.clip(self.high, -1, 1)
+        return rng.uniform(lo, hi).astype(self.dtype)
+
+
+def term_name(code):
+    if code >= _capi.DEFINES["FW_TERM_FAIL_BASE"]:
+        return _capi.SV_ORDER[code - _capi.DEFINES["FW_TERM_FAIL_BASE"]]
+    return TERM_NAMES.get(int(code))
+
+
+class VecInfos:
+    """List-like `infos`: dict i is built on first access (one device->host copy for the whole batch)."""
+
+    def __init__(self, env, done, term, term_obs, targets):
+        self._env, self._done, self._term, self._term_obs, self._targets = env, done, term, term_obs, targets
+        self._host = None
+
+    def __len__(self):
+        return self._env.num_envs
+
+    def _materialise(self):
+        if self._host is None:
+            self._host = (self._done.cpu().numpy(), self._term.cpu().numpy(), self._targets.cpu().numpy(),
+                          None if self._term_obs is None else self._term_obs.cpu().numpy())
+        return self._host
+
+    def __getitem__(self, i):
+        done, term, tgt, tobs = self._materialise()
+        info = {"target": {n: float(tgt[k, i]) for k, n in enumerate(self._env.target_names)}}
+        if done[i]:
+            info["termination"] = term_name(int(term[i]))
+            if tobs is not None:
+                info["terminal_observation"] = tobs[i].reshape(self._env.cc.obs_shape)
+        return info
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class FixedWingVecEnv:
+    def __init__(self, config_path=None, num_envs=1, device="cuda:0", sampler=None, sim_config_path=None,
+                 sim_parameter_path=None, config_kw=None, sim_config_kw=None, seed=0, precision="fp64",
+                 env_offset=0, auto_reset=True, keep_terminal_obs=False):
+        if sampler is not None:
+            raise NotImplementedError("adaptive sampler hook is out of scope (SURVEY §2 #18)")
+        self._lib = _capi.lib()   # raises if the CUDA extension is not built: no fallback
+        if not torch.cuda.is_available():
+            raise _capi.FwError("FixedWingVecEnv needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.device = torch.device(device)
+        self.num_envs = int(num_envs)
+        self.env_offset = int(env_offset)
+        self.auto_reset = bool(auto_reset)
+        self.keep_terminal_obs = bool(keep_terminal_obs)
+        self.cc = CompiledConfig(config_path, sim_config_path, sim_parameter_path, config_kw, sim_config_kw, precision)
+        self.cfg = self.cc.cfg
+        self.target_names = list(self.cc._target_props_init["states"].keys())
+        self.observation_space = Box(self.cc.observation_low, self.cc.observation_high)
+        self.action_space = Box(self.cc.action_space_low, self.cc.action_space_high)
+        self._h = ctypes.c_void_p()
+        pod = self.cc.pod()
+        _capi.check(self._lib.fw_create(ctypes.byref(pod), self.num_envs, self.env_offset,
+                                        self.device.index or 0, ctypes.byref(self._h)))
+        self.obs_dim = self._lib.fw_obs_dim(self._h)
+        n, d = self.num_envs, self.device
+        self._obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=d)
+        self._rew = torch.zeros(n, dtype=torch.float32, device=d)
+        self._done = torch.zeros(n, dtype=torch.uint8, device=d)
+        self._term = torch.zeros(n, dtype=torch.int32, device=d)
+        self._term_obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=d) if keep_terminal_obs else None
+        self._obs64 = self._rew64 = None
+        self._actions = None
+        self.training = True
+        self.seed(seed)
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+    def enable_f64_outputs(self, on=True):
+        """Also write float64 observations / rewards (parity checks; the reference returns float64)."""
+        if on:
+            self._obs64 = torch.zeros((self.num_envs, self.obs_dim), dtype=torch.float64, device=self.device)
+            self._rew64 = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        else:
+            self._obs64 = self._rew64 = None
+
+    def _shape_obs(self, o):
+        return o.view((self.num_envs,) + tuple(self.cc.obs_shape))
+
+    # ---------------------------------------------------------------------------------------------------- API
+    def seed(self, seed=None):
+        seed = 0 if seed is None else int(seed)
+        _capi.check(self._lib.fw_seed(self._h, ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF)))
+        self._seed = seed
+        return [seed + self.env_offset + i for i in range(self.num_envs)] if self.num_envs <= 64 else [seed]
+
+    def reset(self, indices=None, state=None, target=None):
+        """Reset all envs (or `indices`).  `state` / `target`: dict name -> scalar or array over the reset envs,
+        like FixedWingAircraft.reset(state=, target=) (fixed_wing.py:287-315)."""
+        n, d = self.num_envs, self.device
+        mask = None
+        idx = None
+        if indices is not None:
+            idx = torch.as_tensor(np.atleast_1d(indices), dtype=torch.long, device=d)
+            mask = torch.zeros(n, dtype=torch.uint8, device=d)
+            mask[idx] = 1
+        init_state = init_target = None
+        if state:
+            init_state = torch.full((N_INIT_ROWS, n), float("nan"), dtype=torch.float64, device=d)
+            st = dict(state)
+            if "wind" in st:
+                for k, v in zip(WIND_KEYS, st.pop("wind")):
+                    st[k] = v
+            for name, val in st.items():
+                if name in WIND_KEYS:
+                    row = _capi.DEFINES["FW_N_SV"] + WIND_KEYS.index(name)
+                elif name in _capi.SV_NAMES:
+                    row = _capi.sv_id(name)
+                else:
+                    continue
+                v = torch.as_tensor(np.asarray(val, dtype=np.float64), device=d)
+                if idx is None:
+                    init_state[row, :] = v
+                else:
+                    init_state[row, idx] = v
+        if target:
+            init_target = torch.full((_capi.DEFINES["FW_MAX_TARGETS"], n), float("nan"), dtype=torch.float64, device=d)
+            for name, val in target.items():
+                row = self.target_names.index(name)
+                v = torch.as_tensor(np.asarray(val, dtype=np.float64), device=d)
+                if idx is None:
+                    init_target[row, :] = v
+                else:
+                    init_target[row, idx] = v
+        _capi.check(self._lib.fw_reset(self._h, self._ptr(mask), self._ptr(init_state), self._ptr(init_target),
+                                       self._ptr(self._obs), self._ptr(self._obs64), self._stream()))
+        return self._shape_obs(self._obs)
+
+    def step_tensors(self, actions):
+        """Device-only step: (obs, reward, done, term_code) tensors, no host synchronisation.
+        actions: [N, 3] float32 or float64 CUDA tensor (float64 is upcast-free and used for parity)."""
+        if actions.device != self.device:
+            actions = actions.to(self.device, non_blocking=True)
+        if actions.dtype not in (torch.float32, torch.float64):
+            actions = actions.float()
+        actions = actions.contiguous()
+        if actions.shape != (self.num_envs, 3):
+            raise ValueError("actions must have shape (%d, 3)" % self.num_envs)
+        _capi.check(self._lib.fw_step(self._h, self._ptr(actions), 1 if actions.dtype == torch.float64 else 0,
+                                      self._ptr(self._obs), self._ptr(self._rew), self._ptr(self._done),
+                                      self._ptr(self._term), self._ptr(self._obs64), self._ptr(self._rew64),
+                                      self._ptr(self._term_obs), 1 if self.auto_reset else 0, self._stream()))
+        self._actions = actions   # keep alive until the stream has consumed it
+        return self._shape_obs(self._obs), self._rew, self._done, self._term
+
+    def step_async(self, actions):
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions))
+        self._pending = self.step_tensors(actions)
+
+    def step_wait(self):
+        obs, rew, done, term = self._pending
+        infos = VecInfos(self, done, term, self._term_obs, self.get_targets())
+        return obs, rew, done.bool(), infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.fw_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------------------- state, counters, metrics
+    def state_rows(self):
+        n = self._lib.fw_state_rows(self._h)
+        return [self._lib.fw_state_row_name(self._h, r).decode() for r in range(n)]
+
+    def get_state(self):
+        out = torch.empty((self._lib.fw_state_rows(self._h), self.num_envs), dtype=torch.float64, device=self.device)
+        _capi.check(self._lib.fw_get_state(self._h, self._ptr(out), self._stream()))
+        return out
+
+    def set_state(self, state):
+        state = state.to(self.device, torch.float64).contiguous()
+        _capi.check(self._lib.fw_set_state(self._h, self._ptr(state), self._stream()))
+        self._state_keepalive = state
+
+    def get_named_state(self, names):
+        rows = self.state_rows()
+        st = self.get_state()
+        return {n: st[rows.index(n)] for n in names}
+
+    def get_targets(self):
+        rows = self.state_rows()
+        st = self.get_state()
+        r0 = rows.index("target0")
+        return st[r0:r0 + len(self.target_names)]
+
+    def last_attempts(self):
+        out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        _capi.check(self._lib.fw_last_attempts(self._h, self._ptr(out), self._stream()))
+        return out
+
+    def counters(self):
+        c = _capi.fw_counters_t()
+        _capi.check(self._lib.fw_counters(self._h, ctypes.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in c._fields_}
+
+    def reset_counters(self):
+        _capi.check(self._lib.fw_reset_counters(self._h))
+
+    METRIC_SUM_NAMES = ("episodes", "successes", "sum_return", "sum_length", "failures", "steps_term", "success_term",
+                        "goal_steps")
+
+    def metric_sums(self):
+        """Local episode-metric sums (host float64 vector) — all-reduce these across ranks (parallel.py)."""
+        buf = (ctypes.c_double * _capi.DEFINES["FW_N_METRIC_SUMS"])()
+        _capi.check(self._lib.fw_metric_sums(self._h, buf))
+        return np.array(buf[:], dtype=np.float64)
+
+    # ------------------------------------------------------------------- SB VecEnv attribute / method plumbing
+    def get_attr(self, name, indices=None):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        if name == "target":
+            tg = self.get_targets().cpu().numpy()
+            ids = range(self.num_envs) if indices is None else np.atleast_1d(indices)
+            return [{t: float(tg[k, i]) for k, t in enumerate(self.target_names)} for i in ids]
+        if name == "steps_count":
+            sc = self.get_named_state(["steps_count"])["steps_count"].cpu().numpy().astype(int)
+            ids = range(self.num_envs) if indices is None else np.atleast_1d(indices)
+            return [int(sc[i]) for i in ids]
+        if name == "simulator":
+            return [SimulatorView(self)] * n
+        return [getattr(self, name)] * n
+
+    def set_attr(self, name, value, indices=None):
+        setattr(self, name, value)
+
+    def env_method(self, name, *args, indices=None, **kwargs):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        if name == "set_curriculum_level":
+            self.set_curriculum_level(*args, **kwargs)
+            return [None] * n
+        if name == "reset":
+            obs = self.reset(indices=indices, **kwargs)
+            ids = range(self.num_envs) if indices is None else np.atleast_1d(indices)
+            host = obs.cpu().numpy()
+            return [host[i] for i in ids]
+        if name == "seed":
+            return [self.seed(*args, **kwargs)] * n
+        raise NotImplementedError("env_method(%r) is not supported" % name)
+
+    def set_curriculum_level(self, level):
+        """fixed_wing.py:224-285; applies to every env of the batch (the reference calls it on all envs too,
+        train_rl_controller.py:84,224)."""
+        self.cc.set_curriculum_level(level)
+        pod = self.cc.pod()
+        _capi.check(self._lib.fw_set_config(self._h, ctypes.byref(pod)))
+
+
+class SimulatorView:
+    """The slice of the PyFly object surface that callers of the reference touch (fixed_wing.py §8b): dt, params."""
+
+    def __init__(self, env):
+        self.dt = env.cc.dt
+        self.params = env.cc.params
+        self.state = env.cc.state

@@ -1,0 +1,235 @@
+/*
+ * fwgym.h — C-ABI of the B200-native batched fixed-wing simulator (libfwgym.so).
+ *
+ * This is the drop-in boundary for the hot path of eivindeb/fixed-wing-gym:
+ *     FixedWingAircraft.step()  ->  PyFly.step()  ->  scipy solve_ivp(RK45)  ->  reward/target/observation
+ * (reference: gym_fixed_wing/fixed_wing.py:338-437 "step", :287-336 "reset", :214-222 "seed").
+ * The reference has no FFI of its own (pure Python); the binding a maintainer adds is the ctypes stub shown in
+ * INTEGRATION.md.  Plain pointers and sizes only — no torch types.  All pointers marked "device" are CUDA device
+ * pointers owned by the caller (e.g. torch CUDA tensors); every call is stream-ordered on the cudaStream_t passed
+ * as `void* stream` (NULL = legacy default stream).  A handle is not thread-safe; distinct handles are independent.
+ *
+ * All functions return FW_OK (0) or a negative fw_status; fw_last_error() returns a message for the last failure
+ * on the calling thread.
+ */
+#ifndef FWGYM_H
+#define FWGYM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FW_ABI_VERSION 3
+
+/* ---------------------------------------------------------------------------------------------- limits */
+#define FW_MAX_OBS_VARS 32
+#define FW_MAX_TARGETS 3
+#define FW_N_ACT 3            /* elevator, aileron, throttle inputs (fixed_wing.py:39 forces actuation.inputs) */
+#define FW_MAX_FACTORS 16
+#define FW_N_FCLASS 3         /* linear, exponential, quadratic (fixed_wing.py:738-746) */
+#define FW_MAX_GOAL_WORDS 8   /* success_streak_req <= 256 */
+#define FW_N_SV 21            /* PyFly state variables, ids below */
+#define FW_N_ODE 19           /* quat4, omega3, pos3, vel3, actuator value3, actuator dot3 */
+#define FW_N_FILT 6           /* Dryden shaping filters u,v,w,p,q,r */
+#define FW_FILT_MAXN 3
+
+/* PyFly state-variable ids (order of oracle/pyfly_restated.py REQUIRED_VARIABLES + elevons) */
+enum fw_sv {
+  FW_SV_ROLL = 0, FW_SV_PITCH, FW_SV_YAW, FW_SV_OMEGA_P, FW_SV_OMEGA_Q, FW_SV_OMEGA_R,
+  FW_SV_POS_N, FW_SV_POS_E, FW_SV_POS_D, FW_SV_VEL_U, FW_SV_VEL_V, FW_SV_VEL_W,
+  FW_SV_VA, FW_SV_ALPHA, FW_SV_BETA, FW_SV_ELEVATOR, FW_SV_AILERON, FW_SV_RUDDER, FW_SV_THROTTLE,
+  FW_SV_ELEVON_L, FW_SV_ELEVON_R
+};
+
+enum fw_status {
+  FW_OK = 0, FW_ERR_ARG = -1, FW_ERR_CUDA = -2, FW_ERR_CONFIG = -3, FW_ERR_ALLOC = -4, FW_ERR_ABI = -5
+};
+
+/* termination codes written to term_code_out (fixed_wing.py:366-368,383-385,409-416) */
+#define FW_TERM_NONE 0
+#define FW_TERM_STEPS 1
+#define FW_TERM_SUCCESS 2
+#define FW_TERM_FAIL_BASE 16   /* FW_TERM_FAIL_BASE + fw_sv id of the variable whose constraint was violated */
+
+/* variable condition flags (PyFly Variable.apply_conditions) */
+#define FW_VC_VMIN 1u
+#define FW_VC_VMAX 2u
+#define FW_VC_CMIN 4u
+#define FW_VC_CMAX 8u
+#define FW_VC_WRAP 16u
+
+typedef struct {
+  double vmin, vmax, cmin, cmax;   /* value clip and hard constraint, radians where applicable */
+  double init_min, init_max;       /* uniform init range after curriculum scaling (fixed_wing.py:233-245) */
+  uint32_t flags;
+  uint32_t _pad;
+} fw_var_t;
+
+typedef struct {
+  int32_t n;                        /* filter order 1..3 */
+  int32_t stream;                   /* which of the 4 white-noise streams drives it */
+  double Ad[FW_FILT_MAXN * FW_FILT_MAXN];   /* x' = x*Ad + u_prev*Bd0 + u*Bd1 (scipy lsim row-vector form) */
+  double Bd0[FW_FILT_MAXN], Bd1[FW_FILT_MAXN], C[FW_FILT_MAXN];
+  double D;
+} fw_filter_t;
+
+typedef struct {
+  int32_t type;        /* 0 state, 1 target, 2 action (fixed_wing.py:797-830) */
+  int32_t ref;         /* fw_sv id | target index | action index */
+  int32_t value_kind;  /* target: 0 relative, 1 absolute, 2 integrator */
+  int32_t window;      /* action: window_size */
+  int32_t norm;        /* apply (val-mean)/var */
+  int32_t _pad;
+  double mean, var;
+} fw_obs_var_t;
+
+typedef struct {
+  int32_t sv;          /* fw_sv id of the controlled state */
+  int32_t cls;         /* 0 constant, 1 linear, 2 sinusoidal, 3 compensate (fixed_wing.py:933-991) */
+  int32_t wrap;        /* PyFly Variable.wrap of that state */
+  int32_t has_delta, has_bound, to_radians;
+  double low, high, delta, bound;                 /* already in radians when to_radians */
+  double slope_low, slope_high, amp_low, amp_high, period_low, period_high;   /* raw config units */
+} fw_target_t;
+
+typedef struct {
+  int32_t cls;         /* 0 action, 1 state, 2 success, 3 step, 4 goal */
+  int32_t type;        /* action: 0 value 1 delta 2 bound | state: 0 value 1 error 2 int_error | goal: 0 per_state 1 all */
+  int32_t fclass;      /* 0 linear, 1 exponential, 2 quadratic */
+  int32_t ref;         /* state.value: fw_sv id ; state.error/int_error: target index */
+  int32_t window, shaping, has_max, value_timesteps;
+  double scaling, max, sign, value;
+} fw_factor_t;
+
+/* Flat configuration, compiled on the host from the reference's JSON files (config.py) */
+/* simulator half: what PyFly holds (passed to the dynamics kernel as a __grid_constant__ parameter) */
+typedef struct {
+  double dt, rho, g;
+  double rtol, atol;              /* scipy RK45 defaults 1e-3 / 1e-6 */
+  double mass, S_wing, b, c, S_prop, k_motor, k_T_P, k_Omega, C_prop, e, M, a_0, ar;
+  double C_L_0, C_L_alpha, C_L_q, C_L_delta_e;
+  double C_D_p, C_D_0, C_D_alpha1, C_D_alpha2, C_D_beta1, C_D_beta2, C_D_q, C_D_delta_e;
+  double C_m_0, C_m_alpha, C_m_q, C_m_delta_e, C_m_fp;
+  double C_Y_0, C_Y_beta, C_Y_p, C_Y_r, C_Y_delta_a, C_Y_delta_r;
+  double C_l_0, C_l_beta, C_l_p, C_l_r, C_l_delta_a, C_l_delta_r;
+  double C_n_0, C_n_beta, C_n_p, C_n_r, C_n_delta_a, C_n_delta_r;
+  double gammas[9];
+  double Jy;
+  int32_t drag_model;             /* 0 induced (1-sigma)CL^2/(pi e AR) + flat plate, 1 polynomial */
+  int32_t turbulence;             /* Dryden gusts on */
+  int32_t wind_enabled;           /* steady wind may be non-zero */
+  int32_t _pad0;
+  double wind_mag_min, wind_mag_max;
+  double turb_noise_scale;        /* sqrt(pi/dt) */
+  fw_filter_t filt[FW_N_FILT];
+  fw_var_t var[FW_N_SV];
+  double act_coef[FW_N_ACT][6];   /* per dynamics actuator (elevon_l, elevon_r, throttle): c00 c01 c02 c10 c11 c12 */
+  double act_dot_max[FW_N_ACT];
+  int32_t act_has_dot_max[FW_N_ACT];
+  int32_t _pad1;
+  /* action scaling happens at the head of the dynamics kernel (fixed_wing.py:349-354,439-459) */
+  int32_t scale_actions, has_scale_low, has_scale_high, _pad2;
+  double scale_low, scale_high;
+  double act_to_low[FW_N_ACT], act_to_high[FW_N_ACT];
+} fw_sim_t;
+
+/* env half: what FixedWingAircraft holds (passed to the env/reset kernels) */
+typedef struct {
+  int32_t steps_max, integration_window;
+  int32_t obs_len, obs_step, obs_nvar, obs_shape, obs_norm, obs_noise;
+  double obs_noise_mean, obs_noise_std;
+  fw_obs_var_t obs[FW_MAX_OBS_VARS];
+  int32_t has_bounds, _pad3;
+  double bounds_min[FW_N_ACT], bounds_max[FW_N_ACT];
+  int32_t n_targets, resample_every, streak_req, on_success;   /* on_success: 0 none, 1 done, 2 new */
+  double streak_fraction;
+  fw_target_t tgt[FW_MAX_TARGETS];
+  int32_t n_factors, potential, step_fail_timesteps, n_terms;
+  double step_fail_value;
+  int32_t term_fclass[FW_N_FCLASS];
+  double term_weight[FW_N_FCLASS];
+  fw_factor_t fac[FW_MAX_FACTORS];
+} fw_env_t;
+
+typedef struct {
+  int32_t abi_version;
+  int32_t precision;              /* 0 = fp64 dynamics (parity mode), 1 = fp32 dynamics (opt-in) */
+  fw_sim_t sim;
+  fw_env_t env;
+} fw_config_t;
+
+typedef struct {
+  uint64_t env_steps;        /* env steps executed since creation / last reset of counters */
+  uint64_t attempts;         /* dopri5 step attempts (k summed over env steps) */
+  uint64_t accepted;         /* accepted dopri5 steps */
+  uint64_t warp_max_attempts;/* sum over warps and env steps of the per-warp max k (divergence cost, in warp-attempts) */
+  uint64_t warp_steps;       /* number of (warp, env-step) pairs counted above */
+  uint64_t failures;         /* env steps that ended in a constraint failure */
+  uint64_t resets;           /* auto + explicit episode resets */
+  uint64_t rhs_evals;        /* RHS evaluations = 2*env_steps + 6*attempts */
+} fw_counters_t;
+
+typedef struct fw_handle_s* fw_handle;
+
+/* Handle lifetime.  Replaces FixedWingAircraft.__init__ (fixed_wing.py:14-212) x n_envs; global_env_offset makes
+ * RNG streams sharding-invariant. */
+int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset, int device, fw_handle* out);
+int fw_destroy(fw_handle h);
+const char* fw_last_error(void);
+int fw_abi_version(void);
+int64_t fw_config_sizeof(void);   /* sizeof(fw_config_t) as compiled, checked by the ctypes mirror */
+
+/* Replaces FixedWingAircraft.seed (fixed_wing.py:214-222): Philox key for every env of the handle. */
+int fw_seed(fw_handle h, uint64_t seed);
+
+/* Replace the compiled configuration (set_curriculum_level / set_attr paths, fixed_wing.py:224-285). */
+int fw_set_config(fw_handle h, const fw_config_t* cfg);
+
+/* Replaces FixedWingAircraft.reset (fixed_wing.py:287-336) for the envs selected by `mask` (device uint8[N], NULL =
+ * all).  init_state: optional device double [FW_N_SV, N] (SoA; NaN entries = "sample it"), init_target: optional
+ * device double [FW_MAX_TARGETS, N] (NaN = sampled target kept).  obs_out: device float [N, obs_dim] (rows of the
+ * envs not selected are left untouched); obs64_out: optional device double copy for parity checks. */
+int fw_reset(fw_handle h, const uint8_t* mask, const double* init_state, const double* init_target,
+             float* obs_out, double* obs64_out, void* stream);
+
+/* Replaces FixedWingAircraft.step (fixed_wing.py:338-437) + SubprocVecEnv auto-reset for all N envs.
+ * actions: device [N, FW_N_ACT] row-major, float (actions_f64 = 0) or double (actions_f64 = 1).
+ * obs_out float [N, obs_dim] (post-reset observation for envs that finished), rew_out float [N], done_out uint8 [N],
+ * term_out int32 [N] (FW_TERM_*).  Optional (may be NULL): obs64_out / rew64_out double copies; term_obs_out float
+ * [N, obs_dim] terminal observation of finished envs (rows of others untouched). auto_reset = 0 leaves finished envs
+ * un-reset (single-env facade semantics). */
+int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, float* rew_out, uint8_t* done_out,
+            int32_t* term_out, double* obs64_out, double* rew64_out, float* term_obs_out, int auto_reset,
+            void* stream);
+
+/* Full per-env state for parity, checkpoint/resume: device double [fw_state_rows(h), N]. */
+int64_t fw_state_rows(fw_handle h);
+int fw_get_state(fw_handle h, double* out, void* stream);
+int fw_set_state(fw_handle h, const double* in, void* stream);
+/* name of row r of the state matrix ("q0", "omega_p", "steps_count", ...), NULL when out of range */
+const char* fw_state_row_name(fw_handle h, int64_t r);
+
+/* Per-env dopri5 attempt count of the last step: device int32 [N]. */
+int fw_last_attempts(fw_handle h, int32_t* out, void* stream);
+
+/* Counters (synchronises the stream it was last used on). */
+int fw_counters(fw_handle h, fw_counters_t* out);
+int fw_reset_counters(fw_handle h);
+
+/* Episode metric sums for a caller-side NCCL all-reduce: out double [FW_N_METRIC_SUMS] on the host. */
+#define FW_N_METRIC_SUMS 8   /* episodes, successes, sum_return, sum_length, failures, steps_term, success_term, goal_steps */
+int fw_metric_sums(fw_handle h, double* out_host);
+
+/* Introspection */
+int64_t fw_num_envs(fw_handle h);
+int fw_obs_dim(fw_handle h);
+
+/* Micro-benchmark: sustained DFMA throughput of this GPU in FLOP/s (roofline denominator, bench.py). */
+int fw_dfma_peak(int device, double* flops_out, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FWGYM_H */

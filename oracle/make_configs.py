@@ -1,0 +1,50 @@
+"""Regenerate the env-config data files under fixed-wing-gym_b200/params/ from the reference's JSON configs and the
+scenario fixture under tests/golden/ from its test set.  Run in the build container only (/root/reference does not
+exist on the GPU box).  These are DATA (the reference's config-JSON surface, README.md:21-160), re-serialised
+compactly with sorted keys; no reference source code is copied.
+
+    python -m oracle.make_configs
+"""
+import json
+import os
+
+import numpy as np
+
+REF = os.environ.get("FWGYM_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+PARAMS = os.path.join(HERE, "..", "fixed-wing-gym_b200", "params")
+GOLDEN = os.path.join(HERE, "..", "tests", "golden")
+
+SOURCES = {
+    "fixed_wing_config.json": "gym_fixed_wing/fixed_wing_config.json",
+    "fixed_wing_config_dev.json": "gym_fixed_wing/fixed_wing_config_dev.json",
+    "fixed_wing_config_examples.json": "gym_fixed_wing/examples/fixed_wing_config.json",
+    "fixed_wing_config_cnn.json": "gym_fixed_wing/examples/models/cnn_controller/fixed_wing_config.json",
+}
+
+
+def main():
+    for out, src in SOURCES.items():
+        with open(os.path.join(REF, src)) as f:
+            cfg = json.load(f)
+        cfg.pop("render", None)   # visualisation is out of scope
+        with open(os.path.join(PARAMS, out), "w") as f:
+            json.dump(cfg, f, sort_keys=True, separators=(",", ":"))
+            f.write("\n")
+    ex = os.path.join(REF, "gym_fixed_wing", "examples")
+    scen = np.load(os.path.join(ex, "test_sets", "test_set_wind_none_step20-20-3.npy"), allow_pickle=True)
+    skeys = sorted(scen[0]["state"].keys())
+    tkeys = sorted(scen[0]["target"].keys())
+    np.savez_compressed(os.path.join(GOLDEN, "test_set_wind_none.npz"),
+                        state_keys=np.array(skeys), target_keys=np.array(tkeys),
+                        state=np.array([[s["state"][k] for k in skeys] for s in scen]),
+                        target=np.array([[s["target"][k] for k in tkeys] for s in scen]))
+    res = np.load(os.path.join(ex, "evaluations", "eval_res_PID_none.npy"), allow_pickle=True).item()
+    lens = np.array([len(r) for r in res["rewards"]])
+    flat = np.concatenate([np.asarray(r, dtype=np.float64) for r in res["rewards"]])
+    np.savez_compressed(os.path.join(GOLDEN, "eval_res_PID_none_rewards.npz"), lengths=lens, rewards=flat)
+    print("wrote", sorted(SOURCES), "and golden test set / PID reward trace")
+
+
+if __name__ == "__main__":
+    main()
