@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/s of the batched FixedWingAircraft.step hot path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA kernels), one rank per GPU
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+Workload (config.workload): BASELINE.json configs[2] — 65536 envs per GPU, Dryden turbulence (moderate) + observation
+noise, fp64 dopri5 — weak scaling over GPUs, no collective on the step path (NCCL only all-reduces the episode
+metric sums and the timing).  A "step" is one VecEnv.step of every env of the rank (dynamics kernel + env kernel).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 65536
+WORKLOAD = "65536 envs/GPU, fixed_wing_config.json, Dryden turbulence moderate + obs noise std 0.1, fp64 dopri5 (BASELINE configs[2])"
+CONFIG_KW = {"observation": {"noise": {"mean": 0, "var": 0.1}}}
+SIM_KW = {"turbulence": True, "turbulence_intensity": "moderate"}
+# algorithmic work per env step: F = 1080 + 3660 * k flops, k = dopri5 attempts (counted on device)
+F_FIXED, F_ATTEMPT = 1080.0, 3660.0
+ENV_BYTES_PER_STEP = 480.0   # env kernel algorithmic bytes per env step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="fwgym", choices=["fwgym", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_worker(args):
+    """One host core: step one oracle env (restated reference path) with U(-1,1) actions for `n_steps` steps."""
+    wid, n_steps, warm = args
+    import numpy as np
+    from oracle import harness
+    env = harness.make_env("restated", harness.config_path(), CONFIG_KW, SIM_KW)
+    run = harness.OracleRunner(env, seed=1234, env_id=wid)
+    run.reset()
+    rng = np.random.RandomState(wid)
+    for _ in range(warm):
+        run.step(rng.uniform(-1, 1, 3))
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        run.step(rng.uniform(-1, 1, 3))
+    dt = time.perf_counter() - t0
+    k = sum((n - 2) // 6 for n in run.nfev[warm:])
+    return n_steps, dt, k
+
+
+def cpu_reference_rate(seconds=None, cores=None, n_steps=None, warm=5):
+    """Time the CPU oracle (kind "port": the restated reference path — /root/reference and PyFly do not exist on the
+    GPU box) with one process per host core, the SubprocVecEnv topology of train_rl_controller.py:223 (without its
+    per-step pipe synchronisation, which only favours the CPU number)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    if n_steps is None:
+        n_steps = max(20, int(seconds * 150.0))   # ~150 env-steps/s/core first guess sizes the bounded sample
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(w, n_steps, warm) for w in range(cores)], chunksize=1)
+        wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return {"value": total / slowest, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d procs x %d env steps of the bench workload, restated FixedWingAircraft+PyFly oracle "
+                      "(scipy solve_ivp RK45), U(-1,1) actions; %.1f s wall; mean dopri5 attempts/step %.2f"
+                      % (cores, n_steps, wall, sum(r[2] for r in res) / max(1, total))}, slowest
+
+
+CPU_STEPS_PER_UNIT = 16   # reference arm: one bench "step" = every host core advances its env 16 env steps
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    base, slowest = cpu_reference_rate(cores=cores, n_steps=a.steps * CPU_STEPS_PER_UNIT,
+                                       warm=max(3, a.warmup) * CPU_STEPS_PER_UNIT)
+    line = {"impl": "reference", "metric": "env-steps/s", "value": base["value"], "unit": "env-steps/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * slowest / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD + " — bounded CPU sample: one env per host core, %d env steps per bench step"
+                       % CPU_STEPS_PER_UNIT},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, p[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_gpu_arm(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        a.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from fwgym_b200 import FixedWingVecEnv, _capi
+    from oracle import harness   # only for the config path helper + cpu_baseline leg
+
+    n = a.envs_per_gpu
+    vec = FixedWingVecEnv(harness.config_path(), n, device=dev, config_kw=CONFIG_KW, sim_config_kw=SIM_KW,
+                          seed=20261017, env_offset=rank * n)
+    vec.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1 + rank)
+    total = a.warmup + a.steps
+    # synthetic policy output: i.i.d. U(-1,1) actions, a fresh batch per step, resident in HBM before timing
+    actions = torch.rand((total, n, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(a.warmup):
+        vec.step_tensors(actions[i])
+    vec.reset_counters()
+    vec.set_profiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(a.steps):
+        flush.zero_()                       # L2 flush between timed iterations (not inside the timed interval)
+        ev[k][0].record()
+        vec.step_tensors(actions[a.warmup + k])
+        ev[k][1].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    dyn_ms, env_ms, prof_steps = vec.profile()
+    vec.set_profiling(False)
+    ctr = vec.counters()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the public API with HOST buffers: pinned actions in, obs/reward/done out, per step ----
+    h_act = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    h_obs = torch.empty((n, vec.obs_dim), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_act = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    host_actions = (torch.rand((a.steps + 2, n, 3)) * 2 - 1)
+    e2e_steps = a.steps
+
+    def e2e_step(i):
+        h_act.copy_(host_actions[i])
+        d_act.copy_(h_act, non_blocking=True)
+        obs, rew, done, _ = vec.step_tensors(d_act)
+        h_obs.copy_(obs.view(n, -1), non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_done.copy_(done, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(2 + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    tt = torch.tensor([ms, e2e_s * 1e3, dyn_ms, env_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([ctr["env_steps"], ctr["attempts"], ctr["warp_max_attempts"], ctr["warp_steps"],
+                        ctr["failures"], ctr["resets"]], dtype=torch.float64, device=dev)
+    msum = torch.tensor(vec.metric_sums(), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)     # time = max over ranks
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(msum, op=dist.ReduceOp.SUM)   # the only data-path collective: episode metric sums
+    ms, e2e_ms, dyn_ms, env_ms, wall_ms = tt.tolist()
+    env_steps, attempts, wmax, wsteps, failures, resets = cnt.tolist()
+    if rank == 0:
+        total_env_steps = float(n) * a.steps * world
+        value = total_env_steps / (ms * 1e-3)
+        k_mean = attempts / max(1.0, env_steps)
+        # roofline of the dominant kernel (dynamics, FP64 pipe): algorithmic flops of ONE rank / its kernel time
+        fl = ctypes.c_double()
+        pk_ms = ctypes.c_double()
+        _capi.check(_capi.lib().fw_dfma_peak(local, ctypes.byref(fl), ctypes.byref(pk_ms)))
+        flops_rank = (F_FIXED * env_steps + F_ATTEMPT * attempts) / world
+        achieved = flops_rank / (dyn_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dyn_kernel_dram_bytes_per_launch")
+        line = {
+            "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "actions": "i.i.d. U(-1,1)^3 per step",
+                       "l2": "256 MiB memset between timed steps; per-step CUDA events summed",
+                       "parallelism": "env-sharded x%d, no step-path collective" % world},
+            "clocks": clocks,
+            "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": n * 3 * 4, "d2h_bytes_per_step": n * (vec.obs_dim * 4 + 4 + 1)},
+            "gpu_launches": int(2 * a.steps),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fl.value / 1e12, "unit": "TFLOP/s",
+                         "frac": achieved / (fl.value / 1e12), "traffic": traffic,
+                         "peak_source": "DFMA micro-benchmark run in this process (fw_dfma_peak); MEASURED_PEAKS.json "
+                                        "has no FP64 entry",
+                         "kernel": "fw_dyn_kernel<double>", "kernel_ms_per_launch": dyn_ms / max(1, prof_steps),
+                         "kernel_share_of_step": dyn_ms / max(1e-9, dyn_ms + env_ms),
+                         "flops_per_env_step": "1080 + 3660*k, k = dopri5 attempts counted on device",
+                         "mean_attempts_per_env_step": k_mean,
+                         "warp_divergence": {"mean_warp_max_attempts": wmax / max(1.0, wsteps),
+                                             "lane_efficiency": attempts / max(1.0, 32.0 * wmax)}},
+            "env_kernel": {"bound": "hbm", "ms_per_launch": env_ms / max(1, prof_steps),
+                           "achieved_gbs": ENV_BYTES_PER_STEP * n / max(1e-9, env_ms / max(1, prof_steps) * 1e-3) / 1e9,
+                           "peak_gbs": _measured_peaks().get("hbm_gbs")},
+            "wall_ms_timed_region": wall_ms,
+            "episodes": {"finished": msum[0].item(), "failures": msum[4].item(), "resets": resets},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_rate(a.cpu_baseline_seconds)[0]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f)
+    return {"hbm_gbs": 6650.0, "source": "fallback"}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)

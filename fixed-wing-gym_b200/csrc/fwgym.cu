@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <new>
+#include <vector>
 #include "../../include/fwgym.h"
 #include "layout.h"
 #include "philox.cuh"
@@ -33,6 +34,8 @@ struct fw_handle_s {
   unsigned long long* ctr;   // CTR_N
   double* msum;              // FW_N_METRIC_SUMS
   cudaStream_t last_stream;
+  int profiling;
+  std::vector<cudaEvent_t> ev;   // 3 events per profiled step: before dyn, between, after env
 };
 
 static thread_local char g_err[512] = "";
@@ -459,6 +462,7 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   h->offset = global_env_offset;
   h->seed = 0;
   h->last_stream = nullptr;
+  h->profiling = 0;
   int rc = make_layout(h->cfg, n_envs, h->L);
   if (rc) { delete h; return rc; }
   const size_t db = (size_t)h->L.d_rows * h->L.stride * sizeof(double);
@@ -484,6 +488,7 @@ int fw_destroy(fw_handle h) {
   if (!h) return FW_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d); cudaFree(h->i); cudaFree(h->ctr); cudaFree(h->msum);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
   return FW_OK;
 }
@@ -555,6 +560,11 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
   FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, h->ctr};
   const int dgrid = (int)((h->n + FW_DYN_BLOCK - 1) / FW_DYN_BLOCK);
+  cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
+  if (h->profiling) {
+    for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
+    CK(cudaEventRecord(pe[0], s));
+  }
   if (h->cfg.precision == 0) {
     const int smem = 6 * FW_N_ODE * FW_DYN_BLOCK * (int)sizeof(double);
     fw_dyn_kernel<double><<<dgrid, FW_DYN_BLOCK, smem, s>>>(h->cfg.sim, da);
@@ -563,12 +573,38 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
     fw_dyn_kernel<float><<<dgrid, FW_DYN_BLOCK, smem, s>>>(h->cfg.sim, da);
   }
   CK(cudaGetLastError());
+  if (h->profiling) CK(cudaEventRecord(pe[1], s));
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
                term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum};
   const int egrid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
   fw_env_kernel<<<egrid, FW_ENV_BLOCK, 0, s>>>(h->cfg.env, h->cfg.sim, h->L, ea);
   CK(cudaGetLastError());
+  if (h->profiling) CK(cudaEventRecord(pe[2], s));
   h->last_stream = s;
+  return FW_OK;
+}
+
+int fw_set_profiling(fw_handle h, int on) {
+  if (!h) return fail(FW_ERR_ARG, "null handle");
+  h->profiling = on;
+  return FW_OK;
+}
+
+int fw_profile(fw_handle h, double* dyn_ms, double* env_ms, int64_t* steps) {
+  if (!h || !dyn_ms || !env_ms || !steps) return fail(FW_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->last_stream));
+  double d = 0, e = 0;
+  const size_t n = h->ev.size() / 3;
+  for (size_t k = 0; k < n; ++k) {
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, h->ev[3 * k], h->ev[3 * k + 1]));
+    CK(cudaEventElapsedTime(&b, h->ev[3 * k + 1], h->ev[3 * k + 2]));
+    d += a; e += b;
+  }
+  for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
+  h->ev.clear();
+  *dyn_ms = d; *env_ms = e; *steps = (int64_t)n;
   return FW_OK;
 }
 

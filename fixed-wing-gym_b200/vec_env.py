@@ -255,6 +255,15 @@ class FixedWingVecEnv:
     def reset_counters(self):
         _capi.check(self._lib.fw_reset_counters(self._h))
 
+    def set_profiling(self, on=True):
+        _capi.check(self._lib.fw_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self):
+        """-> (dynamics kernel ms, env kernel ms, steps) summed since the last call (synchronises)."""
+        d, e, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        _capi.check(self._lib.fw_profile(self._h, ctypes.byref(d), ctypes.byref(e), ctypes.byref(n)))
+        return d.value, e.value, n.value
+
     METRIC_SUM_NAMES = ("episodes", "successes", "sum_return", "sum_length", "failures", "steps_term", "success_term",
                         "goal_steps")
 

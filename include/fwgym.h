@@ -218,6 +218,11 @@ int fw_last_attempts(fw_handle h, int32_t* out, void* stream);
 int fw_counters(fw_handle h, fw_counters_t* out);
 int fw_reset_counters(fw_handle h);
 
+/* Per-kernel device timing: when on, every fw_step records CUDA events around the dynamics and env kernels on the
+ * launching stream; fw_profile() synchronises, returns the summed milliseconds and the number of steps, and clears. */
+int fw_set_profiling(fw_handle h, int on);
+int fw_profile(fw_handle h, double* dyn_ms, double* env_ms, int64_t* steps);
+
 /* Episode metric sums for a caller-side NCCL all-reduce: out double [FW_N_METRIC_SUMS] on the host. */
 #define FW_N_METRIC_SUMS 8   /* episodes, successes, sum_return, sum_length, failures, steps_term, success_term, goal_steps */
 int fw_metric_sums(fw_handle h, double* out_host);

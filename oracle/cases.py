@@ -1,0 +1,44 @@
+"""Parity cases shared by oracle/make_golden.py and tests/: (config file, env overrides, simulator overrides, envs,
+steps, action scale).  They cover BASELINE.json configs 1-5 at oracle-sized N plus the edge paths the reference
+exercises (failure, success done/new, resample, history > 1, integrator, potential reward)."""
+
+CASES = {
+    # configs[0]/[1]: default config, turbulence off
+    "default": dict(config="fixed_wing_config.json", config_kw=None, sim_kw={"turbulence": False}, n=6, steps=40, amp=1.2),
+    # configs[2]: turbulence + observation noise
+    "turb_noise": dict(config="fixed_wing_config.json", config_kw={"observation": {"noise": {"mean": 0, "var": 0.1}}},
+                       sim_kw={"turbulence": True, "turbulence_intensity": "moderate"}, n=6, steps=40, amp=1.0),
+    # configs[3]: examples config (relative targets, no noise key, 12 obs)
+    "examples": dict(config="fixed_wing_config_examples.json", config_kw=None,
+                     sim_kw={"turbulence": True, "turbulence_intensity": "severe"}, n=4, steps=30, amp=1.0),
+    # configs[4]: dev config + history/integrator/resample overrides
+    "dev_history": dict(config="fixed_wing_config_dev.json",
+                        config_kw={"integration_window": 10, "steps_max": 45,
+                                   "observation": {"length": 5, "step": 1, "shape": "matrix",
+                                                   "states": {6: {"value": "integrator"}, 7: {"value": "relative"}}},
+                                   "target": {"resample_every": 20},
+                                   "reward": {"factors": {1: {"type": "int_error"}}}},
+                        sim_kw={"turbulence": False}, n=4, steps=100, amp=0.5),
+    "norm_step2": dict(config="fixed_wing_config.json",
+                      config_kw={"observation": {"length": 3, "step": 2, "normalize": True}, "steps_max": 30},
+                      sim_kw={"turbulence": False}, n=4, steps=70, amp=1.3),
+    # success streak: loose bounds so the streak fires; on_success new resamples, done terminates
+    "success_new": dict(config="fixed_wing_config.json",
+                        config_kw={"target": {"success_streak_req": 5, "success_streak_fraction": 0.6, "on_success": "new",
+                                              "states": {0: {"bound": 120}, 1: {"bound": 60}, 2: {"bound": 20}}},
+                                   "reward": {"form": "potential"}},
+                        sim_kw={"turbulence": False}, n=4, steps=40, amp=1.0),
+    "success_done": dict(config="fixed_wing_config_examples.json",
+                         config_kw={"steps_max": 60, "target": {"success_streak_req": 8, "success_streak_fraction": 1,
+                                                                "on_success": "done",
+                                                                "states": {0: {"bound": 150}, 1: {"bound": 80}, 2: {"bound": 25}}},
+                                    "reward": {"terms": {0: {"function_class": "exponential", "weight": 0.7}},
+                                               "factors": {i: {"function_class": "exponential"} for i in range(5)}}},
+                         sim_kw={"turbulence": False}, n=4, steps=40, amp=1.0),
+    # constraint failure path: tight omega constraints make PyFly raise inside the integration
+    "failure": dict(config="fixed_wing_config.json",
+                    config_kw={"simulator": {"states": {6: {"constraint_min": -70, "constraint_max": 70},
+                                                        7: {"constraint_min": -70, "constraint_max": 70},
+                                                        8: {"constraint_min": -70, "constraint_max": 70}}}},
+                    sim_kw={"turbulence": False}, n=6, steps=60, amp=1.5),
+}

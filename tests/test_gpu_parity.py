@@ -1,0 +1,155 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI / VecEnv) against (a) the committed golden fixtures
+generated from the UNMODIFIED reference env file, (b) the live CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): bit-exact for integer / indexing state (done flags, dopri5 attempt counts,
+termination codes, step counters); floating point <= 1e-9 relative per step in fp64 (observations, rewards and the
+27 simulator state values, relative to max(|ref|, 1e-3)); <= 1e-4 relative over a 100-step turbulence-off rollout.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import harness
+from oracle.cases import CASES
+from oracle.make_golden import SEED
+import parity_utils as pu
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-9
+
+
+def make_vec(c, n=None, seed=SEED, **kw):
+    from fwgym_b200 import FixedWingVecEnv
+    return FixedWingVecEnv(harness.config_path(c["config"]), n or c["n"], config_kw=c["config_kw"],
+                           sim_config_kw=c["sim_kw"], seed=seed, keep_terminal_obs=True, **kw)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_fixture(built_lib, name):
+    """CUDA vs fixtures produced by the reference's own fixed_wing.py (oracle/make_golden.py)."""
+    c = CASES[name]
+    g = np.load(os.path.join(GOLDEN, "case_%s.npz" % name))
+    vec = make_vec(c)
+    vec.enable_f64_outputs(True)
+    vec.reset()
+    assert pu.rel_err(vec._obs64.cpu().numpy(), g["obs"][0], 1e-3).max() <= TOL
+    worst = dict(obs=0.0, rew=0.0, state=0.0, term_obs=0.0)
+    for t, a in enumerate(g["actions"]):
+        _, _, done, _ = vec.step_tensors(torch.as_tensor(a, dtype=torch.float64, device=vec.device))
+        done = done.cpu().numpy().astype(bool)
+        assert np.array_equal(done, g["done"][t]), "done flags differ at step %d" % t
+        live = ~done
+        k = vec.last_attempts().cpu().numpy()
+        assert np.array_equal(k[live], g["k"][t][live]), "dopri5 attempt counts differ at step %d" % t
+        worst["obs"] = max(worst["obs"], pu.rel_err(vec._obs64.cpu().numpy(), g["obs"][t + 1], 1e-3).max())
+        worst["rew"] = max(worst["rew"], pu.rel_err(vec._rew64.cpu().numpy(), g["rew"][t], 1e-3).max())
+        worst["state"] = max(worst["state"], pu.rel_err(pu.gpu_state(vec), g["state"][t], 1e-3).max())
+        if done.any():
+            tobs = vec._term_obs.cpu().numpy()[done]
+            worst["term_obs"] = max(worst["term_obs"], pu.rel_err(tobs, g["term_obs"][t][done], 1e-3).max())
+    assert worst["obs"] <= TOL and worst["rew"] <= TOL and worst["state"] <= TOL, worst
+    assert worst["term_obs"] <= 1e-6, worst   # terminal observations are float32 on the device
+    vec.close()
+
+
+def test_live_oracle_64_envs(built_lib):
+    """BASELINE configs[1] at an oracle-sized N: per-step parity on identical states, actions and seeds."""
+    c = CASES["default"]
+    n, steps = 64, 12
+    vec = make_vec(c, n=n, seed=5)
+    orc = pu.make_oracles(n, harness.config_path(c["config"]), c["config_kw"], c["sim_kw"], 5)
+    acts = np.random.RandomState(3).uniform(-1, 1, (steps, n, 3))
+    out = pu.run_parity(vec, orc, acts)
+    assert out["done_mismatch"] == 0 and out["k_mismatch"] == 0
+    assert max(out["obs"]) <= TOL and max(out["rew"]) <= TOL and max(out["state"]) <= TOL, out
+
+
+def test_rollout_100_steps(built_lib):
+    """<= 1e-4 relative over a 100-step turbulence-off rollout."""
+    c = CASES["default"]
+    n = 8
+    vec = make_vec(c, n=n, seed=9)
+    orc = pu.make_oracles(n, harness.config_path(c["config"]), c["config_kw"], c["sim_kw"], 9)
+    acts = np.random.RandomState(4).uniform(-1, 1, (100, n, 3))
+    out = pu.run_parity(vec, orc, acts)
+    assert out["done_mismatch"] == 0
+    assert out["state"][-1] <= 1e-4 and max(out["obs"]) <= 1e-4, (out["state"][-1], max(out["obs"]))
+
+
+def test_scenario_injection(built_lib):
+    """reset(state=, target=) with the reference's test-set scenarios (evaluate_controller.py:119)."""
+    ts = np.load(os.path.join(GOLDEN, "test_set_wind_none.npz"))
+    skeys, tkeys = list(ts["state_keys"]), list(ts["target_keys"])
+    n = 8
+    c = dict(config="fixed_wing_config_examples.json", config_kw={"action": {"scale_space": False}},
+             sim_kw={"turbulence": False, "turbulence_intensity": "none"})
+    vec = make_vec(c, n=n, seed=1)
+    vec.enable_f64_outputs(True)
+    state = {k: ts["state"][:n, i] for i, k in enumerate(skeys)}
+    target = {k: ts["target"][:n, i] for i, k in enumerate(tkeys)}
+    vec.reset(state=state, target=target)
+    orc = pu.make_oracles(n, harness.config_path(c["config"]), c["config_kw"], c["sim_kw"], 1)
+    obs_o = np.stack([o.reset(state={k: float(state[k][i]) for k in skeys}, target={k: float(target[k][i]) for k in tkeys})
+                      for i, o in enumerate(orc)])
+    assert pu.rel_err(vec._obs64.cpu().numpy(), obs_o, 1e-3).max() <= TOL
+    acts = np.random.RandomState(8).uniform(-0.4, 0.4, (10, n, 3))
+    acts[:, :, 2] = np.abs(acts[:, :, 2])
+    for a in acts:
+        vec.step_tensors(torch.as_tensor(a, dtype=torch.float64, device=vec.device))
+        res = [o.step(a[i]) for i, o in enumerate(orc)]
+        assert pu.rel_err(vec._obs64.cpu().numpy(), np.stack([r[0] for r in res]), 1e-3).max() <= TOL
+        assert pu.rel_err(vec._rew64.cpu().numpy(), np.array([r[1] for r in res]), 1e-3).max() <= TOL
+
+
+def test_sharding_invariance(built_lib):
+    """RNG is keyed by the GLOBAL env id: one handle of 32 envs == two handles of 16 with offsets 0 and 16, bitwise."""
+    c = CASES["turb_noise"]
+    acts = torch.rand((15, 32, 3), dtype=torch.float64, device="cuda") * 2 - 1
+    whole = make_vec(c, n=32, seed=21)
+    a, b = make_vec(c, n=16, seed=21, env_offset=0), make_vec(c, n=16, seed=21, env_offset=16)
+    ow = whole.reset().clone()
+    oa, ob = a.reset().clone(), b.reset().clone()
+    assert torch.equal(ow, torch.cat([oa, ob]))
+    for t in range(15):
+        ow, rw, dw, _ = whole.step_tensors(acts[t])
+        oa, ra, da, _ = a.step_tensors(acts[t, :16].contiguous())
+        ob, rb, db, _ = b.step_tensors(acts[t, 16:].contiguous())
+        assert torch.equal(ow, torch.cat([oa, ob])) and torch.equal(rw, torch.cat([ra, rb]))
+    assert torch.equal(whole.get_state(), torch.cat([a.get_state(), b.get_state()], dim=1))
+
+
+def test_fp32_mode_reported(built_lib):
+    """Opt-in fp32 dynamics (stated separately from the fp64 parity bar): state error vs the fp64 oracle after 20
+    steps stays below 5e-3 relative; integer state (done flags) still matches."""
+    c = CASES["default"]
+    n = 8
+    vec = make_vec(c, n=n, seed=5, precision="fp32")
+    orc = pu.make_oracles(n, harness.config_path(c["config"]), c["config_kw"], c["sim_kw"], 5)
+    acts = np.random.RandomState(3).uniform(-1, 1, (20, n, 3))
+    out = pu.run_parity(vec, orc, acts)
+    print("fp32 mode: max rel state err over 20 steps %.3e, obs %.3e" % (max(out["state"]), max(out["obs"])))
+    assert out["done_mismatch"] == 0
+    assert max(out["state"]) < 5e-3
+
+
+def test_single_env_facade(built_lib):
+    """FixedWingAircraft facade (N=1): reference constructor / reset / step signatures and 4-tuple."""
+    from fwgym_b200 import FixedWingAircraft
+    env = FixedWingAircraft(harness.config_path(), sim_config_kw={"turbulence": False})
+    env.seed(3)
+    obs = env.reset()
+    assert obs.shape == (14,) and obs.dtype == np.float64
+    orc = pu.make_oracles(1, harness.config_path(), None, {"turbulence": False}, 3)[0]
+    orc.auto_reset = False
+    o0 = orc.reset()
+    assert pu.rel_err(obs, o0, 1e-3).max() <= TOL
+    for t in range(5):
+        a = np.array([0.1 * t, -0.2, 0.5])
+        obs, rew, done, info = env.step(a)
+        o, r, d, i = orc.step(a)
+        assert pu.rel_err(obs, o, 1e-3).max() <= TOL and abs(rew - r) <= TOL and done == d
+        assert set(info["target"]) == {"roll", "pitch", "Va"}
+    env.close()
