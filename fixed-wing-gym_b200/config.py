@@ -181,6 +181,11 @@ class CompiledConfig:
             v = self.state[n]
             if any(getattr(v, a) is not None for a in ("value_min", "value_max", "constraint_min", "constraint_max")):
                 raise ConfigError("value limits / constraints on attitude state %s are not supported" % n)
+        for n in ("position_n", "position_e", "position_d"):
+            v = self.state[n]
+            if any(getattr(v, a) is not None for a in ("value_min", "value_max", "constraint_min", "constraint_max")) or v.wrap:
+                raise ConfigError("value limits / constraints on %s are not supported (position stage states are "
+                                  "never formed in the integrator)" % n)
         if self.cfg["reward"].get("randomize_scaling", False):
             raise ConfigError("reward.randomize_scaling is not supported yet (SURVEY §8f)")
         for key in self.cfg["simulator"]:
@@ -339,6 +344,9 @@ class CompiledConfig:
         for i, v in enumerate(gam):
             s.gammas[i] = float(v)
         s.Jy = float(I[1, 1])
+        s.inv_Jy = 1.0 / float(I[1, 1])
+        s.inv_mass = 1.0 / float(P["mass"])
+        s.inv_pi_e_ar = 1.0 / (np.pi * P["e"] * s.ar)
         s.drag_model = {"induced": 0, "polynomial": 1}[sc.get("drag_model", "induced")]
         s.turbulence = 1 if sc["turbulence"] else 0
         s.wind_mag_min, s.wind_mag_max = sc["wind_magnitude_min"], sc["wind_magnitude_max"]

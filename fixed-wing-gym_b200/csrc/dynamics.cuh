@@ -38,6 +38,7 @@ template <> struct FwMath<float> {
 template <typename T>
 __device__ __forceinline__ T fw_cond(const fw_var_t& v, int sv, T x, int& fail) {
   const uint32_t fl = v.flags;
+  if (fl == 0u) return x;
   if ((fl & FW_VC_CMIN) && x < (T)v.cmin && !fail) fail = FW_TERM_FAIL_BASE + sv;
   if ((fl & FW_VC_CMAX) && x > (T)v.cmax && !fail) fail = FW_TERM_FAIL_BASE + sv;
   if (fl & FW_VC_VMIN) x = x < (T)v.vmin ? (T)v.vmin : x;
@@ -70,9 +71,7 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
   const T p = fw_cond<T>(P.var[FW_SV_OMEGA_P], FW_SV_OMEGA_P, y[4], fail);
   const T q = fw_cond<T>(P.var[FW_SV_OMEGA_Q], FW_SV_OMEGA_Q, y[5], fail);
   const T r = fw_cond<T>(P.var[FW_SV_OMEGA_R], FW_SV_OMEGA_R, y[6], fail);
-  (void)fw_cond<T>(P.var[FW_SV_POS_N], FW_SV_POS_N, y[7], fail);
-  (void)fw_cond<T>(P.var[FW_SV_POS_E], FW_SV_POS_E, y[8], fail);
-  (void)fw_cond<T>(P.var[FW_SV_POS_D], FW_SV_POS_D, y[9], fail);
+  // position variables carry no limits (config.py rejects them): their stage states are never formed
   const T u = fw_cond<T>(P.var[FW_SV_VEL_U], FW_SV_VEL_U, y[10], fail);
   const T v = fw_cond<T>(P.var[FW_SV_VEL_V], FW_SV_VEL_V, y[11], fail);
   const T w = fw_cond<T>(P.var[FW_SV_VEL_W], FW_SV_VEL_W, y[12], fail);
@@ -87,8 +86,8 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
       const T m = (T)P.act_dot_max[i];
       ad[i] = ad[i] < -m ? -m : (ad[i] > m ? m : ad[i]);
     }
-  const T ail = fw_cond<T>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-er + el) / (T)2, fail);
-  const T elev = fw_cond<T>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (er + el) / (T)2, fail);
+  const T ail = fw_cond<T>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-er + el) * (T)0.5, fail);
+  const T elev = fw_cond<T>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (er + el) * (T)0.5, fail);
   const T rud = (T)0;
 
   // ---- airspeed factors (PyFly._calculate_airspeed_factors with the quaternion rotation) ----
@@ -104,10 +103,12 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
     ur -= in.gl[0]; vr -= in.gl[1]; wr -= in.gl[2];
     pa -= in.ga[0]; qa -= in.ga[1]; ra -= in.ga[2];
   }
-  T Va = Mt::sqrt_(ur * ur + vr * vr + wr * wr);
+  const T Va_raw = Mt::sqrt_(ur * ur + vr * vr + wr * wr);
+  T invVa = (T)1 / Va_raw;
   T alpha = Mt::atan2_(wr, ur);
-  T beta = Mt::asin_(vr / Va);
-  Va = fw_cond<T>(P.var[FW_SV_VA], FW_SV_VA, Va, fail);
+  T beta = Mt::asin_(vr * invVa);
+  const T Va = fw_cond<T>(P.var[FW_SV_VA], FW_SV_VA, Va_raw, fail);
+  if (Va != Va_raw) invVa = (T)1 / Va;   // value_min clip engaged (rare)
   alpha = fw_cond<T>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, fail);
   beta = fw_cond<T>(P.var[FW_SV_BETA], FW_SV_BETA, beta, fail);
 
@@ -127,12 +128,12 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
   Mt::sincos_(beta, &sb, &cb);
   const T sgn = alpha > 0 ? (T)1 : (alpha < 0 ? (T)-1 : (T)0);
   const T CL = (1 - sigma) * CLlin + sigma * (2 * sgn * sa * sa * ca);
-  const T inv2Va = (T)1 / (2 * Va);
+  const T inv2Va = (T)0.5 * invVa;
   const T c2Va = (T)P.c * inv2Va, b2Va = (T)P.b * inv2Va;
   const T lift = pre * (CL + (T)P.C_L_q * c2Va * qa + (T)P.C_L_delta_e * elev);
   T CDa;
   if (P.drag_model == 0)
-    CDa = (T)P.C_D_p + (1 - sigma) * CLlin * CLlin / ((T)CUDART_PI * (T)P.e * (T)P.ar) + sigma * (2 * sgn * sa * sa * sa);
+    CDa = (T)P.C_D_p + (1 - sigma) * CLlin * CLlin * (T)P.inv_pi_e_ar + sigma * (2 * sgn * sa * sa * sa);
   else
     CDa = (T)P.C_D_0 + (T)P.C_D_alpha1 * alpha + (T)P.C_D_alpha2 * alpha * alpha;
   const T CDb = (T)P.C_D_beta1 * beta + (T)P.C_D_beta2 * beta * beta;
@@ -163,12 +164,12 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
   dy[3] = (T)0.5 * (r * e0 + q * e1 - p * e2);
   const double* G = P.gammas;
   dy[4] = (T)G[1] * p * q - (T)G[2] * q * r + (T)G[3] * tl + (T)G[4] * tn;
-  dy[5] = (T)G[5] * p * r - (T)G[6] * (p * p - r * r) + tm / (T)P.Jy;
+  dy[5] = (T)G[5] * p * r - (T)G[6] * (p * p - r * r) + tm * (T)P.inv_Jy;
   dy[6] = (T)G[7] * p * q - (T)G[1] * q * r + (T)G[4] * tl + (T)G[8] * tn;
   dy[7] = (e1 * e1 + e0 * e0 - e2 * e2 - e3 * e3) * u + 2 * (e1 * e2 - e3 * e0) * v + 2 * (e1 * e3 + e2 * e0) * w;
   dy[8] = 2 * (e1 * e2 + e3 * e0) * u + (e2 * e2 + e0 * e0 - e1 * e1 - e3 * e3) * v + 2 * (e2 * e3 - e1 * e0) * w;
   dy[9] = 2 * (e1 * e3 - e2 * e0) * u + 2 * (e2 * e3 + e1 * e0) * v + (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2) * w;
-  const T im = (T)1 / (T)P.mass;
+  const T im = (T)P.inv_mass;
   dy[10] = r * v - q * w + fx * im;
   dy[11] = p * w - r * u + fyy * im;
   dy[12] = q * u - p * v + fz * im;
@@ -192,145 +193,201 @@ __constant__ double c_dpA[7][6] = {
     {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
 __constant__ double c_dpE[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
 
+// The position states (y[7..9]) never feed back into the right-hand side, so their K stages are not stored: their
+// contributions to y_new (B row) and to the error estimate (E row) are accumulated in registers as each stage is
+// produced.  The other 16 components keep their K stages in shared memory.
+#define FW_N_KC 16
+__device__ __forceinline__ constexpr int fw_kc_to_ode(int kc) { return kc < 7 ? kc : kc + 3; }
+
 // K-stage storage: shared memory, [slot][component][thread] so a warp's access to one (slot, component) is 32
 // consecutive words -> conflict-free.
 template <typename T, int BLOCK> struct FwKStore {
   T* base;
-  __device__ __forceinline__ T& at(int slot, int c) { return base[(slot * FW_N_ODE + c) * BLOCK + threadIdx.x]; }
+  __device__ __forceinline__ T& at(int slot, int kc) { return base[(slot * FW_N_KC + kc) * BLOCK + threadIdx.x]; }
 };
+
+// 1/x to ~1 ulp without the division slow path (x is a tolerance scale >= atol > 0, always a normal number)
+__device__ __forceinline__ double fw_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+__device__ __forceinline__ float fw_rcp(float x) { return __frcp_rn(x); }
 
 // One env step of PyFly's integration: solve_ivp(fun, (0, dt), y0) with RK45 defaults.  On return y holds
 // sol.y[:, -1]; attempts/accepted count dopri5 step attempts; `fail` != 0 if a ConstraintException was raised by any
 // RHS evaluation (the integration is abandoned immediately, as the exception does in PyFly).
+//
+// Written as a phase machine around ONE right-hand-side call site (instruction-cache footprint): phase 0 evaluates
+// f(t0, y0), phase 1 the probe of select_initial_step, phases 2..7 the six evaluations of one dopri5 attempt.
 template <typename T, int BLOCK>
 __device__ __forceinline__ int fw_integrate_step(const fw_sim_t& P, const FwStepIn<T>& in, T (&y)[FW_N_ODE],
                                                  FwKStore<T, BLOCK> K, int& attempts, int& accepted, int& fail) {
   typedef FwMath<T> Mt;
   const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
-  const T sqrtn = (T)4.358898943540674;   // 19 ** 0.5
+  const T inv_sqrtn = (T)(1.0 / 4.358898943540674);   // 1 / 19 ** 0.5
   T f[FW_N_ODE], ys[FW_N_ODE];
+  T k0pos[3];            // K0 of the position components for the current step
+  T accB[3], accE[3];    // running B-row / E-row sums of the position components
+  T t = 0, min_step = 0, h = 0, h_abs = 0, t_new = 0, h0 = 0, d1 = 0;
+  bool rejected = false;
+  int status = FW_STATUS_RUNNING;
+  int phase = 0;
   attempts = 0;
   accepted = 0;
 
-  // RK45.__init__: f = fun(t0, y0) ; h_abs = select_initial_step(...)   (rk.py:94-100, common.py:109-134)
-  fw_rhs<T>(P, in, y, f, fail);
-  if (fail) return FW_STATUS_FINISHED;
-  T h_abs;
-  {
-    T s0 = 0, s1 = 0;
-#pragma unroll
-    for (int c = 0; c < FW_N_ODE; ++c) {
-      const T sc = atol + fabs(y[c]) * rtol;
-      const T a = y[c] / sc, b = f[c] / sc;
-      s0 += a * a;
-      s1 += b * b;
-      K.at(0, c) = f[c];
-    }
-    const T d0 = Mt::sqrt_(s0) / sqrtn, d1 = Mt::sqrt_(s1) / sqrtn;
-    T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
-    h0 = h0 < tb ? h0 : tb;
-#pragma unroll
-    for (int c = 0; c < FW_N_ODE; ++c) ys[c] = y[c] + h0 * f[c];
-    T f1[FW_N_ODE];
-    fw_rhs<T>(P, in, ys, f1, fail);
-    if (fail) return FW_STATUS_FINISHED;
-    T s2 = 0;
-#pragma unroll
-    for (int c = 0; c < FW_N_ODE; ++c) {
-      const T sc = atol + fabs(y[c]) * rtol;
-      const T a = (f1[c] - f[c]) / sc;
-      s2 += a * a;
-    }
-    const T d2 = Mt::sqrt_(s2) / sqrtn / h0;
-    T h1;
-    if (d1 <= (T)1e-15 && d2 <= (T)1e-15) {
-      h1 = h0 * (T)1e-3;
-      h1 = h1 > (T)1e-6 ? h1 : (T)1e-6;
-    } else {
-      h1 = Mt::pow_((T)0.01 / (d1 > d2 ? d1 : d2), (T)0.2);
-    }
-    h_abs = 100 * h0;
-    h_abs = h_abs < h1 ? h_abs : h1;
-    h_abs = h_abs < tb ? h_abs : tb;
-  }
-
-  // solve_ivp loop of RK45._step_impl (rk.py:111-176); one iteration of this loop == one step attempt
-  T t = 0, min_step = 0;
-  bool newstep = true, rejected = false;
-  int status = FW_STATUS_RUNNING;
   while (status == FW_STATUS_RUNNING) {
-    if (newstep) {
-      min_step = 10 * fabs(Mt::next_up(t) - t);
-      if (h_abs < min_step) h_abs = min_step;
-      rejected = false;
-      newstep = false;
-    }
-    if (h_abs < min_step) { status = FW_STATUS_TOO_SMALL; break; }
-    T t_new = t + h_abs;
-    if (t_new - tb > 0) t_new = tb;
-    const T h = t_new - t;
-    h_abs = fabs(h);
-    ++attempts;
-
-    // rk_step: stages 1..5 then the FSAL stage (row 6 == B) which gives y_new and f_new
-    for (int s = 1; s <= 6; ++s) {
+    // ---------------------------------------------------------------- build the state the RHS is evaluated at
+    if (phase == 0) {
 #pragma unroll
-      for (int c = 0; c < FW_N_ODE; ++c) ys[c] = 0;
+      for (int c = 0; c < FW_N_ODE; ++c) ys[c] = y[c];
+    } else if (phase == 1) {
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) { const int c = fw_kc_to_ode(kc); ys[c] = y[c] + h0 * K.at(0, kc); }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) ys[7 + j] = y[7 + j] + h0 * k0pos[j];
+    } else {
+      const int s = phase - 1;   // 1..6
+      T acc[FW_N_KC];
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) acc[kc] = 0;
       for (int j = 0; j < s; ++j) {
         const T a = (T)c_dpA[s][j];
 #pragma unroll
-        for (int c = 0; c < FW_N_ODE; ++c) ys[c] += a * K.at(j, c);
+        for (int kc = 0; kc < FW_N_KC; ++kc) acc[kc] += a * K.at(j, kc);
       }
 #pragma unroll
-      for (int c = 0; c < FW_N_ODE; ++c) ys[c] = y[c] + ys[c] * h;
-      fw_rhs<T>(P, in, ys, f, fail);
-      if (fail) return FW_STATUS_FINISHED;
-      if (s < 6) {
+      for (int kc = 0; kc < FW_N_KC; ++kc) { const int c = fw_kc_to_ode(kc); ys[c] = y[c] + acc[kc] * h; }
+      // position stage states are never read by the RHS; y_new[pos] is formed from accB when s == 6
 #pragma unroll
-        for (int c = 0; c < FW_N_ODE; ++c) K.at(s, c) = f[c];
-      }
+      for (int j = 0; j < 3; ++j) ys[7 + j] = y[7 + j] + h * accB[j];
     }
-    // ys == y_new, f == f_new.  error = (K^T . E) * h ; scale = atol + max(|y|,|y_new|)*rtol
-    T se = 0;
-#pragma unroll
-    for (int c = 0; c < FW_N_ODE; ++c) {
-      T e = (T)c_dpE[6] * f[c];
-#pragma unroll
-      for (int j = 0; j < 6; ++j)
-        if (j != 1) e += (T)c_dpE[j] * K.at(j, c);
-      e *= h;
-      const T ay = fabs(y[c]), an = fabs(ys[c]);
-      const T sc = atol + (ay > an ? ay : an) * rtol;
-      const T q = e / sc;
-      se += q * q;
-    }
-    const T err = Mt::sqrt_(se) / sqrtn;
-    if (err < (T)1) {
-      T factor;
-      if (err == (T)0) factor = (T)10;
-      else {
-        factor = (T)0.9 * Mt::pow_(err, (T)-0.2);
-        factor = factor < (T)10 ? factor : (T)10;
-      }
-      if (rejected) factor = factor < (T)1 ? factor : (T)1;
-      h_abs *= factor;
-      // accept
-      t = t_new;
+
+    fw_rhs<T>(P, in, ys, f, fail);
+    if (fail) return FW_STATUS_FINISHED;
+
+    // ------------------------------------------------------------------------------- consume the evaluation
+    if (phase == 0) {
+      // RK45.__init__ / select_initial_step, first half (common.py:109-124)
+      T s0 = 0, s1 = 0;
 #pragma unroll
       for (int c = 0; c < FW_N_ODE; ++c) {
-        y[c] = ys[c];
-        K.at(0, c) = f[c];
+        const T isc = fw_rcp(atol + fabs(y[c]) * rtol);
+        const T a = y[c] * isc, b = f[c] * isc;
+        s0 += a * a;
+        s1 += b * b;
       }
-      ++accepted;
-      newstep = true;
-      if (t - tb >= 0) status = FW_STATUS_FINISHED;
-    } else {
-      // NaN error norms land here too: Python's max(0.2, nan) == 0.2
-      T fac = (T)0.9 * Mt::pow_(err, (T)-0.2);
-      fac = fac > (T)0.2 ? fac : (T)0.2;
-      h_abs *= fac;
-      rejected = true;
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) K.at(0, kc) = f[fw_kc_to_ode(kc)];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) k0pos[j] = f[7 + j];
+      const T d0 = Mt::sqrt_(s0) * inv_sqrtn;
+      d1 = Mt::sqrt_(s1) * inv_sqrtn;
+      h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
+      h0 = h0 < tb ? h0 : tb;
+      phase = 1;
+      continue;
     }
+    if (phase == 1) {
+      // select_initial_step, second half (common.py:125-134)
+      T s2 = 0;
+#pragma unroll
+      for (int c = 0; c < FW_N_ODE; ++c) {
+        const T isc = fw_rcp(atol + fabs(y[c]) * rtol);
+        const T f0c = (c >= 7 && c < 10) ? k0pos[c - 7] : K.at(0, c < 7 ? c : c - 3);
+        const T a = (f[c] - f0c) * isc;
+        s2 += a * a;
+      }
+      const T d2 = Mt::sqrt_(s2) * inv_sqrtn / h0;
+      T h1;
+      if (d1 <= (T)1e-15 && d2 <= (T)1e-15) {
+        h1 = h0 * (T)1e-3;
+        h1 = h1 > (T)1e-6 ? h1 : (T)1e-6;
+      } else {
+        h1 = Mt::pow_((T)0.01 / (d1 > d2 ? d1 : d2), (T)0.2);
+      }
+      h_abs = 100 * h0;
+      h_abs = h_abs < h1 ? h_abs : h1;
+      h_abs = h_abs < tb ? h_abs : tb;
+      // first _step_impl call (rk.py:111-135)
+      min_step = 10 * fabs(Mt::next_up(t) - t);
+      if (h_abs < min_step) h_abs = min_step;
+      rejected = false;
+    } else {
+      const int s = phase - 1;
+      if (s < 6) {
+#pragma unroll
+        for (int kc = 0; kc < FW_N_KC; ++kc) K.at(s, kc) = f[fw_kc_to_ode(kc)];
+        const T b = (T)c_dpA[6][s], e = (T)c_dpE[s];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { accB[j] += b * f[7 + j]; accE[j] += e * f[7 + j]; }
+        phase += 1;
+        continue;
+      }
+      // s == 6: ys == y_new, f == f_new.  error = (K^T . E) * h ; scale = atol + max(|y|,|y_new|)*rtol (rk.py:150-152)
+      T se = 0;
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) {
+        const int c = fw_kc_to_ode(kc);
+        T e = (T)c_dpE[6] * f[c];
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+          if (j != 1) e += (T)c_dpE[j] * K.at(j, kc);
+        e *= h;
+        const T ay = fabs(y[c]), an = fabs(ys[c]);
+        const T q = e * fw_rcp(atol + (ay > an ? ay : an) * rtol);
+        se += q * q;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const T e = (accE[j] + (T)c_dpE[6] * f[7 + j]) * h;
+        const T ay = fabs(y[7 + j]), an = fabs(ys[7 + j]);
+        const T q = e * fw_rcp(atol + (ay > an ? ay : an) * rtol);
+        se += q * q;
+      }
+      const T err = Mt::sqrt_(se) * inv_sqrtn;
+      if (err < (T)1) {
+        T factor;
+        if (err == (T)0) factor = (T)10;
+        else {
+          factor = (T)0.9 * Mt::pow_(err, (T)-0.2);
+          factor = factor < (T)10 ? factor : (T)10;
+        }
+        if (rejected) factor = factor < (T)1 ? factor : (T)1;
+        h_abs *= factor;
+        t = t_new;
+#pragma unroll
+        for (int c = 0; c < FW_N_ODE; ++c) y[c] = ys[c];
+#pragma unroll
+        for (int kc = 0; kc < FW_N_KC; ++kc) K.at(0, kc) = f[fw_kc_to_ode(kc)];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) k0pos[j] = f[7 + j];
+        ++accepted;
+        if (t - tb >= 0) { status = FW_STATUS_FINISHED; break; }
+        // next _step_impl call
+        min_step = 10 * fabs(Mt::next_up(t) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        rejected = false;
+      } else {
+        // NaN error norms land here too: Python's max(0.2, nan) == 0.2
+        T fac = (T)0.9 * Mt::pow_(err, (T)-0.2);
+        fac = fac > (T)0.2 ? fac : (T)0.2;
+        h_abs *= fac;
+        rejected = true;
+      }
+    }
+    // ---- start a step attempt (rk.py:137-147)
+    if (h_abs < min_step) { status = FW_STATUS_TOO_SMALL; break; }
+    t_new = t + h_abs;
+    if (t_new - tb > 0) t_new = tb;
+    h = t_new - t;
+    h_abs = fabs(h);
+    ++attempts;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { accB[j] = (T)c_dpA[6][0] * k0pos[j]; accE[j] = (T)c_dpE[0] * k0pos[j]; }
+    phase = 2;
   }
   return status;
 }

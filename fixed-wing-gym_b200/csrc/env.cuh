@@ -193,6 +193,7 @@ __device__ __forceinline__ void fw_observation(const fw_env_t& E, const fw_sim_t
     for (int v = 0; v < nv; ++v) {
       const fw_obs_var_t& ov = E.obs[v];
       double val;
+      bool is_f32 = false;   // the action-delta value is an np.float32 in the reference (fixed_wing.py:826,828)
       if (ov.type == 0) {
         if (L.sv_depth <= 1 || ih == 1) val = fw_sv_value(c, ov.ref);
         else val = fw_ring_get(c, L.sv_row, L.sv_depth, L.n_sv_obs, L.sv_slot[v], hist_len - ih);
@@ -244,11 +245,22 @@ __device__ __forceinline__ void fw_observation(const fw_env_t& E, const fw_sim_t
             acc += (float)fabs(d1 - d0);
           }
           val = (double)acc;
+          is_f32 = true;
         }
       }
-      if (has_init_noise) val += init_noise;
-      if (E.obs_norm && ov.norm) { val -= ov.mean; val /= ov.var; }
-      if (E.obs_noise) val += rng.normal(E.obs_noise_mean, E.obs_noise_std);
+      if (is_f32) {
+        // numpy >= 2 (NEP 50) keeps np.float32 (+,-,/) python-float in float32, so the jitter / normalisation /
+        // noise of this variable are float32 operations in the oracle run; mirrored here.
+        float v32 = (float)val;
+        if (has_init_noise) v32 = v32 + (float)init_noise;
+        if (E.obs_norm && ov.norm) { v32 = v32 - (float)ov.mean; v32 = v32 / (float)ov.var; }
+        if (E.obs_noise) v32 = v32 + (float)rng.normal(E.obs_noise_mean, E.obs_noise_std);
+        val = (double)v32;
+      } else {
+        if (has_init_noise) val += init_noise;
+        if (E.obs_norm && ov.norm) { val -= ov.mean; val /= ov.var; }
+        if (E.obs_noise) val += rng.normal(E.obs_noise_mean, E.obs_noise_std);
+      }
       out(row * nv + v, val);
     }
   }

@@ -17,7 +17,8 @@
 #include "dynamics.cuh"
 #include "env.cuh"
 
-#define FW_DYN_BLOCK 64
+#define FW_DYN_BLOCK 32
+#define FW_DYN_MIN_BLOCKS 8
 #define FW_ENV_BLOCK 128
 
 enum { CTR_ENV_STEPS = 0, CTR_ATTEMPTS, CTR_ACCEPTED, CTR_WARP_MAX, CTR_WARP_STEPS, CTR_FAILURES, CTR_RESETS, CTR_N };
@@ -62,7 +63,7 @@ struct FwDynArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(FW_DYN_BLOCK)
+__global__ void __launch_bounds__(FW_DYN_BLOCK, FW_DYN_MIN_BLOCKS)
 fw_dyn_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwKStore<T, FW_DYN_BLOCK> K{reinterpret_cast<T*>(smem_raw)};
@@ -477,7 +478,7 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   CK(cudaMemset(h->i, 0, ib));
   CK(cudaMemset(h->ctr, 0, CTR_N * sizeof(unsigned long long)));
   CK(cudaMemset(h->msum, 0, FW_N_METRIC_SUMS * sizeof(double)));
-  const int smem64 = 6 * FW_N_ODE * FW_DYN_BLOCK * (int)sizeof(double);
+  const int smem64 = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(double);
   CK(cudaFuncSetAttribute(fw_dyn_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
   CK(cudaFuncSetAttribute(fw_dyn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64 / 2));
   *out = h;
@@ -566,10 +567,10 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
     CK(cudaEventRecord(pe[0], s));
   }
   if (h->cfg.precision == 0) {
-    const int smem = 6 * FW_N_ODE * FW_DYN_BLOCK * (int)sizeof(double);
+    const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(double);
     fw_dyn_kernel<double><<<dgrid, FW_DYN_BLOCK, smem, s>>>(h->cfg.sim, da);
   } else {
-    const int smem = 6 * FW_N_ODE * FW_DYN_BLOCK * (int)sizeof(float);
+    const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(float);
     fw_dyn_kernel<float><<<dgrid, FW_DYN_BLOCK, smem, s>>>(h->cfg.sim, da);
   }
   CK(cudaGetLastError());

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 3
+#define FW_ABI_VERSION 4
 
 /* ---------------------------------------------------------------------------------------------- limits */
 #define FW_MAX_OBS_VARS 32
@@ -116,7 +116,7 @@ typedef struct {
   double C_l_0, C_l_beta, C_l_p, C_l_r, C_l_delta_a, C_l_delta_r;
   double C_n_0, C_n_beta, C_n_p, C_n_r, C_n_delta_a, C_n_delta_r;
   double gammas[9];
-  double Jy;
+  double Jy, inv_Jy, inv_mass, inv_pi_e_ar;   /* host-computed reciprocals (1 ulp from the divisions they replace) */
   int32_t drag_model;             /* 0 induced (1-sigma)CL^2/(pi e AR) + flat plate, 1 polynomial */
   int32_t turbulence;             /* Dryden gusts on */
   int32_t wind_enabled;           /* steady wind may be non-zero */
