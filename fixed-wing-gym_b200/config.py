@@ -376,7 +376,13 @@ class CompiledConfig:
                     flags |= _capi.DEFINES[bit]
                     setattr(v, {"value_min": "vmin", "value_max": "vmax", "constraint_min": "cmin",
                                 "constraint_max": "cmax"}[attr], float(val))
+            v.lo = float(var.value_min) if var.value_min is not None else -math.inf
+            v.hi = float(var.value_max) if var.value_max is not None else math.inf
+            v.clo = float(var.constraint_min) if var.constraint_min is not None else -math.inf
+            v.chi = float(var.constraint_max) if var.constraint_max is not None else math.inf
             if var.wrap:
+                if name not in ("roll", "yaw", "pitch"):
+                    raise ConfigError("wrap is only supported on attitude angles, not %s" % name)
                 flags |= _capi.DEFINES["FW_VC_WRAP"]
             v.flags = flags
             v.init_min = float(var.init_min) if var.init_min is not None else 0.0

@@ -35,15 +35,23 @@ template <> struct FwMath<float> {
 };
 
 // PyFly Variable.apply_conditions: constraint check -> clip -> (wrap).  `fail` keeps the FIRST violated variable.
+// The host stores every missing bound as +-inf (lo/hi for the clip, clo/chi for the constraint), so the body is
+// branch-free compares/selects; variables without any condition skip it on one warp-uniform test.
 template <typename T>
 __device__ __forceinline__ T fw_cond(const fw_var_t& v, int sv, T x, int& fail) {
-  const uint32_t fl = v.flags;
-  if (fl == 0u) return x;
-  if ((fl & FW_VC_CMIN) && x < (T)v.cmin && !fail) fail = FW_TERM_FAIL_BASE + sv;
-  if ((fl & FW_VC_CMAX) && x > (T)v.cmax && !fail) fail = FW_TERM_FAIL_BASE + sv;
-  if (fl & FW_VC_VMIN) x = x < (T)v.vmin ? (T)v.vmin : x;
-  if (fl & FW_VC_VMAX) x = x > (T)v.vmax ? (T)v.vmax : x;
-  if (fl & FW_VC_WRAP) {
+  if (v.flags == 0u) return x;
+  const bool bad = (x < (T)v.clo) | (x > (T)v.chi);
+  if (bad && !fail) fail = FW_TERM_FAIL_BASE + sv;
+  x = x < (T)v.lo ? (T)v.lo : x;     // compares keep NaN, like np.clip
+  x = x > (T)v.hi ? (T)v.hi : x;
+  return x;
+}
+
+// + the wrap of angle variables (roll, yaw); only needed when a state is stored, never inside the RHS
+template <typename T>
+__device__ __forceinline__ T fw_cond_wrap(const fw_var_t& v, int sv, T x, int& fail) {
+  x = fw_cond<T>(v, sv, x, fail);
+  if (v.flags & FW_VC_WRAP) {
     T ax = fabs(x);
     if (ax > (T)CUDART_PI) {   // np.sign(v) * (|v| % pi - pi)
       T s = x > 0 ? (T)1 : (T)-1;
@@ -123,9 +131,21 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
   const T ex1 = Mt::exp_(Mt::exp_arg(-(T)P.M * (alpha - (T)P.a_0)));
   const T ex2 = Mt::exp_(Mt::exp_arg((T)P.M * (alpha + (T)P.a_0)));
   const T sigma = (1 + ex1 + ex2) / ((1 + ex1) * (1 + ex2));
+  // sin/cos of alpha = atan2(wr, ur) and beta = asin(vr / Va) follow algebraically from the airspeed components
+  // when neither angle was altered by a clip (the usual configuration); otherwise fall back to sincos.
   T sa, ca, sb, cb;
-  Mt::sincos_(alpha, &sa, &ca);
-  Mt::sincos_(beta, &sb, &cb);
+  if ((P.var[FW_SV_ALPHA].flags | P.var[FW_SV_BETA].flags) == 0u && Va == Va_raw) {
+    const T hxz2 = ur * ur + wr * wr;
+    const T hxz = Mt::sqrt_(hxz2);
+    const T ih = hxz > (T)0 ? (T)1 / hxz : (T)0;
+    sa = wr * ih;
+    ca = hxz > (T)0 ? ur * ih : (T)1;
+    sb = vr * invVa;
+    cb = hxz * invVa;
+  } else {
+    Mt::sincos_(alpha, &sa, &ca);
+    Mt::sincos_(beta, &sb, &cb);
+  }
   const T sgn = alpha > 0 ? (T)1 : (alpha < 0 ? (T)-1 : (T)0);
   const T CL = (1 - sigma) * CLlin + sigma * (2 * sgn * sa * sa * ca);
   const T inv2Va = (T)0.5 * invVa;

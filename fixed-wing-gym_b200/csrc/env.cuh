@@ -406,7 +406,7 @@ __device__ __forceinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& 
   };
   auto init_var = [&](int sv) -> double {
     double v;
-    if (given(sv, v)) return fw_cond<double>(P.var[sv], sv, v, dummy);
+    if (given(sv, v)) return fw_cond_wrap<double>(P.var[sv], sv, v, dummy);
     return fw_uniform(g, FW_RS_INIT, (uint32_t)sv, P.var[sv].init_min, P.var[sv].init_max);
   };
   // ---- PyFly.reset ----

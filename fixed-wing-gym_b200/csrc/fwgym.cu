@@ -125,9 +125,9 @@ fw_dyn_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
       roll = atan2(2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
       pitch = asin(2 * (e0 * e2 - e1 * e3));
       yaw = atan2(2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
-      roll = fw_cond<double>(P.var[FW_SV_ROLL], FW_SV_ROLL, roll, failv);
-      pitch = fw_cond<double>(P.var[FW_SV_PITCH], FW_SV_PITCH, pitch, failv);
-      yaw = fw_cond<double>(P.var[FW_SV_YAW], FW_SV_YAW, yaw, failv);
+      roll = fw_cond_wrap<double>(P.var[FW_SV_ROLL], FW_SV_ROLL, roll, failv);
+      pitch = fw_cond_wrap<double>(P.var[FW_SV_PITCH], FW_SV_PITCH, pitch, failv);
+      yaw = fw_cond_wrap<double>(P.var[FW_SV_YAW], FW_SV_YAW, yaw, failv);
 #pragma unroll
       for (int j = 0; j < 9; ++j) yd[4 + j] = fw_cond<double>(P.var[FW_SV_OMEGA_P + j], FW_SV_OMEGA_P + j, yd[4 + j], failv);
       yd[13] = fw_cond<double>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, yd[13], failv);

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 4
+#define FW_ABI_VERSION 5
 
 /* ---------------------------------------------------------------------------------------------- limits */
 #define FW_MAX_OBS_VARS 32
@@ -62,6 +62,7 @@ enum fw_status {
 
 typedef struct {
   double vmin, vmax, cmin, cmax;   /* value clip and hard constraint, radians where applicable */
+  double lo, hi, clo, chi;         /* same with missing bounds as -inf/+inf (branch-free device code) */
   double init_min, init_max;       /* uniform init range after curriculum scaling (fixed_wing.py:233-245) */
   uint32_t flags;
   uint32_t _pad;
