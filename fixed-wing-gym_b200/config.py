@@ -347,6 +347,7 @@ class CompiledConfig:
         s.inv_Jy = 1.0 / float(I[1, 1])
         s.inv_mass = 1.0 / float(P["mass"])
         s.inv_pi_e_ar = 1.0 / (np.pi * P["e"] * s.ar)
+        s.exp_2Ma0 = float(np.exp(2.0 * P["M"] * P["a_0"]))
         s.drag_model = {"induced": 0, "polynomial": 1}[sc.get("drag_model", "induced")]
         s.turbulence = 1 if sc["turbulence"] else 0
         s.wind_mag_min, s.wind_mag_max = sc["wind_magnitude_min"], sc["wind_magnitude_max"]

@@ -6,32 +6,39 @@
 #pragma once
 #include <math_constants.h>
 #include "layout.h"
+#include "fwmath.cuh"
 
 #define FW_STATUS_RUNNING 0
 #define FW_STATUS_FINISHED 1
 #define FW_STATUS_TOO_SMALL 2
+#define FW_MAX_ATTEMPTS 100000   // hang guard; a healthy env step takes 2..10 attempts
 
 template <typename T> struct FwMath;
+// fp64: the branch-free routines of fwmath.cuh (straight-line, Estrin polynomials, constant-bank coefficients) so
+// that ptxas can interleave the independent chains of one right-hand side.  sincos stays libdevice: it is only
+// reached when alpha/beta carry a clip (not in any shipped configuration).
 template <> struct FwMath<double> {
-  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
-  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
-  static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
-  static __device__ __forceinline__ double asin_(double x) { return asin(x); }
-  static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+  static __device__ __forceinline__ double sqrt_(double x) { return fwm_sqrt(x); }
+  static __device__ __forceinline__ void sqrt_rsqrt(double x, double* s, double* rs) { fwm_sqrt_rsqrt(x, s, rs); }
+  static __device__ __forceinline__ double exp_(double x) { return fwm_exp(x); }
+  static __device__ __forceinline__ double atan2_(double y, double x) { return fwm_atan2(y, x); }
+  static __device__ __forceinline__ double pow_(double x, double y) { return fwm_pow(x, y); }
+  static __device__ __forceinline__ double div_(double a, double b) { return fwm_div(a, b); }
+  static __device__ __forceinline__ double rcp_(double x) { return fwm_rcp(x); }
   static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
-  static __device__ __forceinline__ double next_up(double x) { return nextafter(x, CUDART_INF); }
-  static __device__ __forceinline__ double exp_arg(double x) { return x; }
+  // nextafter(x, +inf) for finite x >= 0 (the integrator's t)
+  static __device__ __forceinline__ double next_up(double x) { return __longlong_as_double(__double_as_longlong(x) + 1); }
 };
 template <> struct FwMath<float> {
   static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ void sqrt_rsqrt(float x, float* s, float* rs) { *s = sqrtf(x); *rs = 1.0f / *s; }
   static __device__ __forceinline__ float exp_(float x) { return expf(x); }
   static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
-  static __device__ __forceinline__ float asin_(float x) { return asinf(x); }
   static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+  static __device__ __forceinline__ float div_(float a, float b) { return a / b; }
+  static __device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
   static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
-  static __device__ __forceinline__ float next_up(float x) { return nextafterf(x, CUDART_INF_F); }
-  // keep exp() finite in fp32: (1+e1)(1+e2) stays below FLT_MAX (e1*e2 = exp(2*M*a_0) is constant)
-  static __device__ __forceinline__ float exp_arg(float x) { return fminf(x, 80.0f); }
+  static __device__ __forceinline__ float next_up(float x) { return __int_as_float(__float_as_int(x) + 1); }
 };
 
 // PyFly Variable.apply_conditions: constraint check -> clip -> (wrap).  `fail` keeps the FIRST violated variable.
@@ -111,12 +118,16 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
     ur -= in.gl[0]; vr -= in.gl[1]; wr -= in.gl[2];
     pa -= in.ga[0]; qa -= in.ga[1]; ra -= in.ga[2];
   }
-  const T Va_raw = Mt::sqrt_(ur * ur + vr * vr + wr * wr);
-  T invVa = (T)1 / Va_raw;
+  // Va = |v_r|, alpha = atan2(w_r, u_r), beta = asin(v_r / Va) = atan2(v_r, hypot(u_r, w_r)): the two atan2 and the
+  // two sqrt/rsqrt pairs are independent chains
+  const T hxz2 = ur * ur + wr * wr;
+  T Va_raw, invVa, hxz, ih;
+  Mt::sqrt_rsqrt(hxz2 + vr * vr, &Va_raw, &invVa);
+  Mt::sqrt_rsqrt(hxz2, &hxz, &ih);
   T alpha = Mt::atan2_(wr, ur);
-  T beta = Mt::asin_(vr * invVa);
+  T beta = Mt::atan2_(vr, hxz);
   const T Va = fw_cond<T>(P.var[FW_SV_VA], FW_SV_VA, Va_raw, fail);
-  if (Va != Va_raw) invVa = (T)1 / Va;   // value_min clip engaged (rare)
+  if (Va != Va_raw) invVa = Mt::rcp_(Va);   // value_min clip engaged (rare)
   alpha = fw_cond<T>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, fail);
   beta = fw_cond<T>(P.var[FW_SV_BETA], FW_SV_BETA, beta, fail);
 
@@ -128,18 +139,27 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
   const T fgz = mg * (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2);
 
   const T CLlin = (T)P.C_L_0 + (T)P.C_L_alpha * alpha;
-  const T ex1 = Mt::exp_(Mt::exp_arg(-(T)P.M * (alpha - (T)P.a_0)));
-  const T ex2 = Mt::exp_(Mt::exp_arg((T)P.M * (alpha + (T)P.a_0)));
-  const T sigma = (1 + ex1 + ex2) / ((1 + ex1) * (1 + ex2));
-  // sin/cos of alpha = atan2(wr, ur) and beta = asin(vr / Va) follow algebraically from the airspeed components
-  // when neither angle was altered by a clip (the usual configuration); otherwise fall back to sincos.
+  // sigma = (1 + e1 + e2) / ((1 + e1)(1 + e2)), e1 = exp(-M(alpha - a0)), e2 = exp(M(alpha + a0)).  e1 * e2 is the
+  // constant exp(2 M a0) (host-computed), so fp64 needs ONE exponential: with e2 = C / e1 the quotient becomes
+  // (e1 + e1^2 + C) / ((1 + e1)(e1 + C)); |alpha| <= pi keeps e1^2 far inside the fp64 range.
+  T sigma;
+  if constexpr (sizeof(T) == 8) {
+    const T x1 = Mt::exp_(-(T)P.M * (alpha - (T)P.a_0));
+    const T C = (T)P.exp_2Ma0;
+    sigma = Mt::div_(fma(x1, x1, x1) + C, (1 + x1) * (x1 + C));
+  } else {
+    // fp32: (1+e1)(1+e2) must stay below FLT_MAX, so both exponents are clamped (e1 * e2 is constant)
+    const T ex1 = Mt::exp_(fminf(-(T)P.M * (alpha - (T)P.a_0), 80.0f));
+    const T ex2 = Mt::exp_(fminf((T)P.M * (alpha + (T)P.a_0), 80.0f));
+    sigma = (1 + ex1 + ex2) / ((1 + ex1) * (1 + ex2));
+  }
+  // sin/cos of alpha and beta follow algebraically from the airspeed components when neither angle was altered by a
+  // clip (the usual configuration); otherwise fall back to sincos.
   T sa, ca, sb, cb;
   if ((P.var[FW_SV_ALPHA].flags | P.var[FW_SV_BETA].flags) == 0u && Va == Va_raw) {
-    const T hxz2 = ur * ur + wr * wr;
-    const T hxz = Mt::sqrt_(hxz2);
-    const T ih = hxz > (T)0 ? (T)1 / hxz : (T)0;
-    sa = wr * ih;
-    ca = hxz > (T)0 ? ur * ih : (T)1;
+    const bool nz = hxz > (T)0;
+    sa = nz ? wr * ih : (T)0;
+    ca = nz ? ur * ih : (T)1;
     sb = vr * invVa;
     cb = hxz * invVa;
   } else {
@@ -305,7 +325,7 @@ __device__ __forceinline__ int fw_integrate_step(const fw_sim_t& P, const FwStep
       for (int j = 0; j < 3; ++j) k0pos[j] = f[7 + j];
       const T d0 = Mt::sqrt_(s0) * inv_sqrtn;
       d1 = Mt::sqrt_(s1) * inv_sqrtn;
-      h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
+      h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : Mt::div_((T)0.01 * d0, d1);
       h0 = h0 < tb ? h0 : tb;
       phase = 1;
       continue;
@@ -320,13 +340,13 @@ __device__ __forceinline__ int fw_integrate_step(const fw_sim_t& P, const FwStep
         const T a = (f[c] - f0c) * isc;
         s2 += a * a;
       }
-      const T d2 = Mt::sqrt_(s2) * inv_sqrtn / h0;
+      const T d2 = Mt::div_(Mt::sqrt_(s2) * inv_sqrtn, h0);
       T h1;
       if (d1 <= (T)1e-15 && d2 <= (T)1e-15) {
         h1 = h0 * (T)1e-3;
         h1 = h1 > (T)1e-6 ? h1 : (T)1e-6;
       } else {
-        h1 = Mt::pow_((T)0.01 / (d1 > d2 ? d1 : d2), (T)0.2);
+        h1 = Mt::pow_(Mt::div_((T)0.01, d1 > d2 ? d1 : d2), (T)0.2);
       }
       h_abs = 100 * h0;
       h_abs = h_abs < h1 ? h_abs : h1;
@@ -368,13 +388,11 @@ __device__ __forceinline__ int fw_integrate_step(const fw_sim_t& P, const FwStep
         se += q * q;
       }
       const T err = Mt::sqrt_(se) * inv_sqrtn;
+      // 0.9 * err ** -0.2 feeds both outcomes (rk.py:160-172); err == 0 gives a huge value that the min() below turns
+      // into MAX_FACTOR, exactly the reference's special case
+      const T pw = (T)0.9 * Mt::pow_(err, (T)-0.2);
       if (err < (T)1) {
-        T factor;
-        if (err == (T)0) factor = (T)10;
-        else {
-          factor = (T)0.9 * Mt::pow_(err, (T)-0.2);
-          factor = factor < (T)10 ? factor : (T)10;
-        }
+        T factor = pw < (T)10 ? pw : (T)10;
         if (rejected) factor = factor < (T)1 ? factor : (T)1;
         h_abs *= factor;
         t = t_new;
@@ -392,8 +410,7 @@ __device__ __forceinline__ int fw_integrate_step(const fw_sim_t& P, const FwStep
         rejected = false;
       } else {
         // NaN error norms land here too: Python's max(0.2, nan) == 0.2
-        T fac = (T)0.9 * Mt::pow_(err, (T)-0.2);
-        fac = fac > (T)0.2 ? fac : (T)0.2;
+        const T fac = pw > (T)0.2 ? pw : (T)0.2;
         h_abs *= fac;
         rejected = true;
       }
@@ -404,7 +421,7 @@ __device__ __forceinline__ int fw_integrate_step(const fw_sim_t& P, const FwStep
     if (t_new - tb > 0) t_new = tb;
     h = t_new - t;
     h_abs = fabs(h);
-    ++attempts;
+    if (++attempts > FW_MAX_ATTEMPTS) { status = FW_STATUS_TOO_SMALL; break; }   // NaN step sizes never shrink
 #pragma unroll
     for (int j = 0; j < 3; ++j) { accB[j] = (T)c_dpA[6][0] * k0pos[j]; accE[j] = (T)c_dpE[0] * k0pos[j]; }
     phase = 2;

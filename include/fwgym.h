@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 5
+#define FW_ABI_VERSION 6
 
 /* ---------------------------------------------------------------------------------------------- limits */
 #define FW_MAX_OBS_VARS 32
@@ -118,6 +118,7 @@ typedef struct {
   double C_n_0, C_n_beta, C_n_p, C_n_r, C_n_delta_a, C_n_delta_r;
   double gammas[9];
   double Jy, inv_Jy, inv_mass, inv_pi_e_ar;   /* host-computed reciprocals (1 ulp from the divisions they replace) */
+  double exp_2Ma0;                /* exp(2 M a_0) = e1*e2 of the stall blending function (one exp per RHS, dynamics.cuh) */
   int32_t drag_model;             /* 0 induced (1-sigma)CL^2/(pi e AR) + flat plate, 1 polynomial */
   int32_t turbulence;             /* Dryden gusts on */
   int32_t wind_enabled;           /* steady wind may be non-zero */
