@@ -71,65 +71,106 @@ __device__ __forceinline__ T fw_cond_wrap(const fw_var_t& v, int sv, T x, int& f
 // per-step inputs that are constant during one env step
 template <typename T> struct FwStepIn {
   T cmd[3];      // constrained setpoints for elevon_left, elevon_right, throttle
-  T gl[3];       // linear gust (body)
-  T ga[3];       // angular gust
+  T gl[3];       // linear gust (body); zero when turbulence is off
+  T ga[3];       // angular gust; zero when turbulence is off
   T wind[3];     // steady wind NED
 };
 
+// ---- kernel specialisation -------------------------------------------------------------------------------------
+// Every conditioned variable of the right-hand side has a RANK = its position in PyFly's evaluation order (the first
+// violated one names the failure).  A kernel instantiation carries two compile-time rank masks: which variables it
+// clips and which it constraint-checks.  Doing MORE than a configuration asks for is harmless (absent bounds are
+// +-inf), so the host picks the leanest instantiation whose masks cover the configuration's:
+//   FwSpecShipped : what every shipped fixed_wing_config*.json needs (constraints on omega_p/q/r and Va, clips on Va,
+//                   the elevons, throttle, elevator, aileron and the elevon rates), no steady wind, induced drag.
+//                   The RHS body is one straight-line block.
+//   FwSpecGeneric : every variable, runtime wind / drag-model switches.
+enum {
+  FW_R_P = 0, FW_R_Q, FW_R_R, FW_R_U, FW_R_V, FW_R_W, FW_R_EL, FW_R_ER, FW_R_TH, FW_R_AIL, FW_R_ELEV, FW_R_VA,
+  FW_R_ALPHA, FW_R_BETA, FW_R_AD0, FW_R_AD1, FW_R_AD2, FW_R_N
+};
+#define FW_RB(r) (1u << (r))
+__constant__ int c_rank_sv[FW_R_BETA + 1] = {FW_SV_OMEGA_P, FW_SV_OMEGA_Q, FW_SV_OMEGA_R, FW_SV_VEL_U, FW_SV_VEL_V,
+                                             FW_SV_VEL_W, FW_SV_ELEVON_L, FW_SV_ELEVON_R, FW_SV_THROTTLE,
+                                             FW_SV_AILERON, FW_SV_ELEVATOR, FW_SV_VA, FW_SV_ALPHA, FW_SV_BETA};
+struct FwSpecShipped {
+  static constexpr uint32_t clip = FW_RB(FW_R_EL) | FW_RB(FW_R_ER) | FW_RB(FW_R_TH) | FW_RB(FW_R_AIL) |
+                                   FW_RB(FW_R_ELEV) | FW_RB(FW_R_VA) | FW_RB(FW_R_AD0) | FW_RB(FW_R_AD1);
+  static constexpr uint32_t cons = FW_RB(FW_R_P) | FW_RB(FW_R_Q) | FW_RB(FW_R_R) | FW_RB(FW_R_VA);
+  static constexpr bool generic = false;
+};
+struct FwSpecGeneric {
+  static constexpr uint32_t clip = 0xffffffffu, cons = 0xffffffffu;
+  static constexpr bool generic = true;
+};
+
+// branch-free condition of the variable of rank R: violated constraints set bit R of failmask
+template <typename T, class Spec, int R>
+__device__ __forceinline__ T fw_cond_r(const fw_var_t& v, T x, uint32_t& failmask) {
+  if constexpr ((Spec::cons >> R) & 1u) {
+    const bool bad = (x < (T)v.clo) | (x > (T)v.chi);
+    failmask |= bad ? FW_RB(R) : 0u;
+  }
+  if constexpr ((Spec::clip >> R) & 1u) {
+    x = x < (T)v.lo ? (T)v.lo : x;     // compares keep NaN, like np.clip
+    x = x > (T)v.hi ? (T)v.hi : x;
+  }
+  return x;
+}
+
 // d/dt of the 19-state vector.  y is the RAW trial state; PyFly conditions every component (clip / constraint) before
 // use except the quaternion, which is used un-normalised (oracle/pyfly_restated.py: _dynamics, _forces).
-template <typename T>
+template <typename T, class Spec>
 __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in, const T (&y)[FW_N_ODE],
-                                       T (&dy)[FW_N_ODE], int& fail) {
+                                       T (&dy)[FW_N_ODE], uint32_t& failmask) {
   typedef FwMath<T> Mt;
   const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
-  const T p = fw_cond<T>(P.var[FW_SV_OMEGA_P], FW_SV_OMEGA_P, y[4], fail);
-  const T q = fw_cond<T>(P.var[FW_SV_OMEGA_Q], FW_SV_OMEGA_Q, y[5], fail);
-  const T r = fw_cond<T>(P.var[FW_SV_OMEGA_R], FW_SV_OMEGA_R, y[6], fail);
+  const T p = fw_cond_r<T, Spec, FW_R_P>(P.var[FW_SV_OMEGA_P], y[4], failmask);
+  const T q = fw_cond_r<T, Spec, FW_R_Q>(P.var[FW_SV_OMEGA_Q], y[5], failmask);
+  const T r = fw_cond_r<T, Spec, FW_R_R>(P.var[FW_SV_OMEGA_R], y[6], failmask);
   // position variables carry no limits (config.py rejects them): their stage states are never formed
-  const T u = fw_cond<T>(P.var[FW_SV_VEL_U], FW_SV_VEL_U, y[10], fail);
-  const T v = fw_cond<T>(P.var[FW_SV_VEL_V], FW_SV_VEL_V, y[11], fail);
-  const T w = fw_cond<T>(P.var[FW_SV_VEL_W], FW_SV_VEL_W, y[12], fail);
+  const T u = fw_cond_r<T, Spec, FW_R_U>(P.var[FW_SV_VEL_U], y[10], failmask);
+  const T v = fw_cond_r<T, Spec, FW_R_V>(P.var[FW_SV_VEL_V], y[11], failmask);
+  const T w = fw_cond_r<T, Spec, FW_R_W>(P.var[FW_SV_VEL_W], y[12], failmask);
   // actuators: value conditions + rate clip (ControlVariable.apply_conditions)
-  const T el = fw_cond<T>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, y[13], fail);
-  const T er = fw_cond<T>(P.var[FW_SV_ELEVON_R], FW_SV_ELEVON_R, y[14], fail);
-  const T th = fw_cond<T>(P.var[FW_SV_THROTTLE], FW_SV_THROTTLE, y[15], fail);
+  const T el = fw_cond_r<T, Spec, FW_R_EL>(P.var[FW_SV_ELEVON_L], y[13], failmask);
+  const T er = fw_cond_r<T, Spec, FW_R_ER>(P.var[FW_SV_ELEVON_R], y[14], failmask);
+  const T th = fw_cond_r<T, Spec, FW_R_TH>(P.var[FW_SV_THROTTLE], y[15], failmask);
   T ad[3] = {y[16], y[17], y[18]};
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    if (P.act_has_dot_max[i]) {
-      const T m = (T)P.act_dot_max[i];
+    if ((Spec::clip >> (FW_R_AD0 + i)) & 1u) {
+      const T m = P.act_has_dot_max[i] ? (T)P.act_dot_max[i] : (T)CUDART_INF;
       ad[i] = ad[i] < -m ? -m : (ad[i] > m ? m : ad[i]);
     }
-  const T ail = fw_cond<T>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-er + el) * (T)0.5, fail);
-  const T elev = fw_cond<T>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (er + el) * (T)0.5, fail);
+  const T ail = fw_cond_r<T, Spec, FW_R_AIL>(P.var[FW_SV_AILERON], (-er + el) * (T)0.5, failmask);
+  const T elev = fw_cond_r<T, Spec, FW_R_ELEV>(P.var[FW_SV_ELEVATOR], (er + el) * (T)0.5, failmask);
   const T rud = (T)0;
 
   // ---- airspeed factors (PyFly._calculate_airspeed_factors with the quaternion rotation) ----
   T ur = u, vr = v, wr = w;
-  if (P.wind_enabled) {
+  if (Spec::generic && P.wind_enabled) {
     const T wn = in.wind[0], we = in.wind[1], wd = in.wind[2];
     ur -= ((T)-1 + 2 * (e0 * e0 + e1 * e1)) * wn + 2 * (e1 * e2 + e3 * e0) * we + 2 * (e1 * e3 - e2 * e0) * wd;
     vr -= 2 * (e1 * e2 - e3 * e0) * wn + ((T)-1 + 2 * (e0 * e0 + e2 * e2)) * we + 2 * (e2 * e3 + e1 * e0) * wd;
     wr -= 2 * (e1 * e3 + e2 * e0) * wn + 2 * (e2 * e3 - e1 * e0) * we + ((T)-1 + 2 * (e0 * e0 + e3 * e3)) * wd;
   }
-  T pa = p, qa = q, ra = r;
-  if (P.turbulence) {
-    ur -= in.gl[0]; vr -= in.gl[1]; wr -= in.gl[2];
-    pa -= in.ga[0]; qa -= in.ga[1]; ra -= in.ga[2];
-  }
+  // gusts are zero-filled by the caller when turbulence is off (x - 0 is exact)
+  ur -= in.gl[0]; vr -= in.gl[1]; wr -= in.gl[2];
+  const T pa = p - in.ga[0], qa = q - in.ga[1], ra = r - in.ga[2];
   // Va = |v_r|, alpha = atan2(w_r, u_r), beta = asin(v_r / Va) = atan2(v_r, hypot(u_r, w_r)): the two atan2 and the
   // two sqrt/rsqrt pairs are independent chains
   const T hxz2 = ur * ur + wr * wr;
-  T Va_raw, invVa, hxz, ih;
-  Mt::sqrt_rsqrt(hxz2 + vr * vr, &Va_raw, &invVa);
+  T Va_raw, invVa_raw, hxz, ih;
+  Mt::sqrt_rsqrt(hxz2 + vr * vr, &Va_raw, &invVa_raw);
   Mt::sqrt_rsqrt(hxz2, &hxz, &ih);
   T alpha = Mt::atan2_(wr, ur);
   T beta = Mt::atan2_(vr, hxz);
-  const T Va = fw_cond<T>(P.var[FW_SV_VA], FW_SV_VA, Va_raw, fail);
+  const T Va = fw_cond_r<T, Spec, FW_R_VA>(P.var[FW_SV_VA], Va_raw, failmask);
+  T invVa = invVa_raw;
   if (Va != Va_raw) invVa = Mt::rcp_(Va);   // value_min clip engaged (rare)
-  alpha = fw_cond<T>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, fail);
-  beta = fw_cond<T>(P.var[FW_SV_BETA], FW_SV_BETA, beta, fail);
+  alpha = fw_cond_r<T, Spec, FW_R_ALPHA>(P.var[FW_SV_ALPHA], alpha, failmask);
+  beta = fw_cond_r<T, Spec, FW_R_BETA>(P.var[FW_SV_BETA], beta, failmask);
 
   // ---- forces and moments (PyFly._forces) ----
   const T pre = (T)0.5 * (T)P.rho * Va * Va * (T)P.S_wing;
@@ -153,15 +194,15 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
     const T ex2 = Mt::exp_(fminf((T)P.M * (alpha + (T)P.a_0), 80.0f));
     sigma = (1 + ex1 + ex2) / ((1 + ex1) * (1 + ex2));
   }
-  // sin/cos of alpha and beta follow algebraically from the airspeed components when neither angle was altered by a
-  // clip (the usual configuration); otherwise fall back to sincos.
+  // sin/cos of alpha and beta follow algebraically from the airspeed components (beta = asin(v_r / |v_r|) uses the
+  // UNclipped airspeed) when neither angle was altered by a clip (the usual configuration); otherwise sincos.
   T sa, ca, sb, cb;
-  if ((P.var[FW_SV_ALPHA].flags | P.var[FW_SV_BETA].flags) == 0u && Va == Va_raw) {
+  if (!Spec::generic || (P.var[FW_SV_ALPHA].flags | P.var[FW_SV_BETA].flags) == 0u) {
     const bool nz = hxz > (T)0;
     sa = nz ? wr * ih : (T)0;
     ca = nz ? ur * ih : (T)1;
-    sb = vr * invVa;
-    cb = hxz * invVa;
+    sb = vr * invVa_raw;
+    cb = hxz * invVa_raw;
   } else {
     Mt::sincos_(alpha, &sa, &ca);
     Mt::sincos_(beta, &sb, &cb);
@@ -172,7 +213,7 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
   const T c2Va = (T)P.c * inv2Va, b2Va = (T)P.b * inv2Va;
   const T lift = pre * (CL + (T)P.C_L_q * c2Va * qa + (T)P.C_L_delta_e * elev);
   T CDa;
-  if (P.drag_model == 0)
+  if (!Spec::generic || P.drag_model == 0)
     CDa = (T)P.C_D_p + (1 - sigma) * CLlin * CLlin * (T)P.inv_pi_e_ar + sigma * (2 * sgn * sa * sa * sa);
   else
     CDa = (T)P.C_D_0 + (T)P.C_D_alpha1 * alpha + (T)P.C_D_alpha2 * alpha * alpha;
@@ -262,7 +303,7 @@ __device__ __forceinline__ float fw_rcp(float x) { return __frcp_rn(x); }
 //
 // Written as a phase machine around ONE right-hand-side call site (instruction-cache footprint): phase 0 evaluates
 // f(t0, y0), phase 1 the probe of select_initial_step, phases 2..7 the six evaluations of one dopri5 attempt.
-template <typename T, int BLOCK>
+template <typename T, class Spec, int BLOCK>
 __device__ __forceinline__ int fw_integrate_step(const fw_sim_t& P, const FwStepIn<T>& in, T (&y)[FW_N_ODE],
                                                  FwKStore<T, BLOCK> K, int& attempts, int& accepted, int& fail) {
   typedef FwMath<T> Mt;
@@ -305,8 +346,12 @@ __device__ __forceinline__ int fw_integrate_step(const fw_sim_t& P, const FwStep
       for (int j = 0; j < 3; ++j) ys[7 + j] = y[7 + j] + h * accB[j];
     }
 
-    fw_rhs<T>(P, in, ys, f, fail);
-    if (fail) return FW_STATUS_FINISHED;
+    uint32_t failmask = 0u;
+    fw_rhs<T, Spec>(P, in, ys, f, failmask);
+    if (failmask) {   // ConstraintException: the first violated variable in PyFly's evaluation order names it
+      fail = FW_TERM_FAIL_BASE + c_rank_sv[__ffs((int)failmask) - 1];
+      return FW_STATUS_FINISHED;
+    }
 
     // ------------------------------------------------------------------------------- consume the evaluation
     if (phase == 0) {

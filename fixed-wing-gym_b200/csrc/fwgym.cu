@@ -8,6 +8,7 @@
 //   fw_reset_kernel: explicit (masked) reset with optional injected initial states / targets.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -36,6 +37,7 @@ struct fw_handle_s {
   double* msum;              // FW_N_METRIC_SUMS
   cudaStream_t last_stream;
   int profiling;
+  int generic;                   // 1: the configuration needs FwSpecGeneric (see dynamics.cuh)
   std::vector<cudaEvent_t> ev;   // 3 events per profiled step: before dyn, between, after env
 };
 
@@ -62,7 +64,7 @@ struct FwDynArgs {
   unsigned long long* ctr;
 };
 
-template <typename T>
+template <typename T, class Spec>
 __global__ void __launch_bounds__(FW_DYN_BLOCK, FW_DYN_MIN_BLOCKS)
 fw_dyn_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -111,7 +113,7 @@ fw_dyn_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
 #pragma unroll
     for (int j = 0; j < FW_N_ODE; ++j) y[j] = (T)c.D(j);
 
-    fw_integrate_step<T, FW_DYN_BLOCK>(P, in, y, K, attempts, accepted, failv);
+    fw_integrate_step<T, Spec, FW_DYN_BLOCK>(P, in, y, K, attempts, accepted, failv);
 
     // ---- PyFly._set_states_from_ode_solution(save=True) + airspeed factors ----
     double yd[FW_N_ODE];
@@ -445,6 +447,39 @@ static int make_layout(const fw_config_t& cfg, int64_t n, FwLayout& L) {
   return FW_OK;
 }
 
+// Which dynamics-kernel instantiation covers this configuration (dynamics.cuh "kernel specialisation")
+static int needs_generic(const fw_sim_t& S) {
+  static const int rank_sv[FW_R_BETA + 1] = {FW_SV_OMEGA_P, FW_SV_OMEGA_Q, FW_SV_OMEGA_R, FW_SV_VEL_U, FW_SV_VEL_V,
+                                             FW_SV_VEL_W, FW_SV_ELEVON_L, FW_SV_ELEVON_R, FW_SV_THROTTLE,
+                                             FW_SV_AILERON, FW_SV_ELEVATOR, FW_SV_VA, FW_SV_ALPHA, FW_SV_BETA};
+  const char* force = getenv("FWGYM_FORCE_GENERIC");
+  if (force && force[0] == '1') return 1;
+  uint32_t clip = 0, cons = 0;
+  for (int r = 0; r <= FW_R_BETA; ++r) {
+    const uint32_t f = S.var[rank_sv[r]].flags;
+    if (f & (FW_VC_VMIN | FW_VC_VMAX)) clip |= FW_RB(r);
+    if (f & (FW_VC_CMIN | FW_VC_CMAX)) cons |= FW_RB(r);
+  }
+  for (int i = 0; i < FW_N_ACT; ++i)
+    if (S.act_has_dot_max[i]) clip |= FW_RB(FW_R_AD0 + i);
+  if (clip & ~FwSpecShipped::clip) return 1;
+  if (cons & ~FwSpecShipped::cons) return 1;
+  if (S.wind_enabled || S.drag_model != 0) return 1;
+  return 0;
+}
+
+template <typename T, class Spec>
+static cudaError_t launch_dyn(const fw_sim_t& sim, const FwDynArgs& da, int grid, cudaStream_t s) {
+  const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(T);
+  fw_dyn_kernel<T, Spec><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
+  return cudaGetLastError();
+}
+template <typename T, class Spec>
+static cudaError_t allow_dyn_smem() {   // per device: called from fw_create
+  return cudaFuncSetAttribute(fw_dyn_kernel<T, Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(T));
+}
+
 extern "C" {
 
 const char* fw_last_error(void) { return g_err; }
@@ -478,9 +513,11 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   CK(cudaMemset(h->i, 0, ib));
   CK(cudaMemset(h->ctr, 0, CTR_N * sizeof(unsigned long long)));
   CK(cudaMemset(h->msum, 0, FW_N_METRIC_SUMS * sizeof(double)));
-  const int smem64 = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(double);
-  CK(cudaFuncSetAttribute(fw_dyn_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
-  CK(cudaFuncSetAttribute(fw_dyn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64 / 2));
+  h->generic = needs_generic(h->cfg.sim);
+  CK((allow_dyn_smem<double, FwSpecShipped>()));
+  CK((allow_dyn_smem<double, FwSpecGeneric>()));
+  CK((allow_dyn_smem<float, FwSpecShipped>()));
+  CK((allow_dyn_smem<float, FwSpecGeneric>()));
   *out = h;
   return FW_OK;
 }
@@ -509,6 +546,7 @@ int fw_set_config(fw_handle h, const fw_config_t* cfg) {
   if (L.d_rows != h->L.d_rows || memcmp(&L, &h->L, sizeof(L)) != 0)
     return fail(FW_ERR_CONFIG, "fw_set_config: new config changes the state layout; create a new handle");
   h->cfg = *cfg;
+  h->generic = needs_generic(h->cfg.sim);
   return FW_OK;
 }
 
@@ -567,13 +605,12 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
     CK(cudaEventRecord(pe[0], s));
   }
   if (h->cfg.precision == 0) {
-    const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(double);
-    fw_dyn_kernel<double><<<dgrid, FW_DYN_BLOCK, smem, s>>>(h->cfg.sim, da);
+    CK((h->generic ? launch_dyn<double, FwSpecGeneric>(h->cfg.sim, da, dgrid, s)
+                   : launch_dyn<double, FwSpecShipped>(h->cfg.sim, da, dgrid, s)));
   } else {
-    const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(float);
-    fw_dyn_kernel<float><<<dgrid, FW_DYN_BLOCK, smem, s>>>(h->cfg.sim, da);
+    CK((h->generic ? launch_dyn<float, FwSpecGeneric>(h->cfg.sim, da, dgrid, s)
+                   : launch_dyn<float, FwSpecShipped>(h->cfg.sim, da, dgrid, s)));
   }
-  CK(cudaGetLastError());
   if (h->profiling) CK(cudaEventRecord(pe[1], s));
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
                term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum};

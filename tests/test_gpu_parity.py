@@ -55,6 +55,15 @@ def test_golden_fixture(built_lib, name):
     vec.close()
 
 
+@pytest.mark.parametrize("name", ["turb_noise", "failure"])
+def test_generic_kernel_instantiation(built_lib, name, monkeypatch):
+    """The dynamics kernel has two instantiations (dynamics.cuh): FwSpecShipped covers the shipped configurations and
+    FwSpecGeneric everything else (any variable clipped / constrained, steady wind, polynomial drag).  Force the
+    generic one and hold it to the same fixtures."""
+    monkeypatch.setenv("FWGYM_FORCE_GENERIC", "1")
+    test_golden_fixture(built_lib, name)
+
+
 def test_live_oracle_64_envs(built_lib):
     """BASELINE configs[1] at an oracle-sized N: per-step parity on identical states, actions and seeds."""
     c = CASES["default"]
