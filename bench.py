@@ -275,12 +275,14 @@ def run_gpu_arm(a):
             "clocks": clocks,
             "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": n * 3 * 4, "d2h_bytes_per_step": n * (vec.obs_dim * 4 + 4 + 1)},
-            "gpu_launches": int(2 * a.steps),
+            "gpu_launches": int(vec.launches_per_step * a.steps),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fl.value / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / (fl.value / 1e12), "traffic": traffic,
                          "peak_source": "DFMA micro-benchmark run in this process (fw_dfma_peak); MEASURED_PEAKS.json "
                                         "has no FP64 entry",
-                         "kernel": "fw_dyn_kernel<double>", "kernel_ms_per_launch": dyn_ms / max(1, prof_steps),
+                         "kernel": "fw_dyn_kernel<double> (%d re-grouping stage launches per step, timed together)"
+                                   % (vec.launches_per_step - 1),
+                         "kernel_ms_per_launch": dyn_ms / max(1, prof_steps),
                          "kernel_share_of_step": dyn_ms / max(1e-9, dyn_ms + env_ms),
                          "flops_per_env_step": "1080 + 3660*k, k = dopri5 attempts counted on device",
                          "mean_attempts_per_env_step": k_mean,

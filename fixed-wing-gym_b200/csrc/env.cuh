@@ -174,10 +174,21 @@ __device__ __forceinline__ void fw_ring_put(const FwEnvCtx& c, int row0, int dep
 // fixed_wing.py:776-846.  hist_len = len(history["error"][k]) = len(PyFly Variable.history); steps_count as in the
 // reference; `stale` selects the reset-time behaviour where the integrator reads the previous episode's history
 // (fixed_wing.py:317 runs before :318).
-template <typename OutF>
-__device__ __forceinline__ void fw_observation(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
-                                               const FwEnvCtx& c, FwEnvRng& rng, uint32_t flags, int steps_count,
-                                               int hist_len, bool at_reset, OutF out) {
+// Observation sink: float32 rows for the policy, optional float64 copy for parity checks.
+struct FwObsWriter {
+  float* o32;
+  double* o64;
+  int64_t base;
+  __device__ __forceinline__ void operator()(int idx, double v) const {
+    if (o32) o32[base + idx] = (float)v;
+    if (o64) o64[base + idx] = v;
+  }
+};
+
+// One out-of-line copy serves the step, terminal-observation and reset call sites (instruction-cache footprint).
+__device__ __noinline__ void fw_observation(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
+                                            const FwEnvCtx& c, FwEnvRng& rng, uint32_t flags, int steps_count,
+                                            int hist_len, bool at_reset, const FwObsWriter& out) {
   const int nv = E.obs_nvar, len = E.obs_len, step = E.obs_step;
   const int W = E.integration_window;
   for (int row = 0; row < len; ++row) {
@@ -390,10 +401,10 @@ __device__ __forceinline__ void fw_turb_advance(const fw_sim_t& P, const FwEnvCt
 }
 
 // PyFly.reset + FixedWingAircraft.reset for one env.  init_state rows: FW_N_SV + 3 (wind n,e,d); NaN = sample.
-template <typename OutF>
-__device__ __forceinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
-                                             uint32_t k0, uint32_t k1, uint32_t genv, const double* __restrict__ init_state,
-                                             const double* __restrict__ init_target, int64_t in_stride, OutF out) {
+__device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
+                                          uint32_t k0, uint32_t k1, uint32_t genv, const double* __restrict__ init_state,
+                                          const double* __restrict__ init_target, int64_t in_stride,
+                                          const FwObsWriter& out) {
   const uint32_t tick = (uint32_t)c.I(I_TICK);
   c.I(I_TICK) = (int32_t)(tick + 1u);
   c.I(I_EPTICK) = (int32_t)tick;

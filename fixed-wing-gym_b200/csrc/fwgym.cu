@@ -22,6 +22,7 @@
 #define FW_DYN_MIN_BLOCKS 8
 #define FW_ENV_BLOCK 128
 
+#define FW_MAX_STAGES 6
 enum { CTR_ENV_STEPS = 0, CTR_ATTEMPTS, CTR_ACCEPTED, CTR_WARP_MAX, CTR_WARP_STEPS, CTR_FAILURES, CTR_RESETS, CTR_N };
 enum { MS_EPISODES = 0, MS_SUCCESS, MS_RETURN, MS_LENGTH, MS_FAILURES, MS_STEPS_TERM, MS_SUCCESS_TERM, MS_GOAL_STEPS };
 
@@ -38,6 +39,12 @@ struct fw_handle_s {
   cudaStream_t last_stream;
   int profiling;
   int generic;                   // 1: the configuration needs FwSpecGeneric (see dynamics.cuh)
+  // staged re-grouping of the dynamics kernel: stage k parks its stragglers in carry[k % 2]
+  int n_stages;
+  int min_active[FW_MAX_STAGES];
+  double* carry_d[2];
+  int32_t* carry_i[2];
+  int32_t* carry_count;          // [FW_MAX_STAGES]
   std::vector<cudaEvent_t> ev;   // 3 events per profiled step: before dyn, between, after env
 };
 
@@ -53,6 +60,20 @@ static int fail(int code, const char* fmt, const char* a = "") {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ dynamics kernel
+// Staged re-grouping (DESIGN.md "divergence"): dopri5 needs 2..8 step attempts per env step and a warp costs its
+// slowest lane.  Stage 0 takes the envs in natural order and integrates while at least `min_active` lanes of the
+// warp are still going; then the finished lanes commit and the stragglers are PARKED: their solver state goes to a
+// carry buffer at a freshly claimed list position (coalesced), and the next stage picks the list up 32 at a time, so
+// its warps are full again.  The last stage runs with min_active = 1.  Per-env results do not depend on the grouping.
+enum { CY_Y = 0, CY_K0 = FW_N_ODE, CY_KP = CY_K0 + FW_N_KC, CY_T = CY_KP + 3, CY_H, CY_CMD, CY_ROWS = CY_CMD + 3 };
+enum { CI_ENV = 0, CI_ATTEMPTS, CI_ACCEPTED, CI_REJECTED, CI_ROWS };
+
+struct FwCarry {
+  double* d;        // [CY_ROWS][cap]
+  int32_t* i;       // [CI_ROWS][cap]
+  int32_t* count;   // entries
+};
+
 struct FwDynArgs {
   double* d;
   int32_t* i;
@@ -62,131 +83,206 @@ struct FwDynArgs {
   uint32_t k0, k1;
   uint32_t env_offset;
   unsigned long long* ctr;
+  FwCarry in, out;   // parked solver states: read by this stage (stage > 0) / written by it (unless last)
+  int64_t cap;       // row length of the carry buffers
+  int min_active;
 };
 
-template <typename T, class Spec>
+// ---- action -> actuator commands (fixed_wing.py:349-354,439-459; Actuation.set_and_constrain_commands) ----
+__device__ __forceinline__ void fw_commands(const fw_sim_t& P, const FwDynArgs& a, const FwEnvCtx& c, double (&cmd)[3]) {
+  double act[3];
+  if (a.actions_f64) {
+    const double* p = reinterpret_cast<const double*>(a.actions) + c.env * 3;
+    act[0] = p[0]; act[1] = p[1]; act[2] = p[2];
+  } else {
+    const float* p = reinterpret_cast<const float*>(a.actions) + c.env * 3;
+    act[0] = p[0]; act[1] = p[1]; act[2] = p[2];
+  }
+  if (P.scale_actions) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double x = act[j];
+      if (P.has_scale_low) x = fmax(x, P.scale_low);
+      if (P.has_scale_high) x = fmin(x, P.scale_high);
+      act[j] = (P.act_to_high[j] - P.act_to_low[j]) * (x - P.scale_low) / (P.scale_high - P.scale_low) + P.act_to_low[j];
+    }
+  }
+  int dummy = 0;
+  const double er_c = -1.0 * act[1] + act[0], el_c = act[1] + act[0];
+  cmd[0] = fw_cond<double>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, el_c, dummy);
+  cmd[1] = fw_cond<double>(P.var[FW_SV_ELEVON_R], FW_SV_ELEVON_R, er_c, dummy);
+  cmd[2] = fw_cond<double>(P.var[FW_SV_THROTTLE], FW_SV_THROTTLE, act[2], dummy);
+  c.D(D_CMD + 0) = fw_cond<double>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (cmd[1] + cmd[0]) / 2, dummy);
+  c.D(D_CMD + 1) = fw_cond<double>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-cmd[1] + cmd[0]) / 2, dummy);
+  c.D(D_CMD + 2) = cmd[2];
+}
+
+// ---- PyFly._set_states_from_ode_solution(save=True) + airspeed factors + next gust column ----
+template <typename T>
+__device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwDynArgs& a, const FwEnvCtx& c,
+                                               const FwIvp<T>& S) {
+  int failv = S.fail;
+  double yd[FW_N_ODE];
+#pragma unroll
+  for (int j = 0; j < FW_N_ODE; ++j) yd[j] = (double)S.y[j];
+  double roll = 0, pitch = 0, yaw = 0, Va = 0, alpha = 0, beta = 0, elev = 0, ail = 0;
+  if (!failv) {
+    const double qn = sqrt(yd[0] * yd[0] + yd[1] * yd[1] + yd[2] * yd[2] + yd[3] * yd[3]);
+    const double e0 = yd[0] / qn, e1 = yd[1] / qn, e2 = yd[2] / qn, e3 = yd[3] / qn;
+    yd[0] = e0; yd[1] = e1; yd[2] = e2; yd[3] = e3;
+    roll = atan2(2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
+    pitch = asin(2 * (e0 * e2 - e1 * e3));
+    yaw = atan2(2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
+    roll = fw_cond_wrap<double>(P.var[FW_SV_ROLL], FW_SV_ROLL, roll, failv);
+    pitch = fw_cond_wrap<double>(P.var[FW_SV_PITCH], FW_SV_PITCH, pitch, failv);
+    yaw = fw_cond_wrap<double>(P.var[FW_SV_YAW], FW_SV_YAW, yaw, failv);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) yd[4 + j] = fw_cond<double>(P.var[FW_SV_OMEGA_P + j], FW_SV_OMEGA_P + j, yd[4 + j], failv);
+    yd[13] = fw_cond<double>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, yd[13], failv);
+    yd[14] = fw_cond<double>(P.var[FW_SV_ELEVON_R], FW_SV_ELEVON_R, yd[14], failv);
+    yd[15] = fw_cond<double>(P.var[FW_SV_THROTTLE], FW_SV_THROTTLE, yd[15], failv);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (P.act_has_dot_max[j]) yd[16 + j] = fmin(fmax(yd[16 + j], -P.act_dot_max[j]), P.act_dot_max[j]);
+    ail = fw_cond<double>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-yd[14] + yd[13]) / 2, failv);
+    elev = fw_cond<double>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (yd[14] + yd[13]) / 2, failv);
+    double wb[3] = {0, 0, 0};
+    if (P.wind_enabled) {
+      const double wv[3] = {c.D(D_WIND + 0), c.D(D_WIND + 1), c.D(D_WIND + 2)};
+      fw_rot_euler(roll, pitch, yaw, wv, wb);
+    }
+    double gl[3] = {0, 0, 0};
+    if (P.turbulence) { gl[0] = c.D(D_GUST + 0); gl[1] = c.D(D_GUST + 1); gl[2] = c.D(D_GUST + 2); }
+    const double ur = yd[10] - (wb[0] + gl[0]), vr = yd[11] - (wb[1] + gl[1]), wr = yd[12] - (wb[2] + gl[2]);
+    Va = sqrt(ur * ur + vr * vr + wr * wr);
+    alpha = atan2(wr, ur);
+    beta = asin(vr / Va);
+    Va = fw_cond<double>(P.var[FW_SV_VA], FW_SV_VA, Va, failv);
+    alpha = fw_cond<double>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, failv);
+    beta = fw_cond<double>(P.var[FW_SV_BETA], FW_SV_BETA, beta, failv);
+  }
+  if (!failv) {
+#pragma unroll
+    for (int j = 0; j < FW_N_ODE; ++j) c.D(j) = yd[j];
+    c.D(D_ROLL) = roll; c.D(D_PITCH) = pitch; c.D(D_YAW) = yaw;
+    c.D(D_VA) = Va; c.D(D_ALPHA) = alpha; c.D(D_BETA) = beta;
+    c.D(D_ELEV) = elev; c.D(D_AIL) = ail;
+    if (P.turbulence) {   // gust column for the next sim step (cur_sim_step + 1)
+      double un[4];
+      fw_turb_noise(P, a.k0, a.k1, a.env_offset + (uint32_t)c.env, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
+      fw_turb_advance(P, c, un);
+    }
+  }
+  c.I(I_STATUS) = failv;
+  c.I(I_LASTK) = S.attempts;
+}
+
+template <typename T, class Spec, bool STAGE0>
 __global__ void __launch_bounds__(FW_DYN_BLOCK, FW_DYN_MIN_BLOCKS)
 fw_dyn_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwKStore<T, FW_DYN_BLOCK> K{reinterpret_cast<T*>(smem_raw)};
-  const int64_t env = (int64_t)blockIdx.x * FW_DYN_BLOCK + threadIdx.x;
-  const bool valid = env < a.n;
-  int attempts = 0, accepted = 0, failv = 0;
-  if (valid) {
-    FwEnvCtx c{a.d, a.i, a.stride, env};
-    // ---- action -> actuator commands (fixed_wing.py:349-354,439-459; Actuation.set_and_constrain_commands) ----
-    double act[3];
-    if (a.actions_f64) {
-      const double* p = reinterpret_cast<const double*>(a.actions) + env * 3;
-      act[0] = p[0]; act[1] = p[1]; act[2] = p[2];
-    } else {
-      const float* p = reinterpret_cast<const float*>(a.actions) + env * 3;
-      act[0] = p[0]; act[1] = p[1]; act[2] = p[2];
-    }
-    if (P.scale_actions) {
+  const int64_t slot = (int64_t)blockIdx.x * FW_DYN_BLOCK + threadIdx.x;
+  int64_t env = slot;
+  bool valid;
+  if (STAGE0) {
+    valid = slot < a.n;
+  } else {
+    const int64_t cnt = *a.in.count;
+    if ((int64_t)blockIdx.x * FW_DYN_BLOCK >= cnt) return;
+    valid = slot < cnt;
+    env = valid ? a.in.i[CI_ENV * a.cap + slot] : 0;
+  }
+  FwEnvCtx c{a.d, a.i, a.stride, env};
+  FwIvp<T> S;
+  FwStepIn<T> in;
+  S.status = valid ? FW_STATUS_RUNNING : FW_STATUS_FINISHED;
+  S.fail = 0; S.rejected = 0; S.attempts = 0; S.accepted = 0;
+  S.t = 0; S.h_abs = 0;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        double x = act[j];
-        if (P.has_scale_low) x = fmax(x, P.scale_low);   // np.clip propagates NaN; so do these for NaN in x? (fmax drops it)
-        if (P.has_scale_high) x = fmin(x, P.scale_high);
-        act[j] = (P.act_to_high[j] - P.act_to_low[j]) * (x - P.scale_low) / (P.scale_high - P.scale_low) + P.act_to_low[j];
-      }
+  for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { S.k0pos[j] = 0; in.cmd[j] = 0; in.gl[j] = 0; in.ga[j] = 0; in.wind[j] = 0; }
+  if (valid) {
+    if (STAGE0) {
+      double cmd[3];
+      fw_commands(P, a, c, cmd);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) in.cmd[j] = (T)cmd[j];
+#pragma unroll
+      for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = (T)c.D(j);
+    } else {
+      const double* cd = a.in.d + slot;
+      const int32_t* ci = a.in.i + slot;
+#pragma unroll
+      for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = (T)cd[(CY_Y + j) * a.cap];
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) K.at(0, kc) = (T)cd[(CY_K0 + kc) * a.cap];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { S.k0pos[j] = (T)cd[(CY_KP + j) * a.cap]; in.cmd[j] = (T)cd[(CY_CMD + j) * a.cap]; }
+      S.t = (T)cd[CY_T * a.cap];
+      S.h_abs = (T)cd[CY_H * a.cap];
+      S.attempts = ci[CI_ATTEMPTS * a.cap];
+      S.accepted = ci[CI_ACCEPTED * a.cap];
+      S.rejected = ci[CI_REJECTED * a.cap];
     }
-    int dummy = 0;
-    const double er_c = -1.0 * act[1] + act[0], el_c = act[1] + act[0];
-    const double cmd_el = fw_cond<double>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, el_c, dummy);
-    const double cmd_er = fw_cond<double>(P.var[FW_SV_ELEVON_R], FW_SV_ELEVON_R, er_c, dummy);
-    const double cmd_th = fw_cond<double>(P.var[FW_SV_THROTTLE], FW_SV_THROTTLE, act[2], dummy);
-    c.D(D_CMD + 0) = fw_cond<double>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (cmd_er + cmd_el) / 2, dummy);
-    c.D(D_CMD + 1) = fw_cond<double>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-cmd_er + cmd_el) / 2, dummy);
-    c.D(D_CMD + 2) = cmd_th;
-
-    FwStepIn<T> in;
-    in.cmd[0] = (T)cmd_el; in.cmd[1] = (T)cmd_er; in.cmd[2] = (T)cmd_th;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       in.gl[j] = P.turbulence ? (T)c.D(D_GUST + j) : (T)0;
       in.ga[j] = P.turbulence ? (T)c.D(D_GUST + 3 + j) : (T)0;
       in.wind[j] = P.wind_enabled ? (T)c.D(D_WIND + j) : (T)0;
     }
-    T y[FW_N_ODE];
-#pragma unroll
-    for (int j = 0; j < FW_N_ODE; ++j) y[j] = (T)c.D(j);
-
-    fw_integrate_step<T, Spec, FW_DYN_BLOCK>(P, in, y, K, attempts, accepted, failv);
-
-    // ---- PyFly._set_states_from_ode_solution(save=True) + airspeed factors ----
-    double yd[FW_N_ODE];
-#pragma unroll
-    for (int j = 0; j < FW_N_ODE; ++j) yd[j] = (double)y[j];
-    double roll = 0, pitch = 0, yaw = 0, Va = 0, alpha = 0, beta = 0, elev = 0, ail = 0;
-    if (!failv) {
-      const double qn = sqrt(yd[0] * yd[0] + yd[1] * yd[1] + yd[2] * yd[2] + yd[3] * yd[3]);
-      const double e0 = yd[0] / qn, e1 = yd[1] / qn, e2 = yd[2] / qn, e3 = yd[3] / qn;
-      yd[0] = e0; yd[1] = e1; yd[2] = e2; yd[3] = e3;
-      roll = atan2(2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
-      pitch = asin(2 * (e0 * e2 - e1 * e3));
-      yaw = atan2(2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
-      roll = fw_cond_wrap<double>(P.var[FW_SV_ROLL], FW_SV_ROLL, roll, failv);
-      pitch = fw_cond_wrap<double>(P.var[FW_SV_PITCH], FW_SV_PITCH, pitch, failv);
-      yaw = fw_cond_wrap<double>(P.var[FW_SV_YAW], FW_SV_YAW, yaw, failv);
-#pragma unroll
-      for (int j = 0; j < 9; ++j) yd[4 + j] = fw_cond<double>(P.var[FW_SV_OMEGA_P + j], FW_SV_OMEGA_P + j, yd[4 + j], failv);
-      yd[13] = fw_cond<double>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, yd[13], failv);
-      yd[14] = fw_cond<double>(P.var[FW_SV_ELEVON_R], FW_SV_ELEVON_R, yd[14], failv);
-      yd[15] = fw_cond<double>(P.var[FW_SV_THROTTLE], FW_SV_THROTTLE, yd[15], failv);
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        if (P.act_has_dot_max[j]) yd[16 + j] = fmin(fmax(yd[16 + j], -P.act_dot_max[j]), P.act_dot_max[j]);
-      ail = fw_cond<double>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-yd[14] + yd[13]) / 2, failv);
-      elev = fw_cond<double>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (yd[14] + yd[13]) / 2, failv);
-      double wb[3] = {0, 0, 0};
-      if (P.wind_enabled) {
-        const double wv[3] = {c.D(D_WIND + 0), c.D(D_WIND + 1), c.D(D_WIND + 2)};
-        fw_rot_euler(roll, pitch, yaw, wv, wb);
-      }
-      double gl[3] = {0, 0, 0};
-      if (P.turbulence) { gl[0] = c.D(D_GUST + 0); gl[1] = c.D(D_GUST + 1); gl[2] = c.D(D_GUST + 2); }
-      const double ur = yd[10] - (wb[0] + gl[0]), vr = yd[11] - (wb[1] + gl[1]), wr = yd[12] - (wb[2] + gl[2]);
-      Va = sqrt(ur * ur + vr * vr + wr * wr);
-      alpha = atan2(wr, ur);
-      beta = asin(vr / Va);
-      Va = fw_cond<double>(P.var[FW_SV_VA], FW_SV_VA, Va, failv);
-      alpha = fw_cond<double>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, failv);
-      beta = fw_cond<double>(P.var[FW_SV_BETA], FW_SV_BETA, beta, failv);
-    }
-    if (!failv) {
-#pragma unroll
-      for (int j = 0; j < FW_N_ODE; ++j) c.D(j) = yd[j];
-      c.D(D_ROLL) = roll; c.D(D_PITCH) = pitch; c.D(D_YAW) = yaw;
-      c.D(D_VA) = Va; c.D(D_ALPHA) = alpha; c.D(D_BETA) = beta;
-      c.D(D_ELEV) = elev; c.D(D_AIL) = ail;
-      if (P.turbulence) {   // gust column for the next sim step (cur_sim_step + 1)
-        double un[4];
-        fw_turb_noise(P, a.k0, a.k1, a.env_offset + (uint32_t)env, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
-        fw_turb_advance(P, c, un);
-      }
-    }
-    c.I(I_STATUS) = failv;
-    c.I(I_LASTK) = attempts;
   }
-  // ---- counters: one atomic per warp ----
+
+  const int passes = fw_integrate_warp<T, Spec, FW_DYN_BLOCK, STAGE0>(P, in, S, K, a.min_active);
+
+  // ---- finished lanes commit; stragglers are parked for the next stage ----
   const unsigned full = 0xffffffffu;
-  int sa = attempts, sc = accepted, mx = attempts, nf = failv ? 1 : 0, nv = valid ? 1 : 0;
+  const bool done = valid && S.status != FW_STATUS_RUNNING;
+  const bool park = valid && S.status == FW_STATUS_RUNNING;
+  const unsigned pm = __ballot_sync(full, park);
+  if (pm) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(a.out.count, __popc(pm));
+    base = __shfl_sync(full, base, 0);
+    if (park) {
+      const int64_t pos = base + __popc(pm & ((1u << lane) - 1u));
+      double* cd = a.out.d + pos;
+      int32_t* ci = a.out.i + pos;
+#pragma unroll
+      for (int j = 0; j < FW_N_ODE; ++j) cd[(CY_Y + j) * a.cap] = (double)S.y[j];
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) cd[(CY_K0 + kc) * a.cap] = (double)K.at(0, kc);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { cd[(CY_KP + j) * a.cap] = (double)S.k0pos[j]; cd[(CY_CMD + j) * a.cap] = (double)in.cmd[j]; }
+      cd[CY_T * a.cap] = (double)S.t;
+      cd[CY_H * a.cap] = (double)S.h_abs;
+      ci[CI_ENV * a.cap] = (int32_t)env;
+      ci[CI_ATTEMPTS * a.cap] = S.attempts;
+      ci[CI_ACCEPTED * a.cap] = S.accepted;
+      ci[CI_REJECTED * a.cap] = S.rejected;
+    }
+  }
+  if (done) fw_commit_step<T>(P, a, c, S);
+
+  // ---- counters: one atomic per warp ----
+  int sa = done ? S.attempts : 0, sc = done ? S.accepted : 0, nf = (done && S.fail) ? 1 : 0, nv = done ? 1 : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sa += __shfl_xor_sync(full, sa, o);
     sc += __shfl_xor_sync(full, sc, o);
     nf += __shfl_xor_sync(full, nf, o);
     nv += __shfl_xor_sync(full, nv, o);
-    mx = max(mx, __shfl_xor_sync(full, mx, o));
   }
-  if ((threadIdx.x & 31) == 0 && nv) {
-    atomicAdd(a.ctr + CTR_ENV_STEPS, (unsigned long long)nv);
-    atomicAdd(a.ctr + CTR_ATTEMPTS, (unsigned long long)sa);
-    atomicAdd(a.ctr + CTR_ACCEPTED, (unsigned long long)sc);
-    atomicAdd(a.ctr + CTR_WARP_MAX, (unsigned long long)mx);
-    atomicAdd(a.ctr + CTR_WARP_STEPS, 1ull);
+  if ((threadIdx.x & 31) == 0) {
+    if (nv) {
+      atomicAdd(a.ctr + CTR_ENV_STEPS, (unsigned long long)nv);
+      atomicAdd(a.ctr + CTR_ATTEMPTS, (unsigned long long)sa);
+      atomicAdd(a.ctr + CTR_ACCEPTED, (unsigned long long)sc);
+    }
+    atomicAdd(a.ctr + CTR_WARP_MAX, (unsigned long long)passes);   // warp passes (cost), all stages
+    if (STAGE0) atomicAdd(a.ctr + CTR_WARP_STEPS, 1ull);
     if (nf) atomicAdd(a.ctr + CTR_FAILURES, (unsigned long long)nf);
   }
 }
@@ -212,21 +308,10 @@ struct FwEnvArgs {
   double* msum;
 };
 
-struct FwObsWriter {
-  float* o32;
-  double* o64;
-  int64_t base;
-  __device__ __forceinline__ void operator()(int idx, double v) const {
-    if (o32) o32[base + idx] = (float)v;
-    if (o64) o64[base + idx] = v;
-  }
-};
-
-__global__ void __launch_bounds__(FW_ENV_BLOCK)
-fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
-              const FwEnvArgs a) {
-  const int64_t env = (int64_t)blockIdx.x * FW_ENV_BLOCK + threadIdx.x;
-  if (env >= a.n) return;
+// Env-side work of one env step for env `env` (fixed_wing.py:338-437 after the simulator call).  Episode-metric
+// contributions are returned in m[] / n_reset and summed per warp by the caller (one atomic per warp and metric).
+__device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvArgs& a,
+                                            int64_t env, double (&m)[FW_N_METRIC_SUMS], int& n_reset) {
   FwEnvCtx c{a.d, a.i, L.stride, env};
   uint32_t flags = (uint32_t)c.I(I_FLAGS);
   int steps = c.I(I_STEPS);
@@ -271,7 +356,7 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
       c.I(I_GOALRING + wd) = (int32_t)word;
       const int cnt = c.I(I_GOALCNT) + newb - oldb;
       c.I(I_GOALCNT) = cnt;
-      if (newb) atomicAdd(a.msum + MS_GOAL_STEPS, 1.0);
+      if (newb) m[MS_GOAL_STEPS] += 1.0;
       if (steps_tgt >= E.streak_req && (double)cnt / (double)E.streak_req >= E.streak_fraction) {
         achieved_on_step = !(flags & FWF_GOAL_ACHIEVED);
         flags |= FWF_GOAL_ACHIEVED | FWF_EP_SUCCESS;
@@ -306,11 +391,7 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
   }
   c.I(I_STEPS) = steps;
   const bool do_reset = done && a.auto_reset;
-  if (do_reset) {
-    if (a.term_obs_out) fw_observation(E, P, L, c, rng, flags, steps, hist_len, false, tw);
-  } else {
-    fw_observation(E, P, L, c, rng, flags, steps, hist_len, false, ow);
-  }
+  if (!do_reset || a.term_obs_out) fw_observation(E, P, L, c, rng, flags, steps, hist_len, false, do_reset ? tw : ow);
   c.I(I_FLAGS) = (int32_t)flags;
   const double epret = c.D(D_EPRET) + reward;
   c.D(D_EPRET) = epret;
@@ -319,19 +400,53 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
   a.done_out[env] = done ? 1 : 0;
   a.term_out[env] = term;
   if (done) {
-    atomicAdd(a.msum + MS_EPISODES, 1.0);
-    atomicAdd(a.msum + MS_RETURN, epret);
-    atomicAdd(a.msum + MS_LENGTH, (double)steps);
-    if (flags & FWF_EP_SUCCESS) atomicAdd(a.msum + MS_SUCCESS, 1.0);
-    if (term >= FW_TERM_FAIL_BASE) atomicAdd(a.msum + MS_FAILURES, 1.0);
-    if (term == FW_TERM_STEPS) atomicAdd(a.msum + MS_STEPS_TERM, 1.0);
-    if (term == FW_TERM_SUCCESS) atomicAdd(a.msum + MS_SUCCESS_TERM, 1.0);
+    m[MS_EPISODES] += 1.0;
+    m[MS_RETURN] += epret;
+    m[MS_LENGTH] += (double)steps;
+    if (flags & FWF_EP_SUCCESS) m[MS_SUCCESS] += 1.0;
+    if (term >= FW_TERM_FAIL_BASE) m[MS_FAILURES] += 1.0;
+    if (term == FW_TERM_STEPS) m[MS_STEPS_TERM] += 1.0;
+    if (term == FW_TERM_SUCCESS) m[MS_SUCCESS_TERM] += 1.0;
   }
   if (do_reset) {
-    atomicAdd(a.ctr + CTR_RESETS, 1ull);
+    n_reset += 1;
     fw_reset_env(E, P, L, c, a.k0, a.k1, genv, nullptr, nullptr, 0, ow);
   }
 }
+
+// per-warp sum of the metric contributions, then one atomic per non-zero metric (all 32 lanes must call)
+__device__ __forceinline__ void fw_flush_metrics(const FwEnvArgs& a, double (&m)[FW_N_METRIC_SUMS], int n_reset) {
+  const unsigned full = 0xffffffffu;
+  bool any = n_reset != 0;
+#pragma unroll
+  for (int k = 0; k < FW_N_METRIC_SUMS; ++k) any |= m[k] != 0.0;
+  if (!__any_sync(full, any)) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < FW_N_METRIC_SUMS; ++k) m[k] += __shfl_xor_sync(full, m[k], o);
+    n_reset += __shfl_xor_sync(full, n_reset, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < FW_N_METRIC_SUMS; ++k)
+      if (m[k] != 0.0) atomicAdd(a.msum + k, m[k]);
+    if (n_reset) atomicAdd(a.ctr + CTR_RESETS, (unsigned long long)n_reset);
+  }
+}
+
+__global__ void __launch_bounds__(FW_ENV_BLOCK, 4)
+fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
+              const FwEnvArgs a) {
+  const int64_t env = (int64_t)blockIdx.x * FW_ENV_BLOCK + threadIdx.x;
+  double m[FW_N_METRIC_SUMS];
+#pragma unroll
+  for (int k = 0; k < FW_N_METRIC_SUMS; ++k) m[k] = 0.0;
+  int n_reset = 0;
+  if (env < a.n) fw_env_step(E, P, L, a, env, m, n_reset);
+  fw_flush_metrics(a, m, n_reset);
+}
+
 
 struct FwResetArgs {
   double* d;
@@ -469,15 +584,36 @@ static int needs_generic(const fw_sim_t& S) {
 }
 
 template <typename T, class Spec>
-static cudaError_t launch_dyn(const fw_sim_t& sim, const FwDynArgs& da, int grid, cudaStream_t s) {
+static cudaError_t launch_dyn(const fw_sim_t& sim, const FwDynArgs& da, bool stage0, int grid, cudaStream_t s) {
   const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(T);
-  fw_dyn_kernel<T, Spec><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
+  if (stage0) fw_dyn_kernel<T, Spec, true><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
+  else fw_dyn_kernel<T, Spec, false><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
   return cudaGetLastError();
 }
 template <typename T, class Spec>
 static cudaError_t allow_dyn_smem() {   // per device: called from fw_create
-  return cudaFuncSetAttribute(fw_dyn_kernel<T, Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(T));
+  const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(T);
+  cudaError_t e = cudaFuncSetAttribute(fw_dyn_kernel<T, Spec, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fw_dyn_kernel<T, Spec, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+// FWGYM_STAGES="24,16": stage thresholds (min active lanes per warp before the stragglers are parked); a final
+// run-to-completion stage is always appended.  "" or "0" = single stage (no re-grouping).
+static void parse_stages(fw_handle_s* h) {
+  const char* e = getenv("FWGYM_STAGES");
+  const char* spec = e ? e : "24,16";
+  h->n_stages = 0;
+  const char* p = spec;
+  while (*p && h->n_stages < FW_MAX_STAGES - 1) {
+    char* end;
+    long v = strtol(p, &end, 10);
+    if (end == p) break;
+    if (v > 1 && v <= 32) h->min_active[h->n_stages++] = (int)v;
+    p = (*end == ',') ? end + 1 : end;
+    if (*end != ',') break;
+  }
+  h->min_active[h->n_stages++] = 1;
 }
 
 extern "C" {
@@ -509,6 +645,16 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
     delete h;
     return fail(FW_ERR_ALLOC, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  parse_stages(h);
+  h->carry_d[0] = h->carry_d[1] = nullptr; h->carry_i[0] = h->carry_i[1] = nullptr; h->carry_count = nullptr;
+  for (int k = 0; k < 2 && h->n_stages > 1; ++k)
+    if (cudaMalloc(&h->carry_d[k], (size_t)CY_ROWS * h->L.stride * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->carry_i[k], (size_t)CI_ROWS * h->L.stride * sizeof(int32_t)) != cudaSuccess) {
+      delete h;
+      return fail(FW_ERR_ALLOC, "cudaMalloc (carry) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  CK(cudaMalloc(&h->carry_count, FW_MAX_STAGES * sizeof(int32_t)));
+  CK(cudaMemset(h->carry_count, 0, FW_MAX_STAGES * sizeof(int32_t)));
   CK(cudaMemset(h->d, 0, db));
   CK(cudaMemset(h->i, 0, ib));
   CK(cudaMemset(h->ctr, 0, CTR_N * sizeof(unsigned long long)));
@@ -526,6 +672,8 @@ int fw_destroy(fw_handle h) {
   if (!h) return FW_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d); cudaFree(h->i); cudaFree(h->ctr); cudaFree(h->msum);
+  cudaFree(h->carry_d[0]); cudaFree(h->carry_d[1]); cudaFree(h->carry_i[0]); cudaFree(h->carry_i[1]);
+  cudaFree(h->carry_count);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
   return FW_OK;
@@ -552,6 +700,7 @@ int fw_set_config(fw_handle h, const fw_config_t* cfg) {
 
 int64_t fw_num_envs(fw_handle h) { return h ? h->n : 0; }
 int fw_obs_dim(fw_handle h) { return h ? h->cfg.env.obs_len * h->cfg.env.obs_nvar : 0; }
+int fw_launches_per_step(fw_handle h) { return h ? h->n_stages + 1 : 0; }
 int64_t fw_state_rows(fw_handle h) { return h ? h->L.d_rows + h->L.i_rows : 0; }
 
 const char* fw_state_row_name(fw_handle h, int64_t r) {
@@ -597,19 +746,27 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
-  FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, h->ctr};
+  FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, h->ctr,
+               FwCarry{nullptr, nullptr, nullptr}, FwCarry{nullptr, nullptr, nullptr}, h->L.stride, 1};
   const int dgrid = (int)((h->n + FW_DYN_BLOCK - 1) / FW_DYN_BLOCK);
   cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
   if (h->profiling) {
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
     CK(cudaEventRecord(pe[0], s));
   }
-  if (h->cfg.precision == 0) {
-    CK((h->generic ? launch_dyn<double, FwSpecGeneric>(h->cfg.sim, da, dgrid, s)
-                   : launch_dyn<double, FwSpecShipped>(h->cfg.sim, da, dgrid, s)));
-  } else {
-    CK((h->generic ? launch_dyn<float, FwSpecGeneric>(h->cfg.sim, da, dgrid, s)
-                   : launch_dyn<float, FwSpecShipped>(h->cfg.sim, da, dgrid, s)));
+  if (h->n_stages > 1) CK(cudaMemsetAsync(h->carry_count, 0, FW_MAX_STAGES * sizeof(int32_t), s));
+  for (int k = 0; k < h->n_stages; ++k) {
+    da.min_active = h->min_active[k];
+    if (k > 0) da.in = FwCarry{h->carry_d[(k - 1) & 1], h->carry_i[(k - 1) & 1], h->carry_count + (k - 1)};
+    da.out = FwCarry{h->carry_d[k & 1], h->carry_i[k & 1], h->carry_count + k};
+    // later stages are launched at the worst-case size; blocks beyond the parked count exit at once
+    if (h->cfg.precision == 0) {
+      CK((h->generic ? launch_dyn<double, FwSpecGeneric>(h->cfg.sim, da, k == 0, dgrid, s)
+                     : launch_dyn<double, FwSpecShipped>(h->cfg.sim, da, k == 0, dgrid, s)));
+    } else {
+      CK((h->generic ? launch_dyn<float, FwSpecGeneric>(h->cfg.sim, da, k == 0, dgrid, s)
+                     : launch_dyn<float, FwSpecShipped>(h->cfg.sim, da, k == 0, dgrid, s)));
+    }
   }
   if (h->profiling) CK(cudaEventRecord(pe[1], s));
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,

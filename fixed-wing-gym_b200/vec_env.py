@@ -95,6 +95,7 @@ class FixedWingVecEnv:
         _capi.check(self._lib.fw_create(ctypes.byref(pod), self.num_envs, self.env_offset,
                                         self.device.index or 0, ctypes.byref(self._h)))
         self.obs_dim = self._lib.fw_obs_dim(self._h)
+        self.launches_per_step = self._lib.fw_launches_per_step(self._h)
         n, d = self.num_envs, self.device
         self._obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=d)
         self._rew = torch.zeros(n, dtype=torch.float32, device=d)
