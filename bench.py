@@ -280,14 +280,13 @@ def run_gpu_arm(a):
                          "frac": achieved / (fl.value / 1e12), "traffic": traffic,
                          "peak_source": "DFMA micro-benchmark run in this process (fw_dfma_peak); MEASURED_PEAKS.json "
                                         "has no FP64 entry",
-                         "kernel": "fw_dyn_kernel<double> (%d re-grouping stage launches per step, timed together)"
-                                   % (vec.launches_per_step - 1),
+                         "kernel": "fw_init_kernel + fw_attempt_kernel <double> (the simulator step; timed together)",
                          "kernel_ms_per_launch": dyn_ms / max(1, prof_steps),
                          "kernel_share_of_step": dyn_ms / max(1e-9, dyn_ms + env_ms),
                          "flops_per_env_step": "1080 + 3660*k, k = dopri5 attempts counted on device",
                          "mean_attempts_per_env_step": k_mean,
-                         "warp_divergence": {"mean_warp_max_attempts": wmax / max(1.0, wsteps),
-                                             "lane_efficiency": attempts / max(1.0, 32.0 * wmax)}},
+                         "warp_divergence": {"warp_passes": wmax / world, "lane_attempts": wsteps / world,
+                                             "lane_efficiency": wsteps / max(1.0, 32.0 * wmax)}},
             "env_kernel": {"bound": "hbm", "ms_per_launch": env_ms / max(1, prof_steps),
                            "achieved_gbs": ENV_BYTES_PER_STEP * n / max(1e-9, env_ms / max(1, prof_steps) * 1e-3) / 1e9,
                            "peak_gbs": _measured_peaks().get("hbm_gbs")},

@@ -298,9 +298,9 @@ __device__ __forceinline__ double fw_rcp(double x) {
 __device__ __forceinline__ float fw_rcp(float x) { return __frcp_rn(x); }
 
 // ---- resumable scipy-RK45 state of ONE solve_ivp(fun, (0, dt), y0) call ---------------------------------------------
-// Everything an aircraft carries from one dopri5 step attempt to the next: between attempts it can live in registers
-// (the warp keeps integrating) or be parked in HBM (csrc/fwgym.cu: staged re-grouping) and picked up by another lane.
-// K0 = f(t, y) (FSAL) lives in slot 0 of the lane's K store; its position components in k0pos.
+// Everything an aircraft carries from one dopri5 step attempt to the next.  K0 = f(t, y) (FSAL) lives in slot 0 of the
+// lane's K store; its position components in k0pos.  Between the INIT kernel and the ATTEMPT kernel (csrc/fwgym.cu)
+// the state is parked in HBM, so any lane can pick any aircraft up at an attempt boundary.
 template <typename T> struct FwIvp {
   T y[FW_N_ODE];
   T k0pos[3];
@@ -311,190 +311,164 @@ template <typename T> struct FwIvp {
   int fail;          // != 0: ConstraintException raised by an RHS evaluation (FW_TERM_FAIL_BASE + sv)
 };
 
-// Advance the lanes of a warp through whole dopri5 step attempts until fewer than `min_active` lanes are still
-// integrating (min_active = 1: run every lane to completion).  MUST be called by all 32 lanes (warp votes); lanes
-// whose S.status != RUNNING idle.  With INIT the first pass also runs RK45.__init__ (f(t0, y0) and
-// select_initial_step), so the one right-hand-side call site below serves all eight kinds of evaluation
-// (instruction-cache footprint).  Returns the number of passes the warp made (its cost in "warp-attempts").
-//
-// Follows scipy/integrate/_ivp/rk.py:85-176 (_step_impl), common.py:68-134 (select_initial_step), base.py:179-210.
-template <typename T, class Spec, int BLOCK, bool INIT>
-__device__ __forceinline__ int fw_integrate_warp(const fw_sim_t& P, const FwStepIn<T>& in, FwIvp<T>& S,
-                                                 FwKStore<T, BLOCK> K, int min_active) {
+template <typename T>
+__device__ __forceinline__ int fw_fail_code(uint32_t failmask) {
+  // the first violated variable in PyFly's evaluation order names the ConstraintException
+  return FW_TERM_FAIL_BASE + c_rank_sv[__ffs((int)failmask) - 1];
+}
+
+// RK45.__init__: f0 = f(t0, y0) and select_initial_step (scipy/integrate/_ivp/common.py:68-134, rk.py:85-109).
+// Two right-hand-side evaluations.  Returns the failure code (0 = ok); on success f0 holds f(t0, y0) and h_abs the
+// initial step size (clamped to the interval; the min_step clamp of the first _step_impl call is applied by
+// fw_ivp_attempt like for every other entry).
+template <typename T, class Spec>
+__device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const FwStepIn<T>& in, const T (&y)[FW_N_ODE],
+                                           T (&f0)[FW_N_ODE], T& h_abs) {
   typedef FwMath<T> Mt;
   const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
   const T inv_sqrtn = (T)(1.0 / 4.358898943540674);   // 1 / 19 ** 0.5
-  bool first = INIT;
-  int passes = 0;
-  for (;;) {
-    const bool run = S.status == FW_STATUS_RUNNING;
-    const int nrun = __popc(__ballot_sync(0xffffffffu, run));
-    if (nrun == 0 || (!first && nrun < min_active)) break;
-    ++passes;
-    if (run) {
-      T accB[3], accE[3];    // running B-row / E-row sums of the position components (never stored as K stages)
-      T h = 0, t_new = 0, h0 = 0, d1 = 0;
-      int s = -1;            // -1: f(t0, y0); 0: probe of select_initial_step; 1..6: dopri5 stages of one attempt
-      if (!first) {
-        // ---- start a step attempt (rk.py:137-147); min_step = 10 * |nextafter(t, inf) - t| (rk.py:114)
-        const T min_step = 10 * fabs(Mt::next_up(S.t) - S.t);
-        if (!S.rejected && S.h_abs < min_step) S.h_abs = min_step;      // clamp on entry to _step_impl only
-        if (S.h_abs < min_step || S.attempts >= FW_MAX_ATTEMPTS) {
-          S.status = FW_STATUS_TOO_SMALL;   // (the attempt cap is a hang guard: NaN step sizes never shrink)
-        } else {
-          t_new = S.t + S.h_abs;
-          if (t_new - tb > 0) t_new = tb;
-          h = t_new - S.t;
-          S.h_abs = fabs(h);
-          ++S.attempts;
-        }
+  uint32_t failmask = 0u;
+  fw_rhs<T, Spec>(P, in, y, f0, failmask);
+  if (failmask) return fw_fail_code<T>(failmask);
+  T isc[FW_N_ODE];
+  T s0 = 0, s1 = 0;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { accB[j] = (T)c_dpA[6][0] * S.k0pos[j]; accE[j] = (T)c_dpE[0] * S.k0pos[j]; }
-        s = 1;
-      }
-#pragma unroll 1
-      for (; s <= 6 && S.status == FW_STATUS_RUNNING; ++s) {
-        T ys[FW_N_ODE], f[FW_N_ODE];
-        // ------------------------------------------------------------ the state the RHS is evaluated at
-        if (s < 0) {
-#pragma unroll
-          for (int c = 0; c < FW_N_ODE; ++c) ys[c] = S.y[c];
-        } else if (s == 0) {
-#pragma unroll
-          for (int kc = 0; kc < FW_N_KC; ++kc) { const int c = fw_kc_to_ode(kc); ys[c] = S.y[c] + h0 * K.at(0, kc); }
-#pragma unroll
-          for (int j = 0; j < 3; ++j) ys[7 + j] = S.y[7 + j] + h0 * S.k0pos[j];
-        } else {
-          T acc[FW_N_KC];
-#pragma unroll
-          for (int kc = 0; kc < FW_N_KC; ++kc) acc[kc] = 0;
-          for (int j = 0; j < s; ++j) {
-            const T a = (T)c_dpA[s][j];
-#pragma unroll
-            for (int kc = 0; kc < FW_N_KC; ++kc) acc[kc] += a * K.at(j, kc);
-          }
-#pragma unroll
-          for (int kc = 0; kc < FW_N_KC; ++kc) { const int c = fw_kc_to_ode(kc); ys[c] = S.y[c] + acc[kc] * h; }
-          // position stage states are never read by the RHS; y_new[pos] is formed from accB when s == 6
-#pragma unroll
-          for (int j = 0; j < 3; ++j) ys[7 + j] = S.y[7 + j] + h * accB[j];
-        }
-
-        uint32_t failmask = 0u;
-        fw_rhs<T, Spec>(P, in, ys, f, failmask);
-        if (failmask) {   // ConstraintException: the first violated variable in PyFly's evaluation order names it
-          S.fail = FW_TERM_FAIL_BASE + c_rank_sv[__ffs((int)failmask) - 1];
-          S.status = FW_STATUS_FINISHED;
-          break;
-        }
-
-        // ---------------------------------------------------------------------- consume the evaluation
-        if (s < 0) {
-          // RK45.__init__ / select_initial_step, first half (common.py:109-124)
-          T s0 = 0, s1 = 0;
-#pragma unroll
-          for (int c = 0; c < FW_N_ODE; ++c) {
-            const T isc = fw_rcp(atol + fabs(S.y[c]) * rtol);
-            const T a = S.y[c] * isc, b = f[c] * isc;
-            s0 += a * a;
-            s1 += b * b;
-          }
-#pragma unroll
-          for (int kc = 0; kc < FW_N_KC; ++kc) K.at(0, kc) = f[fw_kc_to_ode(kc)];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) S.k0pos[j] = f[7 + j];
-          const T d0 = Mt::sqrt_(s0) * inv_sqrtn;
-          d1 = Mt::sqrt_(s1) * inv_sqrtn;
-          h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : Mt::div_((T)0.01 * d0, d1);
-          h0 = h0 < tb ? h0 : tb;
-        } else if (s == 0) {
-          // select_initial_step, second half (common.py:125-134)
-          T s2 = 0;
-#pragma unroll
-          for (int c = 0; c < FW_N_ODE; ++c) {
-            const T isc = fw_rcp(atol + fabs(S.y[c]) * rtol);
-            const T f0c = (c >= 7 && c < 10) ? S.k0pos[c - 7] : K.at(0, c < 7 ? c : c - 3);
-            const T a = (f[c] - f0c) * isc;
-            s2 += a * a;
-          }
-          const T d2 = Mt::div_(Mt::sqrt_(s2) * inv_sqrtn, h0);
-          T h1;
-          if (d1 <= (T)1e-15 && d2 <= (T)1e-15) {
-            h1 = h0 * (T)1e-3;
-            h1 = h1 > (T)1e-6 ? h1 : (T)1e-6;
-          } else {
-            h1 = Mt::pow_(Mt::div_((T)0.01, d1 > d2 ? d1 : d2), (T)0.2);
-          }
-          T ha = 100 * h0;
-          ha = ha < h1 ? ha : h1;
-          ha = ha < tb ? ha : tb;
-          // first _step_impl call (rk.py:111-147) at t = 0
-          const T min_step = 10 * fabs(Mt::next_up((T)0) - (T)0);
-          if (ha < min_step) ha = min_step;
-          t_new = ha;
-          if (t_new - tb > 0) t_new = tb;
-          h = t_new;
-          S.h_abs = fabs(h);
-          S.rejected = 0;
-          ++S.attempts;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) { accB[j] = (T)c_dpA[6][0] * S.k0pos[j]; accE[j] = (T)c_dpE[0] * S.k0pos[j]; }
-        } else if (s < 6) {
-#pragma unroll
-          for (int kc = 0; kc < FW_N_KC; ++kc) K.at(s, kc) = f[fw_kc_to_ode(kc)];
-          const T b = (T)c_dpA[6][s], e = (T)c_dpE[s];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) { accB[j] += b * f[7 + j]; accE[j] += e * f[7 + j]; }
-        } else {
-          // s == 6: ys == y_new, f == f_new.  error = (K^T . E) * h ; scale = atol + max(|y|,|y_new|)*rtol
-          // (rk.py:150-152)
-          T se = 0;
-#pragma unroll
-          for (int kc = 0; kc < FW_N_KC; ++kc) {
-            const int c = fw_kc_to_ode(kc);
-            T e = (T)c_dpE[6] * f[c];
-#pragma unroll
-            for (int j = 0; j < 6; ++j)
-              if (j != 1) e += (T)c_dpE[j] * K.at(j, kc);
-            e *= h;
-            const T ay = fabs(S.y[c]), an = fabs(ys[c]);
-            const T q = e * fw_rcp(atol + (ay > an ? ay : an) * rtol);
-            se += q * q;
-          }
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const T e = (accE[j] + (T)c_dpE[6] * f[7 + j]) * h;
-            const T ay = fabs(S.y[7 + j]), an = fabs(ys[7 + j]);
-            const T q = e * fw_rcp(atol + (ay > an ? ay : an) * rtol);
-            se += q * q;
-          }
-          const T err = Mt::sqrt_(se) * inv_sqrtn;
-          // 0.9 * err ** -0.2 feeds both outcomes (rk.py:160-172); err == 0 gives a huge value that the min() below
-          // turns into MAX_FACTOR, exactly the reference's special case
-          const T pw = (T)0.9 * Mt::pow_(err, (T)-0.2);
-          if (err < (T)1) {
-            T factor = pw < (T)10 ? pw : (T)10;
-            if (S.rejected) factor = factor < (T)1 ? factor : (T)1;
-            S.h_abs *= factor;
-            S.t = t_new;
-#pragma unroll
-            for (int c = 0; c < FW_N_ODE; ++c) S.y[c] = ys[c];
-#pragma unroll
-            for (int kc = 0; kc < FW_N_KC; ++kc) K.at(0, kc) = f[fw_kc_to_ode(kc)];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) S.k0pos[j] = f[7 + j];
-            ++S.accepted;
-            S.rejected = 0;
-            if (S.t - tb >= 0) S.status = FW_STATUS_FINISHED;
-          } else {
-            // NaN error norms land here too: Python's max(0.2, nan) == 0.2
-            S.h_abs *= pw > (T)0.2 ? pw : (T)0.2;
-            S.rejected = 1;
-          }
-        }
-      }
-    }
-    first = false;
+  for (int c = 0; c < FW_N_ODE; ++c) {
+    isc[c] = fw_rcp(atol + fabs(y[c]) * rtol);
+    const T a = y[c] * isc[c], b = f0[c] * isc[c];
+    s0 += a * a;
+    s1 += b * b;
   }
-  return passes;
+  const T d0 = Mt::sqrt_(s0) * inv_sqrtn;
+  const T d1 = Mt::sqrt_(s1) * inv_sqrtn;
+  T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : Mt::div_((T)0.01 * d0, d1);
+  h0 = h0 < tb ? h0 : tb;
+  T y1[FW_N_ODE], f1[FW_N_ODE];
+#pragma unroll
+  for (int c = 0; c < FW_N_ODE; ++c) y1[c] = y[c] + h0 * f0[c];
+  fw_rhs<T, Spec>(P, in, y1, f1, failmask);
+  if (failmask) return fw_fail_code<T>(failmask);
+  T s2 = 0;
+#pragma unroll
+  for (int c = 0; c < FW_N_ODE; ++c) {
+    const T a = (f1[c] - f0[c]) * isc[c];
+    s2 += a * a;
+  }
+  const T d2 = Mt::div_(Mt::sqrt_(s2) * inv_sqrtn, h0);
+  T h1;
+  if (d1 <= (T)1e-15 && d2 <= (T)1e-15) {
+    h1 = h0 * (T)1e-3;
+    h1 = h1 > (T)1e-6 ? h1 : (T)1e-6;
+  } else {
+    h1 = Mt::pow_(Mt::div_((T)0.01, d1 > d2 ? d1 : d2), (T)0.2);
+  }
+  T ha = 100 * h0;
+  ha = ha < h1 ? ha : h1;
+  h_abs = ha < tb ? ha : tb;
+  return 0;
+}
+
+// ONE dopri5 step attempt (the body of the `while not step_accepted` loop of RK45._step_impl, rk.py:111-176) for a
+// lane whose S.status is RUNNING; six right-hand-side evaluations through one call site.  Updates S (and K slot 0 on
+// acceptance); sets S.status to FINISHED when t reaches t_bound or an RHS evaluation raises, TOO_SMALL when the step
+// size underflows.
+template <typename T, class Spec, int BLOCK>
+__device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const FwStepIn<T>& in, FwIvp<T>& S,
+                                               FwKStore<T, BLOCK> K) {
+  typedef FwMath<T> Mt;
+  const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
+  const T inv_sqrtn = (T)(1.0 / 4.358898943540674);
+  // ---- start a step attempt (rk.py:111-147); min_step = 10 * |nextafter(t, inf) - t|
+  const T min_step = 10 * fabs(Mt::next_up(S.t) - S.t);
+  if (!S.rejected && S.h_abs < min_step) S.h_abs = min_step;      // clamp on entry to _step_impl only
+  if (S.h_abs < min_step || S.attempts >= FW_MAX_ATTEMPTS) {
+    S.status = FW_STATUS_TOO_SMALL;   // (the attempt cap is a hang guard: NaN step sizes never shrink)
+    return;
+  }
+  T t_new = S.t + S.h_abs;
+  if (t_new - tb > 0) t_new = tb;
+  const T h = t_new - S.t;
+  S.h_abs = fabs(h);
+  ++S.attempts;
+  T accB[3], accE[3];    // running B-row / E-row sums of the position components (never stored as K stages)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { accB[j] = (T)c_dpA[6][0] * S.k0pos[j]; accE[j] = (T)c_dpE[0] * S.k0pos[j]; }
+#pragma unroll 1
+  for (int s = 1; s <= 6; ++s) {
+    T ys[FW_N_ODE], f[FW_N_ODE];
+    {
+      T acc[FW_N_KC];
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) acc[kc] = 0;
+      for (int j = 0; j < s; ++j) {
+        const T a = (T)c_dpA[s][j];
+#pragma unroll
+        for (int kc = 0; kc < FW_N_KC; ++kc) acc[kc] += a * K.at(j, kc);
+      }
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) { const int c = fw_kc_to_ode(kc); ys[c] = S.y[c] + acc[kc] * h; }
+      // position stage states are never read by the RHS; y_new[pos] is formed from accB when s == 6
+#pragma unroll
+      for (int j = 0; j < 3; ++j) ys[7 + j] = S.y[7 + j] + h * accB[j];
+    }
+    uint32_t failmask = 0u;
+    fw_rhs<T, Spec>(P, in, ys, f, failmask);
+    if (failmask) {
+      S.fail = fw_fail_code<T>(failmask);
+      S.status = FW_STATUS_FINISHED;
+      return;
+    }
+    if (s < 6) {
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) K.at(s, kc) = f[fw_kc_to_ode(kc)];
+      const T b = (T)c_dpA[6][s], e = (T)c_dpE[s];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { accB[j] += b * f[7 + j]; accE[j] += e * f[7 + j]; }
+      continue;
+    }
+    // s == 6: ys == y_new, f == f_new.  error = (K^T . E) * h ; scale = atol + max(|y|,|y_new|)*rtol (rk.py:150-152)
+    T se = 0;
+#pragma unroll
+    for (int kc = 0; kc < FW_N_KC; ++kc) {
+      const int c = fw_kc_to_ode(kc);
+      T e = (T)c_dpE[6] * f[c];
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j != 1) e += (T)c_dpE[j] * K.at(j, kc);
+      e *= h;
+      const T ay = fabs(S.y[c]), an = fabs(ys[c]);
+      const T q = e * fw_rcp(atol + (ay > an ? ay : an) * rtol);
+      se += q * q;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const T e = (accE[j] + (T)c_dpE[6] * f[7 + j]) * h;
+      const T ay = fabs(S.y[7 + j]), an = fabs(ys[7 + j]);
+      const T q = e * fw_rcp(atol + (ay > an ? ay : an) * rtol);
+      se += q * q;
+    }
+    const T err = Mt::sqrt_(se) * inv_sqrtn;
+    // 0.9 * err ** -0.2 feeds both outcomes (rk.py:160-172); err == 0 gives a huge value that the min() below turns
+    // into MAX_FACTOR, exactly the reference's special case
+    const T pw = (T)0.9 * Mt::pow_(err, (T)-0.2);
+    if (err < (T)1) {
+      T factor = pw < (T)10 ? pw : (T)10;
+      if (S.rejected) factor = factor < (T)1 ? factor : (T)1;
+      S.h_abs *= factor;
+      S.t = t_new;
+#pragma unroll
+      for (int c = 0; c < FW_N_ODE; ++c) S.y[c] = ys[c];
+#pragma unroll
+      for (int kc = 0; kc < FW_N_KC; ++kc) K.at(0, kc) = f[fw_kc_to_ode(kc)];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) S.k0pos[j] = f[7 + j];
+      ++S.accepted;
+      S.rejected = 0;
+      if (S.t - tb >= 0) S.status = FW_STATUS_FINISHED;
+    } else {
+      // NaN error norms land here too: Python's max(0.2, nan) == 0.2
+      S.h_abs *= pw > (T)0.2 ? pw : (T)0.2;
+      S.rejected = 1;
+    }
+  }
 }

@@ -22,7 +22,6 @@
 #define FW_DYN_MIN_BLOCKS 8
 #define FW_ENV_BLOCK 128
 
-#define FW_MAX_STAGES 6
 enum { CTR_ENV_STEPS = 0, CTR_ATTEMPTS, CTR_ACCEPTED, CTR_WARP_MAX, CTR_WARP_STEPS, CTR_FAILURES, CTR_RESETS, CTR_N };
 enum { MS_EPISODES = 0, MS_SUCCESS, MS_RETURN, MS_LENGTH, MS_FAILURES, MS_STEPS_TERM, MS_SUCCESS_TERM, MS_GOAL_STEPS };
 
@@ -39,12 +38,13 @@ struct fw_handle_s {
   cudaStream_t last_stream;
   int profiling;
   int generic;                   // 1: the configuration needs FwSpecGeneric (see dynamics.cuh)
-  // staged re-grouping of the dynamics kernel: stage k parks its stragglers in carry[k % 2]
-  int n_stages;
-  int min_active[FW_MAX_STAGES];
-  double* carry_d[2];
-  int32_t* carry_i[2];
-  int32_t* carry_count;          // [FW_MAX_STAGES]
+  // init -> attempt -> env pipeline (see "dynamics kernels")
+  double* carry_d;               // [CY_ROWS][stride]
+  int32_t* carry_i;              // [CI_ROWS][stride]
+  int32_t* long_list;            // [stride]
+  int32_t* queue;                // [Q_N]
+  int attempt_grid;              // persistent warps of the attempt kernel (resident capacity of the device)
+  double long_div, long_h;       // priority threshold on the initial step size: long_h = dt / long_div
   std::vector<cudaEvent_t> ev;   // 3 events per profiled step: before dyn, between, after env
 };
 
@@ -59,20 +59,24 @@ static int fail(int code, const char* fmt, const char* a = "") {
     if (e_ != cudaSuccess) return fail(FW_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e_)); \
   } while (0)
 
-// ------------------------------------------------------------------------------------------------ dynamics kernel
-// Staged re-grouping (DESIGN.md "divergence"): dopri5 needs 2..8 step attempts per env step and a warp costs its
-// slowest lane.  Stage 0 takes the envs in natural order and integrates while at least `min_active` lanes of the
-// warp are still going; then the finished lanes commit and the stragglers are PARKED: their solver state goes to a
-// carry buffer at a freshly claimed list position (coalesced), and the next stage picks the list up 32 at a time, so
-// its warps are full again.  The last stage runs with min_active = 1.  Per-env results do not depend on the grouping.
-enum { CY_Y = 0, CY_K0 = FW_N_ODE, CY_KP = CY_K0 + FW_N_KC, CY_T = CY_KP + 3, CY_H, CY_CMD, CY_ROWS = CY_CMD + 3 };
-enum { CI_ENV = 0, CI_ATTEMPTS, CI_ACCEPTED, CI_REJECTED, CI_ROWS };
-
-struct FwCarry {
-  double* d;        // [CY_ROWS][cap]
-  int32_t* i;       // [CI_ROWS][cap]
-  int32_t* count;   // entries
+// ----------------------------------------------------------------------------------------------- dynamics kernels
+// One env step of the simulator is three launches (DESIGN.md "pipeline"):
+//   fw_init_kernel    natural order, one thread per aircraft: action -> commands, f(t0, y0) and scipy's initial step
+//                     size (2 RHS evaluations), parked in the carry rows; aircraft that will need many attempts
+//                     (tiny first step, e.g. right after a reset) are put on a priority list.
+//   fw_attempt_kernel persistent warps (as many as fit the GPU), one aircraft per lane.  Each pass of a warp is ONE
+//                     dopri5 step attempt (6 RHS evaluations) for all its lanes; a lane whose aircraft finished its
+//                     env step parks the result and adopts the next waiting aircraft (priority list first, then the
+//                     natural order), so warps stay full although aircraft need 2..8 attempts.  Attempt boundaries
+//                     are the only points where an aircraft changes lanes, so all lanes of a warp are always in the
+//                     same dopri5 stage.  Per-aircraft results do not depend on the lane assignment.
+//   fw_env_kernel     natural order: PyFly's state commit + the env-side work (below).
+enum {
+  CY_K0 = 0, CY_KP = CY_K0 + FW_N_KC, CY_H = CY_KP + 3, CY_CMD, CY_RES = CY_CMD + 3,   // RES: 19 rows, final raw y
+  CY_ROWS = CY_RES + FW_N_ODE
 };
+enum { CI_FAIL = 0, CI_ATTEMPTS, CI_ACCEPTED, CI_ROWS };
+enum { Q_LONG_COUNT = 0, Q_LONG_CURSOR, Q_NAT_CURSOR, Q_N };
 
 struct FwDynArgs {
   double* d;
@@ -80,12 +84,12 @@ struct FwDynArgs {
   int64_t stride, n;
   const void* actions;
   int actions_f64;
-  uint32_t k0, k1;
-  uint32_t env_offset;
   unsigned long long* ctr;
-  FwCarry in, out;   // parked solver states: read by this stage (stage > 0) / written by it (unless last)
-  int64_t cap;       // row length of the carry buffers
-  int min_active;
+  double* cd;          // carry rows [CY_ROWS][stride]
+  int32_t* ci;         // carry int rows [CI_ROWS][stride]
+  int32_t* long_list;  // [stride] aircraft to start first
+  int32_t* q;          // [Q_N] queue counters, zeroed at the start of every step
+  double long_h;       // initial step sizes below this go on the priority list
 };
 
 // ---- action -> actuator commands (fixed_wing.py:349-354,439-459; Actuation.set_and_constrain_commands) ----
@@ -117,16 +121,171 @@ __device__ __forceinline__ void fw_commands(const fw_sim_t& P, const FwDynArgs& 
   c.D(D_CMD + 2) = cmd[2];
 }
 
-// ---- PyFly._set_states_from_ode_solution(save=True) + airspeed factors + next gust column ----
 template <typename T>
-__device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwDynArgs& a, const FwEnvCtx& c,
-                                               const FwIvp<T>& S) {
-  int failv = S.fail;
-  double yd[FW_N_ODE];
+__device__ __forceinline__ void fw_load_gusts(const fw_sim_t& P, const FwEnvCtx& c, FwStepIn<T>& in) {
 #pragma unroll
-  for (int j = 0; j < FW_N_ODE; ++j) yd[j] = (double)S.y[j];
-  double roll = 0, pitch = 0, yaw = 0, Va = 0, alpha = 0, beta = 0, elev = 0, ail = 0;
+  for (int j = 0; j < 3; ++j) {
+    in.gl[j] = P.turbulence ? (T)c.D(D_GUST + j) : (T)0;
+    in.ga[j] = P.turbulence ? (T)c.D(D_GUST + 3 + j) : (T)0;
+    in.wind[j] = P.wind_enabled ? (T)c.D(D_WIND + j) : (T)0;
+  }
+}
+
+#define FW_INIT_BLOCK 64
+template <typename T, class Spec>
+__global__ void __launch_bounds__(FW_INIT_BLOCK)
+fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
+  const int64_t env = (int64_t)blockIdx.x * FW_INIT_BLOCK + threadIdx.x;
+  const bool valid = env < a.n;
+  bool is_long = false;
+  if (valid) {
+    FwEnvCtx c{a.d, a.i, a.stride, env};
+    double cmd[3];
+    fw_commands(P, a, c, cmd);
+    FwStepIn<T> in;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) in.cmd[j] = (T)cmd[j];
+    fw_load_gusts<T>(P, c, in);
+    T y[FW_N_ODE], f0[FW_N_ODE], h_abs = 0;
+#pragma unroll
+    for (int j = 0; j < FW_N_ODE; ++j) y[j] = (T)c.D(j);
+    const int failv = fw_ivp_init<T, Spec>(P, in, y, f0, h_abs);
+    double* cd = a.cd + env;
+    int32_t* ci = a.ci + env;
+#pragma unroll
+    for (int kc = 0; kc < FW_N_KC; ++kc) cd[(CY_K0 + kc) * a.stride] = (double)f0[fw_kc_to_ode(kc)];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { cd[(CY_KP + j) * a.stride] = (double)f0[7 + j]; cd[(CY_CMD + j) * a.stride] = cmd[j]; }
+    cd[CY_H * a.stride] = (double)h_abs;
+    ci[CI_FAIL * a.stride] = failv;     // != 0: ConstraintException inside RK45.__init__; nothing left to integrate
+    ci[CI_ATTEMPTS * a.stride] = 0;
+    ci[CI_ACCEPTED * a.stride] = 0;
+    is_long = !failv && (double)h_abs < a.long_h;
+  }
+  // priority list: one atomic per warp
+  const unsigned full = 0xffffffffu;
+  const unsigned lm = __ballot_sync(full, is_long);
+  if (lm) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(a.q + Q_LONG_COUNT, __popc(lm));
+    base = __shfl_sync(full, base, 0);
+    if (is_long) a.long_list[base + __popc(lm & ((1u << lane) - 1u))] = (int32_t)env;
+  }
+}
+
+template <typename T, class Spec>
+__global__ void __launch_bounds__(FW_DYN_BLOCK, FW_DYN_MIN_BLOCKS)
+fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwKStore<T, FW_DYN_BLOCK> K{reinterpret_cast<T*>(smem_raw)};
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int n_long = a.q[Q_LONG_COUNT];     // final: the init kernel has completed
+  const int n_nat = (int)a.n;
+  FwIvp<T> S;
+  FwStepIn<T> in;
+  int64_t env = -1;
+  S.status = FW_STATUS_FINISHED;
+  S.fail = 0; S.rejected = 0; S.attempts = 0; S.accepted = 0; S.t = 0; S.h_abs = 0;
+#pragma unroll
+  for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { S.k0pos[j] = 0; in.cmd[j] = 0; in.gl[j] = 0; in.ga[j] = 0; in.wind[j] = 0; }
+  bool long_left = n_long > 0, nat_left = true;
+  unsigned long long passes = 0, lane_attempts = 0;
+  for (;;) {
+    // ---- lanes without an aircraft adopt the next waiting ones (priority list first) ----
+    const unsigned idle = __ballot_sync(full, S.status != FW_STATUS_RUNNING);
+    if (idle && (long_left || nat_left)) {
+      const int want = __popc(idle);
+      const int rank = __popc(idle & ((1u << lane) - 1u));
+      int got_long = 0, got_nat = 0, base_long = 0, base_nat = 0;
+      if (long_left) {
+        if (lane == 0) base_long = atomicAdd(a.q + Q_LONG_CURSOR, want);
+        base_long = __shfl_sync(full, base_long, 0);
+        got_long = min(want, max(0, n_long - base_long));
+        if (base_long + want >= n_long) long_left = false;
+      }
+      if (got_long < want && nat_left) {
+        const int need = want - got_long;
+        if (lane == 0) base_nat = atomicAdd(a.q + Q_NAT_CURSOR, need);
+        base_nat = __shfl_sync(full, base_nat, 0);
+        got_nat = min(need, max(0, n_nat - base_nat));
+        if (base_nat + need >= n_nat) nat_left = false;
+      }
+      if (S.status != FW_STATUS_RUNNING) {
+        const bool from_long = rank < got_long;
+        int64_t e = -1;
+        if (from_long) e = a.long_list[base_long + rank];
+        else if (rank - got_long < got_nat) e = (int64_t)base_nat + (rank - got_long);
+        env = -1;
+        if (e >= 0) {
+          const double* cd = a.cd + e;
+          const int32_t* ci = a.ci + e;
+          const double h0 = cd[CY_H * a.stride];
+          const int failv = ci[CI_FAIL * a.stride];
+          // skipped: aircraft that raised inside RK45.__init__ (the init kernel parked that result), and the
+          // natural-order visit of an aircraft that is on the priority list
+          const bool skip = failv != 0 || (!from_long && h0 < a.long_h);
+          if (!skip) {
+            env = e;
+            FwEnvCtx c{a.d, a.i, a.stride, e};
+#pragma unroll
+            for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = (T)c.D(j);
+#pragma unroll
+            for (int kc = 0; kc < FW_N_KC; ++kc) K.at(0, kc) = (T)cd[(CY_K0 + kc) * a.stride];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { S.k0pos[j] = (T)cd[(CY_KP + j) * a.stride]; in.cmd[j] = (T)cd[(CY_CMD + j) * a.stride]; }
+            fw_load_gusts<T>(P, c, in);
+            S.t = 0; S.h_abs = (T)h0; S.rejected = 0; S.attempts = 0; S.accepted = 0; S.fail = 0;
+            S.status = FW_STATUS_RUNNING;
+          }
+        }
+      }
+    }
+    const unsigned running = __ballot_sync(full, S.status == FW_STATUS_RUNNING);
+    if (!running) {
+      if (!long_left && !nat_left) break;
+      continue;   // everything adopted in this round was a skip; draw again
+    }
+    // ---- one dopri5 step attempt for every lane that holds an aircraft ----
+    ++passes;
+    if (S.status == FW_STATUS_RUNNING) {
+      ++lane_attempts;
+      fw_ivp_attempt<T, Spec, FW_DYN_BLOCK>(P, in, S, K);
+      if (S.status != FW_STATUS_RUNNING) {   // env step finished (or raised): park the result for the env kernel
+        double* cd = a.cd + env;
+        int32_t* ci = a.ci + env;
+#pragma unroll
+        for (int j = 0; j < FW_N_ODE; ++j) cd[(CY_RES + j) * a.stride] = (double)S.y[j];
+        ci[CI_FAIL * a.stride] = S.fail;
+        ci[CI_ATTEMPTS * a.stride] = S.attempts;
+        ci[CI_ACCEPTED * a.stride] = S.accepted;
+      }
+    }
+  }
+  // ---- counters: warp passes (cost) and lane attempts (useful work) ----
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lane_attempts += __shfl_xor_sync(full, lane_attempts, o);
+  if (lane == 0 && passes) {
+    atomicAdd(a.ctr + CTR_WARP_MAX, passes);
+    atomicAdd(a.ctr + CTR_WARP_STEPS, lane_attempts);
+  }
+}
+
+// ---- PyFly._set_states_from_ode_solution(save=True) + airspeed factors + next gust column (env kernel prologue) ----
+__device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx& c, const double* __restrict__ cd,
+                                               const int32_t* __restrict__ ci, int64_t stride, uint32_t k0, uint32_t k1,
+                                               uint32_t genv, int& attempts_out, int& accepted_out) {
+  int failv = ci[CI_FAIL * stride];
+  attempts_out = ci[CI_ATTEMPTS * stride];
+  accepted_out = ci[CI_ACCEPTED * stride];
   if (!failv) {
+    double yd[FW_N_ODE];
+#pragma unroll
+    for (int j = 0; j < FW_N_ODE; ++j) yd[j] = cd[(CY_RES + j) * stride];
+    double roll = 0, pitch = 0, yaw = 0, Va = 0, alpha = 0, beta = 0, elev = 0, ail = 0;
     const double qn = sqrt(yd[0] * yd[0] + yd[1] * yd[1] + yd[2] * yd[2] + yd[3] * yd[3]);
     const double e0 = yd[0] / qn, e1 = yd[1] / qn, e2 = yd[2] / qn, e3 = yd[3] / qn;
     yd[0] = e0; yd[1] = e1; yd[2] = e2; yd[3] = e3;
@@ -160,131 +319,21 @@ __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwDynArg
     Va = fw_cond<double>(P.var[FW_SV_VA], FW_SV_VA, Va, failv);
     alpha = fw_cond<double>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, failv);
     beta = fw_cond<double>(P.var[FW_SV_BETA], FW_SV_BETA, beta, failv);
-  }
-  if (!failv) {
+    if (!failv) {
 #pragma unroll
-    for (int j = 0; j < FW_N_ODE; ++j) c.D(j) = yd[j];
-    c.D(D_ROLL) = roll; c.D(D_PITCH) = pitch; c.D(D_YAW) = yaw;
-    c.D(D_VA) = Va; c.D(D_ALPHA) = alpha; c.D(D_BETA) = beta;
-    c.D(D_ELEV) = elev; c.D(D_AIL) = ail;
-    if (P.turbulence) {   // gust column for the next sim step (cur_sim_step + 1)
-      double un[4];
-      fw_turb_noise(P, a.k0, a.k1, a.env_offset + (uint32_t)c.env, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
-      fw_turb_advance(P, c, un);
+      for (int j = 0; j < FW_N_ODE; ++j) c.D(j) = yd[j];
+      c.D(D_ROLL) = roll; c.D(D_PITCH) = pitch; c.D(D_YAW) = yaw;
+      c.D(D_VA) = Va; c.D(D_ALPHA) = alpha; c.D(D_BETA) = beta;
+      c.D(D_ELEV) = elev; c.D(D_AIL) = ail;
+      if (P.turbulence) {   // gust column for the next sim step (cur_sim_step + 1)
+        double un[4];
+        fw_turb_noise(P, k0, k1, genv, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
+        fw_turb_advance(P, c, un);
+      }
     }
   }
   c.I(I_STATUS) = failv;
-  c.I(I_LASTK) = S.attempts;
-}
-
-template <typename T, class Spec, bool STAGE0>
-__global__ void __launch_bounds__(FW_DYN_BLOCK, FW_DYN_MIN_BLOCKS)
-fw_dyn_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FwKStore<T, FW_DYN_BLOCK> K{reinterpret_cast<T*>(smem_raw)};
-  const int64_t slot = (int64_t)blockIdx.x * FW_DYN_BLOCK + threadIdx.x;
-  int64_t env = slot;
-  bool valid;
-  if (STAGE0) {
-    valid = slot < a.n;
-  } else {
-    const int64_t cnt = *a.in.count;
-    if ((int64_t)blockIdx.x * FW_DYN_BLOCK >= cnt) return;
-    valid = slot < cnt;
-    env = valid ? a.in.i[CI_ENV * a.cap + slot] : 0;
-  }
-  FwEnvCtx c{a.d, a.i, a.stride, env};
-  FwIvp<T> S;
-  FwStepIn<T> in;
-  S.status = valid ? FW_STATUS_RUNNING : FW_STATUS_FINISHED;
-  S.fail = 0; S.rejected = 0; S.attempts = 0; S.accepted = 0;
-  S.t = 0; S.h_abs = 0;
-#pragma unroll
-  for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = 0;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) { S.k0pos[j] = 0; in.cmd[j] = 0; in.gl[j] = 0; in.ga[j] = 0; in.wind[j] = 0; }
-  if (valid) {
-    if (STAGE0) {
-      double cmd[3];
-      fw_commands(P, a, c, cmd);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) in.cmd[j] = (T)cmd[j];
-#pragma unroll
-      for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = (T)c.D(j);
-    } else {
-      const double* cd = a.in.d + slot;
-      const int32_t* ci = a.in.i + slot;
-#pragma unroll
-      for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = (T)cd[(CY_Y + j) * a.cap];
-#pragma unroll
-      for (int kc = 0; kc < FW_N_KC; ++kc) K.at(0, kc) = (T)cd[(CY_K0 + kc) * a.cap];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) { S.k0pos[j] = (T)cd[(CY_KP + j) * a.cap]; in.cmd[j] = (T)cd[(CY_CMD + j) * a.cap]; }
-      S.t = (T)cd[CY_T * a.cap];
-      S.h_abs = (T)cd[CY_H * a.cap];
-      S.attempts = ci[CI_ATTEMPTS * a.cap];
-      S.accepted = ci[CI_ACCEPTED * a.cap];
-      S.rejected = ci[CI_REJECTED * a.cap];
-    }
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      in.gl[j] = P.turbulence ? (T)c.D(D_GUST + j) : (T)0;
-      in.ga[j] = P.turbulence ? (T)c.D(D_GUST + 3 + j) : (T)0;
-      in.wind[j] = P.wind_enabled ? (T)c.D(D_WIND + j) : (T)0;
-    }
-  }
-
-  const int passes = fw_integrate_warp<T, Spec, FW_DYN_BLOCK, STAGE0>(P, in, S, K, a.min_active);
-
-  // ---- finished lanes commit; stragglers are parked for the next stage ----
-  const unsigned full = 0xffffffffu;
-  const bool done = valid && S.status != FW_STATUS_RUNNING;
-  const bool park = valid && S.status == FW_STATUS_RUNNING;
-  const unsigned pm = __ballot_sync(full, park);
-  if (pm) {
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(a.out.count, __popc(pm));
-    base = __shfl_sync(full, base, 0);
-    if (park) {
-      const int64_t pos = base + __popc(pm & ((1u << lane) - 1u));
-      double* cd = a.out.d + pos;
-      int32_t* ci = a.out.i + pos;
-#pragma unroll
-      for (int j = 0; j < FW_N_ODE; ++j) cd[(CY_Y + j) * a.cap] = (double)S.y[j];
-#pragma unroll
-      for (int kc = 0; kc < FW_N_KC; ++kc) cd[(CY_K0 + kc) * a.cap] = (double)K.at(0, kc);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) { cd[(CY_KP + j) * a.cap] = (double)S.k0pos[j]; cd[(CY_CMD + j) * a.cap] = (double)in.cmd[j]; }
-      cd[CY_T * a.cap] = (double)S.t;
-      cd[CY_H * a.cap] = (double)S.h_abs;
-      ci[CI_ENV * a.cap] = (int32_t)env;
-      ci[CI_ATTEMPTS * a.cap] = S.attempts;
-      ci[CI_ACCEPTED * a.cap] = S.accepted;
-      ci[CI_REJECTED * a.cap] = S.rejected;
-    }
-  }
-  if (done) fw_commit_step<T>(P, a, c, S);
-
-  // ---- counters: one atomic per warp ----
-  int sa = done ? S.attempts : 0, sc = done ? S.accepted : 0, nf = (done && S.fail) ? 1 : 0, nv = done ? 1 : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sa += __shfl_xor_sync(full, sa, o);
-    sc += __shfl_xor_sync(full, sc, o);
-    nf += __shfl_xor_sync(full, nf, o);
-    nv += __shfl_xor_sync(full, nv, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (nv) {
-      atomicAdd(a.ctr + CTR_ENV_STEPS, (unsigned long long)nv);
-      atomicAdd(a.ctr + CTR_ATTEMPTS, (unsigned long long)sa);
-      atomicAdd(a.ctr + CTR_ACCEPTED, (unsigned long long)sc);
-    }
-    atomicAdd(a.ctr + CTR_WARP_MAX, (unsigned long long)passes);   // warp passes (cost), all stages
-    if (STAGE0) atomicAdd(a.ctr + CTR_WARP_STEPS, 1ull);
-    if (nf) atomicAdd(a.ctr + CTR_FAILURES, (unsigned long long)nf);
-  }
+  c.I(I_LASTK) = attempts_out;
 }
 
 // ---------------------------------------------------------------------------------------------------- env kernel
@@ -306,13 +355,18 @@ struct FwEnvArgs {
   int obs_dim;
   unsigned long long* ctr;
   double* msum;
+  const double* cd;    // carry rows written by the init / attempt kernels
+  const int32_t* ci;
 };
 
 // Env-side work of one env step for env `env` (fixed_wing.py:338-437 after the simulator call).  Episode-metric
 // contributions are returned in m[] / n_reset and summed per warp by the caller (one atomic per warp and metric).
 __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvArgs& a,
-                                            int64_t env, double (&m)[FW_N_METRIC_SUMS], int& n_reset) {
+                                            int64_t env, double (&m)[FW_N_METRIC_SUMS], int& n_reset, int& attempts,
+                                            int& accepted, int& failed) {
   FwEnvCtx c{a.d, a.i, L.stride, env};
+  fw_commit_step(P, c, a.cd + env, a.ci + env, L.stride, a.k0, a.k1, a.env_offset + (uint32_t)env, attempts, accepted);
+  failed = c.I(I_STATUS) != 0;
   uint32_t flags = (uint32_t)c.I(I_FLAGS);
   int steps = c.I(I_STEPS);
   const int status = c.I(I_STATUS);
@@ -442,9 +496,24 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
   double m[FW_N_METRIC_SUMS];
 #pragma unroll
   for (int k = 0; k < FW_N_METRIC_SUMS; ++k) m[k] = 0.0;
-  int n_reset = 0;
-  if (env < a.n) fw_env_step(E, P, L, a, env, m, n_reset);
+  int n_reset = 0, attempts = 0, accepted = 0, failed = 0, nv = 0;
+  if (env < a.n) { fw_env_step(E, P, L, a, env, m, n_reset, attempts, accepted, failed); nv = 1; }
   fw_flush_metrics(a, m, n_reset);
+  // dopri5 counters (fw_counters): one atomic per warp
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    attempts += __shfl_xor_sync(full, attempts, o);
+    accepted += __shfl_xor_sync(full, accepted, o);
+    failed += __shfl_xor_sync(full, failed, o);
+    nv += __shfl_xor_sync(full, nv, o);
+  }
+  if ((threadIdx.x & 31) == 0 && nv) {
+    atomicAdd(a.ctr + CTR_ENV_STEPS, (unsigned long long)nv);
+    atomicAdd(a.ctr + CTR_ATTEMPTS, (unsigned long long)attempts);
+    atomicAdd(a.ctr + CTR_ACCEPTED, (unsigned long long)accepted);
+    if (failed) atomicAdd(a.ctr + CTR_FAILURES, (unsigned long long)failed);
+  }
 }
 
 
@@ -584,36 +653,28 @@ static int needs_generic(const fw_sim_t& S) {
 }
 
 template <typename T, class Spec>
-static cudaError_t launch_dyn(const fw_sim_t& sim, const FwDynArgs& da, bool stage0, int grid, cudaStream_t s) {
+static cudaError_t launch_dyn(const fw_sim_t& sim, const FwDynArgs& da, int attempt_grid, cudaStream_t s) {
+  const int igrid = (int)((da.n + FW_INIT_BLOCK - 1) / FW_INIT_BLOCK);
+  fw_init_kernel<T, Spec><<<igrid, FW_INIT_BLOCK, 0, s>>>(sim, da);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
   const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(T);
-  if (stage0) fw_dyn_kernel<T, Spec, true><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
-  else fw_dyn_kernel<T, Spec, false><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
+  const int64_t warps = (da.n + FW_DYN_BLOCK - 1) / FW_DYN_BLOCK;
+  const int grid = (int)(warps < attempt_grid ? warps : attempt_grid);
+  fw_attempt_kernel<T, Spec><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
   return cudaGetLastError();
 }
+// per device (called from fw_create): opt in to the K-stage shared memory and size the persistent grid
 template <typename T, class Spec>
-static cudaError_t allow_dyn_smem() {   // per device: called from fw_create
+static cudaError_t prepare_dyn(int sm_count, int* grid_out) {
   const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(T);
-  cudaError_t e = cudaFuncSetAttribute(fw_dyn_kernel<T, Spec, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(fw_attempt_kernel<T, Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fw_dyn_kernel<T, Spec, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-}
-
-// FWGYM_STAGES="24,16": stage thresholds (min active lanes per warp before the stragglers are parked); a final
-// run-to-completion stage is always appended.  "" or "0" = single stage (no re-grouping).
-static void parse_stages(fw_handle_s* h) {
-  const char* e = getenv("FWGYM_STAGES");
-  const char* spec = e ? e : "24,16";
-  h->n_stages = 0;
-  const char* p = spec;
-  while (*p && h->n_stages < FW_MAX_STAGES - 1) {
-    char* end;
-    long v = strtol(p, &end, 10);
-    if (end == p) break;
-    if (v > 1 && v <= 32) h->min_active[h->n_stages++] = (int)v;
-    p = (*end == ',') ? end + 1 : end;
-    if (*end != ',') break;
-  }
-  h->min_active[h->n_stages++] = 1;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fw_attempt_kernel<T, Spec>, FW_DYN_BLOCK, smem);
+  if (e != cudaSuccess) return e;
+  if (grid_out) *grid_out = per_sm * sm_count;
+  return cudaSuccess;
 }
 
 extern "C" {
@@ -645,25 +706,39 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
     delete h;
     return fail(FW_ERR_ALLOC, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  parse_stages(h);
-  h->carry_d[0] = h->carry_d[1] = nullptr; h->carry_i[0] = h->carry_i[1] = nullptr; h->carry_count = nullptr;
-  for (int k = 0; k < 2 && h->n_stages > 1; ++k)
-    if (cudaMalloc(&h->carry_d[k], (size_t)CY_ROWS * h->L.stride * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&h->carry_i[k], (size_t)CI_ROWS * h->L.stride * sizeof(int32_t)) != cudaSuccess) {
-      delete h;
-      return fail(FW_ERR_ALLOC, "cudaMalloc (carry) failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-  CK(cudaMalloc(&h->carry_count, FW_MAX_STAGES * sizeof(int32_t)));
-  CK(cudaMemset(h->carry_count, 0, FW_MAX_STAGES * sizeof(int32_t)));
+  h->carry_d = nullptr; h->carry_i = nullptr; h->long_list = nullptr; h->queue = nullptr;
+  if (cudaMalloc(&h->carry_d, (size_t)CY_ROWS * h->L.stride * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->carry_i, (size_t)CI_ROWS * h->L.stride * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&h->long_list, (size_t)h->L.stride * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&h->queue, Q_N * sizeof(int32_t)) != cudaSuccess) {
+    delete h;
+    return fail(FW_ERR_ALLOC, "cudaMalloc (carry) failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  CK(cudaMemset(h->carry_d, 0, (size_t)CY_ROWS * h->L.stride * sizeof(double)));
+  CK(cudaMemset(h->carry_i, 0, (size_t)CI_ROWS * h->L.stride * sizeof(int32_t)));
+  {
+    // aircraft whose first dopri5 step is below dt / FWGYM_LONG_DIV need the most attempts (e.g. the 1e-6 start after
+    // a reset): they are started first so that they do not become the tail of the attempt kernel
+    const char* e = getenv("FWGYM_LONG_DIV");
+    h->long_div = e ? atof(e) : 32.0;
+    h->long_h = h->long_div > 0 ? h->cfg.sim.dt / h->long_div : 0.0;
+  }
   CK(cudaMemset(h->d, 0, db));
   CK(cudaMemset(h->i, 0, ib));
   CK(cudaMemset(h->ctr, 0, CTR_N * sizeof(unsigned long long)));
   CK(cudaMemset(h->msum, 0, FW_N_METRIC_SUMS * sizeof(double)));
   h->generic = needs_generic(h->cfg.sim);
-  CK((allow_dyn_smem<double, FwSpecShipped>()));
-  CK((allow_dyn_smem<double, FwSpecGeneric>()));
-  CK((allow_dyn_smem<float, FwSpecShipped>()));
-  CK((allow_dyn_smem<float, FwSpecGeneric>()));
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int sms = prop.multiProcessorCount;
+    int g = 0;
+    if (h->cfg.precision == 0) CK((h->generic ? prepare_dyn<double, FwSpecGeneric>(sms, &g) : prepare_dyn<double, FwSpecShipped>(sms, &g)));
+    else CK((h->generic ? prepare_dyn<float, FwSpecGeneric>(sms, &g) : prepare_dyn<float, FwSpecShipped>(sms, &g)));
+    const char* e = getenv("FWGYM_ATTEMPT_WARPS_PER_SM");
+    if (e && atoi(e) > 0) g = atoi(e) * sms;
+    h->attempt_grid = g > 0 ? g : sms;
+  }
   *out = h;
   return FW_OK;
 }
@@ -672,8 +747,7 @@ int fw_destroy(fw_handle h) {
   if (!h) return FW_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d); cudaFree(h->i); cudaFree(h->ctr); cudaFree(h->msum);
-  cudaFree(h->carry_d[0]); cudaFree(h->carry_d[1]); cudaFree(h->carry_i[0]); cudaFree(h->carry_i[1]);
-  cudaFree(h->carry_count);
+  cudaFree(h->carry_d); cudaFree(h->carry_i); cudaFree(h->long_list); cudaFree(h->queue);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
   return FW_OK;
@@ -694,13 +768,23 @@ int fw_set_config(fw_handle h, const fw_config_t* cfg) {
   if (L.d_rows != h->L.d_rows || memcmp(&L, &h->L, sizeof(L)) != 0)
     return fail(FW_ERR_CONFIG, "fw_set_config: new config changes the state layout; create a new handle");
   h->cfg = *cfg;
-  h->generic = needs_generic(h->cfg.sim);
+  if (needs_generic(h->cfg.sim) != h->generic) {
+    h->generic = !h->generic;
+    cudaDeviceProp prop;
+    CK(cudaSetDevice(h->device));
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    int g = 0;
+    if (h->cfg.precision == 0) CK((h->generic ? prepare_dyn<double, FwSpecGeneric>(prop.multiProcessorCount, &g) : prepare_dyn<double, FwSpecShipped>(prop.multiProcessorCount, &g)));
+    else CK((h->generic ? prepare_dyn<float, FwSpecGeneric>(prop.multiProcessorCount, &g) : prepare_dyn<float, FwSpecShipped>(prop.multiProcessorCount, &g)));
+    if (g > 0) h->attempt_grid = g;
+  }
+  h->long_h = h->long_div > 0 ? h->cfg.sim.dt / h->long_div : 0.0;
   return FW_OK;
 }
 
 int64_t fw_num_envs(fw_handle h) { return h ? h->n : 0; }
 int fw_obs_dim(fw_handle h) { return h ? h->cfg.env.obs_len * h->cfg.env.obs_nvar : 0; }
-int fw_launches_per_step(fw_handle h) { return h ? h->n_stages + 1 : 0; }
+int fw_launches_per_step(fw_handle h) { return h ? 3 : 0; }
 int64_t fw_state_rows(fw_handle h) { return h ? h->L.d_rows + h->L.i_rows : 0; }
 
 const char* fw_state_row_name(fw_handle h, int64_t r) {
@@ -746,31 +830,25 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
-  FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, h->ctr,
-               FwCarry{nullptr, nullptr, nullptr}, FwCarry{nullptr, nullptr, nullptr}, h->L.stride, 1};
-  const int dgrid = (int)((h->n + FW_DYN_BLOCK - 1) / FW_DYN_BLOCK);
+  FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, h->ctr, h->carry_d, h->carry_i, h->long_list,
+               h->queue, h->long_h};
   cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
   if (h->profiling) {
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
     CK(cudaEventRecord(pe[0], s));
   }
-  if (h->n_stages > 1) CK(cudaMemsetAsync(h->carry_count, 0, FW_MAX_STAGES * sizeof(int32_t), s));
-  for (int k = 0; k < h->n_stages; ++k) {
-    da.min_active = h->min_active[k];
-    if (k > 0) da.in = FwCarry{h->carry_d[(k - 1) & 1], h->carry_i[(k - 1) & 1], h->carry_count + (k - 1)};
-    da.out = FwCarry{h->carry_d[k & 1], h->carry_i[k & 1], h->carry_count + k};
-    // later stages are launched at the worst-case size; blocks beyond the parked count exit at once
-    if (h->cfg.precision == 0) {
-      CK((h->generic ? launch_dyn<double, FwSpecGeneric>(h->cfg.sim, da, k == 0, dgrid, s)
-                     : launch_dyn<double, FwSpecShipped>(h->cfg.sim, da, k == 0, dgrid, s)));
-    } else {
-      CK((h->generic ? launch_dyn<float, FwSpecGeneric>(h->cfg.sim, da, k == 0, dgrid, s)
-                     : launch_dyn<float, FwSpecShipped>(h->cfg.sim, da, k == 0, dgrid, s)));
-    }
+  CK(cudaMemsetAsync(h->queue, 0, Q_N * sizeof(int32_t), s));
+  if (h->cfg.precision == 0) {
+    CK((h->generic ? launch_dyn<double, FwSpecGeneric>(h->cfg.sim, da, h->attempt_grid, s)
+                   : launch_dyn<double, FwSpecShipped>(h->cfg.sim, da, h->attempt_grid, s)));
+  } else {
+    CK((h->generic ? launch_dyn<float, FwSpecGeneric>(h->cfg.sim, da, h->attempt_grid, s)
+                   : launch_dyn<float, FwSpecShipped>(h->cfg.sim, da, h->attempt_grid, s)));
   }
   if (h->profiling) CK(cudaEventRecord(pe[1], s));
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
-               term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum};
+               term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum, h->carry_d,
+               h->carry_i};
   const int egrid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
   fw_env_kernel<<<egrid, FW_ENV_BLOCK, 0, s>>>(h->cfg.env, h->cfg.sim, h->L, ea);
   CK(cudaGetLastError());

@@ -166,8 +166,8 @@ typedef struct {
   uint64_t env_steps;        /* env steps executed since creation / last reset of counters */
   uint64_t attempts;         /* dopri5 step attempts (k summed over env steps) */
   uint64_t accepted;         /* accepted dopri5 steps */
-  uint64_t warp_max_attempts;/* sum over warps and env steps of the per-warp max k (divergence cost, in warp-attempts) */
-  uint64_t warp_steps;       /* number of (warp, env-step) pairs counted above */
+  uint64_t warp_max_attempts;/* warp passes of the attempt kernel: each pass is one dopri5 attempt for up to 32 lanes (cost) */
+  uint64_t warp_steps;       /* lane attempts executed in those passes (useful work); lane efficiency = this / (32 * passes) */
   uint64_t failures;         /* env steps that ended in a constraint failure */
   uint64_t resets;           /* auto + explicit episode resets */
   uint64_t rhs_evals;        /* RHS evaluations = 2*env_steps + 6*attempts */
