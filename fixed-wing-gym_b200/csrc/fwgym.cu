@@ -286,12 +286,15 @@ __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx
 #pragma unroll
     for (int j = 0; j < FW_N_ODE; ++j) yd[j] = cd[(CY_RES + j) * stride];
     double roll = 0, pitch = 0, yaw = 0, Va = 0, alpha = 0, beta = 0, elev = 0, ail = 0;
-    const double qn = sqrt(yd[0] * yd[0] + yd[1] * yd[1] + yd[2] * yd[2] + yd[3] * yd[3]);
-    const double e0 = yd[0] / qn, e1 = yd[1] / qn, e2 = yd[2] / qn, e3 = yd[3] / qn;
+    // quaternion / |quaternion|, Euler angles: fwmath routines (asin(x) = atan2(x, sqrt((1 - x)(1 + x))))
+    double qn, iqn;
+    fwm_sqrt_rsqrt(yd[0] * yd[0] + yd[1] * yd[1] + yd[2] * yd[2] + yd[3] * yd[3], &qn, &iqn);
+    const double e0 = yd[0] * iqn, e1 = yd[1] * iqn, e2 = yd[2] * iqn, e3 = yd[3] * iqn;
     yd[0] = e0; yd[1] = e1; yd[2] = e2; yd[3] = e3;
-    roll = atan2(2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
-    pitch = asin(2 * (e0 * e2 - e1 * e3));
-    yaw = atan2(2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
+    roll = fwm_atan2(2 * (e0 * e1 + e2 * e3), e0 * e0 + e3 * e3 - e1 * e1 - e2 * e2);
+    const double sp = 2 * (e0 * e2 - e1 * e3);
+    pitch = fwm_atan2(sp, fwm_sqrt((1 - sp) * (1 + sp)));
+    yaw = fwm_atan2(2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
     roll = fw_cond_wrap<double>(P.var[FW_SV_ROLL], FW_SV_ROLL, roll, failv);
     pitch = fw_cond_wrap<double>(P.var[FW_SV_PITCH], FW_SV_PITCH, pitch, failv);
     yaw = fw_cond_wrap<double>(P.var[FW_SV_YAW], FW_SV_YAW, yaw, failv);
@@ -313,9 +316,10 @@ __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx
     double gl[3] = {0, 0, 0};
     if (P.turbulence) { gl[0] = c.D(D_GUST + 0); gl[1] = c.D(D_GUST + 1); gl[2] = c.D(D_GUST + 2); }
     const double ur = yd[10] - (wb[0] + gl[0]), vr = yd[11] - (wb[1] + gl[1]), wr = yd[12] - (wb[2] + gl[2]);
-    Va = sqrt(ur * ur + vr * vr + wr * wr);
-    alpha = atan2(wr, ur);
-    beta = asin(vr / Va);
+    const double hxz2 = ur * ur + wr * wr;
+    Va = fwm_sqrt(hxz2 + vr * vr);
+    alpha = fwm_atan2(wr, ur);
+    beta = fwm_atan2(vr, fwm_sqrt(hxz2));   // asin(vr / Va)
     Va = fw_cond<double>(P.var[FW_SV_VA], FW_SV_VA, Va, failv);
     alpha = fw_cond<double>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, failv);
     beta = fw_cond<double>(P.var[FW_SV_BETA], FW_SV_BETA, beta, failv);

@@ -8,6 +8,7 @@
 //   index  : draw index inside (tick, stream).
 #pragma once
 #include <stdint.h>
+#include "fwmath.cuh"
 
 #define FW_RS_INIT 0    // PyFly Variable.reset uniform draws, index = fw_sv id
 #define FW_RS_WIND 1    // steady wind magnitude / components
@@ -54,9 +55,11 @@ __device__ __forceinline__ void fw_normal2(const FwRng& g, uint32_t stream, uint
   fw_philox4x32_10(g.env, g.tick, stream, idx, g.k0, g.k1, w);
   double u1 = 1.0 - fw_u53(w[0], w[1]);
   double u2 = fw_u53(w[2], w[3]);
-  double r = sqrt(-2.0 * log(u1));
+  // branch-free fwmath routines (csrc/fwmath.cuh): 14 observation-noise draws + 4 gust draws per env step make
+  // this the env kernel's largest block of arithmetic
+  double r = fwm_sqrt(-2.0 * fwm_log(u1));
   double s, c;
-  sincospi(2.0 * u2, &s, &c);
+  fwm_sincospi(2.0 * u2, &s, &c);
   z0 = r * c;
   z1 = r * s;
 }

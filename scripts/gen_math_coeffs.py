@@ -66,6 +66,19 @@ def log_L(w):       # ln(m) = 2f + 2f*w*L(w), f = (m-1)/(m+1), w = f*f   (atanh 
     return (mp.atanh(f) / f - 1) / w
 
 
+def sinpi_S(z):     # sin(pi r) = r*(pi + z*S(z)), z = r*r
+    if abs(z) < mp.mpf(10) ** -20:
+        return -mp.pi ** 3 / 6 + z * mp.pi ** 5 / 120
+    r = mp.sqrt(z)
+    return (mp.sin(mp.pi * r) / r - mp.pi) / z
+
+
+def cospi_C(z):     # cos(pi r) = 1 + z*C(z)
+    if abs(z) < mp.mpf(10) ** -20:
+        return -mp.pi ** 2 / 2 + z * mp.pi ** 4 / 24
+    return (mp.cos(mp.pi * mp.sqrt(z)) - 1) / z
+
+
 if __name__ == "__main__":
     tz = mp.tan(mp.pi / 8) ** 2
     fit("FW_ATAN_R", atan_R, mp.mpf(0), tz * (1 + mp.mpf(10) ** -6), mp.mpf(2) ** -54)
@@ -73,3 +86,6 @@ if __name__ == "__main__":
     fit("FW_EXP_P", exp_P, -h, h, mp.mpf(2) ** -52)
     fw = ((mp.sqrt(2) - 1) / (mp.sqrt(2) + 1)) ** 2
     fit("FW_LOG_L", log_L, mp.mpf(0), fw * (1 + mp.mpf(10) ** -6), mp.mpf(2) ** -49)
+    q = mp.mpf(1) / 16 * (1 + mp.mpf(10) ** -6)
+    fit("FW_SINPI_S", sinpi_S, mp.mpf(0), q, mp.mpf(2) ** -50)
+    fit("FW_COSPI_C", cospi_C, mp.mpf(0), q, mp.mpf(2) ** -51)

@@ -10,4 +10,6 @@ void t_sqrt(const double* x, double* o, long n) { for (long i = 0; i < n; ++i) o
 void t_rsqrt(const double* x, double* o, long n) { for (long i = 0; i < n; ++i) { double s; fwm_sqrt_rsqrt(x[i], &s, &o[i]); } }
 void t_rcp(const double* x, double* o, long n) { for (long i = 0; i < n; ++i) o[i] = fwm_rcp(x[i]); }
 void t_div(const double* a, const double* b, double* o, long n) { for (long i = 0; i < n; ++i) o[i] = fwm_div(a[i], b[i]); }
+void t_sinpi(const double* x, double* o, long n) { for (long i = 0; i < n; ++i) { double c; fwm_sincospi(x[i], &o[i], &c); } }
+void t_cospi(const double* x, double* o, long n) { for (long i = 0; i < n; ++i) { double s; fwm_sincospi(x[i], &s, &o[i]); } }
 }

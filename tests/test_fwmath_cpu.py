@@ -81,3 +81,20 @@ def test_sqrt_rcp_div(lib):
     assert ulps(call(lib, "t_div", a, b), a / b).max() <= 1
     assert call(lib, "t_sqrt", [0.0])[0] == 0.0
     assert np.isnan(call(lib, "t_sqrt", [np.nan])[0])
+
+
+def test_sincospi(lib):
+    import mpmath as mp
+    rng = np.random.RandomState(4)
+    x = np.concatenate([rng.uniform(0, 2, 200000), [0.0, 0.25, 0.5, 0.75, 1.0, 1.25, 1.5, 1.75, 1.9999999]])
+    s, c = call(lib, "t_sinpi", x), call(lib, "t_cospi", x)
+    # reference: exact sin/cos of pi*x (quadrant reduction done in exact arithmetic)
+    k = np.rint(2 * x)
+    r = x - k / 2
+    sr, cr = np.sin(np.pi * r), np.cos(np.pi * r)
+    q = k.astype(int) % 4
+    s_ref = np.where(q == 0, sr, np.where(q == 1, cr, np.where(q == 2, -sr, -cr)))
+    c_ref = np.where(q == 0, cr, np.where(q == 1, -sr, np.where(q == 2, -cr, sr)))
+    assert np.abs(s - s_ref).max() <= 4e-16 and np.abs(c - c_ref).max() <= 4e-16
+    for xv in (0.3, 1.7, 0.9999):
+        assert abs(call(lib, "t_sinpi", [xv])[0] - float(mp.sin(mp.pi * mp.mpf(xv)))) < 4e-16
