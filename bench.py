@@ -213,30 +213,32 @@ def run_gpu_arm(a):
     ctr = vec.counters()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end through the public API with HOST buffers: pinned actions in, obs/reward/done out, per step ----
-    h_act = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-    h_obs = torch.empty((n, vec.obs_dim), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
-    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
-    d_act = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    host_actions = (torch.rand((a.steps + 2, n, 3)) * 2 - 1)
+    # ---- end-to-end through the public API with HOST buffers (fwgym_b200.HostStepper): every step moves its actions
+    # pinned-host -> device and its observations / rewards / dones device -> pinned-host; two submissions in flight,
+    # so the PCIe traffic of step t overlaps the kernels of step t+1.  The loop ends when the LAST step's results
+    # are on the host.
+    from fwgym_b200 import HostStepper
+    stepper = HostStepper(vec, depth=2)
+    host_actions = (torch.rand((a.steps + 4, n, 3)) * 2 - 1)
     e2e_steps = a.steps
+    checksum = 0.0
 
-    def e2e_step(i):
-        h_act.copy_(host_actions[i])
-        d_act.copy_(h_act, non_blocking=True)
-        obs, rew, done, _ = vec.step_tensors(d_act)
-        h_obs.copy_(obs.view(n, -1), non_blocking=True)
-        h_rew.copy_(rew, non_blocking=True)
-        h_done.copy_(done, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+    def e2e_run(first, count):
+        nonlocal checksum
+        pending = []
+        for i in range(count):
+            pending.append(stepper.submit(host_actions[first + i]))
+            if len(pending) == stepper.depth:
+                obs, rew, done = stepper.wait(pending.pop(0))
+                checksum += float(rew[0])          # touch the host result of every step
+        while pending:
+            obs, rew, done = stepper.wait(pending.pop(0))
+            checksum += float(rew[0])
 
-    for i in range(2):
-        e2e_step(i)
+    e2e_run(0, 4)
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(2 + i)
+    e2e_run(4, e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -274,7 +276,8 @@ def run_gpu_arm(a):
                        "parallelism": "env-sharded x%d, no step-path collective" % world},
             "clocks": clocks,
             "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
-                    "h2d_bytes_per_step": n * 3 * 4, "d2h_bytes_per_step": n * (vec.obs_dim * 4 + 4 + 1)},
+                    "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes,
+                    "how": "HostStepper(depth=2): pinned host buffers, copies on their own streams, wall clock"},
             "gpu_launches": int(vec.launches_per_step * a.steps),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fl.value / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / (fl.value / 1e12), "traffic": traffic,

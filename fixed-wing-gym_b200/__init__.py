@@ -4,5 +4,5 @@ The directory is named `fixed-wing-gym_b200/` (not an importable identifier); im
 alias package at the repo root.
 """
 from .config import CompiledConfig, ConfigError  # noqa: F401
-from .vec_env import FixedWingVecEnv, Box  # noqa: F401
+from .vec_env import FixedWingVecEnv, HostStepper, Box  # noqa: F401
 from .env import FixedWingAircraft  # noqa: F401

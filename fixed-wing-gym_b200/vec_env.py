@@ -175,9 +175,10 @@ class FixedWingVecEnv:
                                        self._ptr(self._obs), self._ptr(self._obs64), self._stream()))
         return self._shape_obs(self._obs)
 
-    def step_tensors(self, actions):
+    def step_tensors(self, actions, out=None):
         """Device-only step: (obs, reward, done, term_code) tensors, no host synchronisation.
-        actions: [N, 3] float32 or float64 CUDA tensor (float64 is upcast-free and used for parity)."""
+        actions: [N, 3] float32 or float64 CUDA tensor (float64 is upcast-free and used for parity).
+        out: optional (obs, rew, done, term) device tensors to write instead of the env's own (HostStepper)."""
         if actions.device != self.device:
             actions = actions.to(self.device, non_blocking=True)
         if actions.dtype not in (torch.float32, torch.float64):
@@ -185,12 +186,13 @@ class FixedWingVecEnv:
         actions = actions.contiguous()
         if actions.shape != (self.num_envs, 3):
             raise ValueError("actions must have shape (%d, 3)" % self.num_envs)
+        obs, rew, done, term = out if out is not None else (self._obs, self._rew, self._done, self._term)
         _capi.check(self._lib.fw_step(self._h, self._ptr(actions), 1 if actions.dtype == torch.float64 else 0,
-                                      self._ptr(self._obs), self._ptr(self._rew), self._ptr(self._done),
-                                      self._ptr(self._term), self._ptr(self._obs64), self._ptr(self._rew64),
+                                      self._ptr(obs), self._ptr(rew), self._ptr(done),
+                                      self._ptr(term), self._ptr(self._obs64), self._ptr(self._rew64),
                                       self._ptr(self._term_obs), 1 if self.auto_reset else 0, self._stream()))
         self._actions = actions   # keep alive until the stream has consumed it
-        return self._shape_obs(self._obs), self._rew, self._done, self._term
+        return self._shape_obs(obs), rew, done, term
 
     def step_async(self, actions):
         if not torch.is_tensor(actions):
@@ -312,6 +314,66 @@ class FixedWingVecEnv:
         self.cc.set_curriculum_level(level)
         pod = self.cc.pod()
         _capi.check(self._lib.fw_set_config(self._h, ctypes.byref(pod)))
+
+
+class HostStepper:
+    """Host-buffer stepping for callers whose policy lives on the CPU: actions come from (pinned) host memory and
+    observations / rewards / dones land in pinned host memory, every step.  The copies run on their own CUDA streams
+    and the device-side buffers are double-buffered, so with `depth` submissions in flight the PCIe traffic of step t
+    overlaps the kernels of step t+1 (the SubprocVecEnv reference overlaps its pipe traffic with env work the same
+    way, one process per env).  submit() never blocks on the GPU; wait() blocks until that step's results are on the
+    host.  With depth=1 this is a plain synchronous host step."""
+
+    def __init__(self, vec, depth=2):
+        self.vec, self.depth = vec, int(depth)
+        n, d, od = vec.num_envs, vec.device, vec.obs_dim
+        self.s_in, self.s_out = torch.cuda.Stream(d), torch.cuda.Stream(d)
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append(dict(
+                h_act=mk((n, 3), torch.float32), h_obs=mk((n, od), torch.float32), h_rew=mk((n,), torch.float32),
+                h_done=mk((n,), torch.uint8),
+                d_act=torch.empty((n, 3), dtype=torch.float32, device=d),
+                d_obs=torch.empty((n, od), dtype=torch.float32, device=d),
+                d_rew=torch.empty(n, dtype=torch.float32, device=d), d_done=torch.empty(n, dtype=torch.uint8, device=d),
+                d_term=torch.empty(n, dtype=torch.int32, device=d),
+                e_in=torch.cuda.Event(), e_step=torch.cuda.Event(), e_out=torch.cuda.Event(), busy=False))
+        self.k = 0
+        self.h2d_bytes = n * 3 * 4
+        self.d2h_bytes = n * (od * 4 + 4 + 1)
+
+    def submit(self, actions):
+        """actions: [N, 3] float32 numpy array or CPU tensor.  Returns the slot to wait() on."""
+        v = self.vec
+        sl = self.slots[self.k % self.depth]
+        if sl["busy"]:
+            raise RuntimeError("HostStepper: wait() for the oldest submission before submitting again")
+        a = actions if torch.is_tensor(actions) else torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32))
+        sl["h_act"].copy_(a)
+        cur = torch.cuda.current_stream(v.device)
+        with torch.cuda.stream(self.s_in):
+            sl["d_act"].copy_(sl["h_act"], non_blocking=True)
+            sl["e_in"].record(self.s_in)
+        cur.wait_event(sl["e_in"])
+        v.step_tensors(sl["d_act"], out=(sl["d_obs"], sl["d_rew"], sl["d_done"], sl["d_term"]))
+        sl["e_step"].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(sl["e_step"])
+            sl["h_obs"].copy_(sl["d_obs"], non_blocking=True)
+            sl["h_rew"].copy_(sl["d_rew"], non_blocking=True)
+            sl["h_done"].copy_(sl["d_done"], non_blocking=True)
+            sl["e_out"].record(self.s_out)
+        sl["busy"] = True
+        self.k += 1
+        return sl
+
+    def wait(self, sl):
+        """-> (obs [N, obs_dim] float32, reward [N] float32, done [N] uint8) numpy views of the slot's pinned buffers
+        (valid until the slot is submitted again)."""
+        sl["e_out"].synchronize()
+        sl["busy"] = False
+        return sl["h_obs"].numpy(), sl["h_rew"].numpy(), sl["h_done"].numpy()
 
 
 class SimulatorView:
