@@ -36,7 +36,7 @@ struct FwEnvRng {
 };
 
 // current value of a PyFly state variable (`simulator.state[name].value`)
-__device__ __forceinline__ double fw_sv_value(const FwEnvCtx& c, int sv) {
+__device__ __noinline__ double fw_sv_value(const FwEnvCtx& c, int sv) {
   switch (sv) {
     case FW_SV_ROLL: return c.D(D_ROLL);
     case FW_SV_PITCH: return c.D(D_PITCH);
@@ -64,7 +64,7 @@ __device__ __forceinline__ double fw_sv_value(const FwEnvCtx& c, int sv) {
 }
 
 // python float floor-mod x % m for m > 0
-__device__ __forceinline__ double fw_pymod(double x, double m) {
+__device__ __noinline__ double fw_pymod(double x, double m) {
   double r = fmod(x, m);
   if (r != 0.0 && r < 0.0) r += m;
   return r;
@@ -380,23 +380,32 @@ __device__ __forceinline__ void fw_turb_noise(const fw_sim_t& P, uint32_t k0, ui
   for (int j = 0; j < 4; ++j) u[j] *= P.turb_noise_scale;
 }
 
-// advance the six shaping filters by one sample (scipy lsim recurrence) and refresh the gust rows
+// advance the six shaping filters by one sample (scipy lsim recurrence) and refresh the gust rows.  The host zero-pads
+// Ad / Bd0 / Bd1 / C of filters of order < 3 (config.py), so the loops are fixed-size and everything stays in registers.
 __device__ __forceinline__ void fw_turb_advance(const fw_sim_t& P, const FwEnvCtx& c, const double (&unew)[4]) {
+#pragma unroll
   for (int f = 0; f < FW_N_FILT; ++f) {
     const fw_filter_t& F = P.filt[f];
-    const double up = c.D(D_TU + F.stream), un = unew[F.stream];
+    const int st = F.stream;
+    const double up = c.D(D_TU + st);
+    const double un = st == 0 ? unew[0] : (st == 1 ? unew[1] : (st == 2 ? unew[2] : unew[3]));
     double x[FW_FILT_MAXN], xn[FW_FILT_MAXN];
-    for (int a = 0; a < F.n; ++a) x[a] = c.D(D_TX + 3 * f + a);
+#pragma unroll
+    for (int a = 0; a < FW_FILT_MAXN; ++a) x[a] = c.D(D_TX + 3 * f + a);
     double yv = F.D * un;
-    for (int b = 0; b < F.n; ++b) {
+#pragma unroll
+    for (int b = 0; b < FW_FILT_MAXN; ++b) {
       double s = up * F.Bd0[b] + un * F.Bd1[b];
-      for (int a = 0; a < F.n; ++a) s += x[a] * F.Ad[a * FW_FILT_MAXN + b];
+#pragma unroll
+      for (int a = 0; a < FW_FILT_MAXN; ++a) s += x[a] * F.Ad[a * FW_FILT_MAXN + b];
       xn[b] = s;
       yv += s * F.C[b];
     }
-    for (int b = 0; b < F.n; ++b) c.D(D_TX + 3 * f + b) = xn[b];
+#pragma unroll
+    for (int b = 0; b < FW_FILT_MAXN; ++b) c.D(D_TX + 3 * f + b) = xn[b];
     c.D(D_GUST + f) = yv;
   }
+#pragma unroll
   for (int j = 0; j < 4; ++j) c.D(D_TU + j) = unew[j];
 }
 

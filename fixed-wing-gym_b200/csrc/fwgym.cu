@@ -493,7 +493,10 @@ __device__ __forceinline__ void fw_flush_metrics(const FwEnvArgs& a, double (&m)
   }
 }
 
-__global__ void __launch_bounds__(FW_ENV_BLOCK, 4)
+#ifndef FW_ENV_MIN_BLOCKS
+#define FW_ENV_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(FW_ENV_BLOCK, FW_ENV_MIN_BLOCKS)
 fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
               const FwEnvArgs a) {
   const int64_t env = (int64_t)blockIdx.x * FW_ENV_BLOCK + threadIdx.x;

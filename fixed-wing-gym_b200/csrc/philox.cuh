@@ -16,8 +16,10 @@
 #define FW_RS_ENV_U 3   // env-side uniform draws in call order (target sampling, init noise)
 #define FW_RS_ENV_N 4   // env-side normal draws in call order (observation noise), two per block
 
-__host__ __device__ __forceinline__ void fw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                          uint32_t k0, uint32_t k1, uint32_t out[4]) {
+// Out of line on purpose: ~100 instructions x ~25 call sites would otherwise dominate the env kernel's code size,
+// and that kernel is bound by instruction fetch.
+__device__ __noinline__ void fw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -35,7 +37,7 @@ struct FwRng {
 };
 
 // 53-bit uniform in [0,1) from two words (same construction as numpy's random_sample: (a>>5, b>>6))
-__host__ __device__ __forceinline__ double fw_u53(uint32_t a, uint32_t b) {
+__device__ __forceinline__ double fw_u53(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
@@ -50,7 +52,7 @@ __device__ __forceinline__ double fw_uniform(const FwRng& g, uint32_t stream, ui
 }
 
 // two standard normals per Philox block (Box-Muller); u1 in (0,1] so the log is finite
-__device__ __forceinline__ void fw_normal2(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
+__device__ __noinline__ void fw_normal2(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
   uint32_t w[4];
   fw_philox4x32_10(g.env, g.tick, stream, idx, g.k0, g.k1, w);
   double u1 = 1.0 - fw_u53(w[0], w[1]);
