@@ -397,16 +397,14 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const FwStepIn
   for (int s = 1; s <= 6; ++s) {
     T ys[FW_N_ODE], f[FW_N_ODE];
     {
-      T acc[FW_N_KC];
+      // y_s = y + h * sum_j a_sj K_j, accumulated as y += (h a_sj) K_j (one fma per term, no separate scaling pass)
 #pragma unroll
-      for (int kc = 0; kc < FW_N_KC; ++kc) acc[kc] = 0;
+      for (int kc = 0; kc < FW_N_KC; ++kc) ys[fw_kc_to_ode(kc)] = S.y[fw_kc_to_ode(kc)];
       for (int j = 0; j < s; ++j) {
-        const T a = (T)c_dpA[s][j];
+        const T ha = h * (T)c_dpA[s][j];
 #pragma unroll
-        for (int kc = 0; kc < FW_N_KC; ++kc) acc[kc] += a * K.at(j, kc);
+        for (int kc = 0; kc < FW_N_KC; ++kc) ys[fw_kc_to_ode(kc)] = fma(ha, K.at(j, kc), ys[fw_kc_to_ode(kc)]);
       }
-#pragma unroll
-      for (int kc = 0; kc < FW_N_KC; ++kc) { const int c = fw_kc_to_ode(kc); ys[c] = S.y[c] + acc[kc] * h; }
       // position stage states are never read by the RHS; y_new[pos] is formed from accB when s == 6
 #pragma unroll
       for (int j = 0; j < 3; ++j) ys[7 + j] = S.y[7 + j] + h * accB[j];

@@ -133,7 +133,10 @@ __device__ __forceinline__ void fw_load_gusts(const fw_sim_t& P, const FwEnvCtx&
 
 #define FW_INIT_BLOCK 64
 template <typename T, class Spec>
-__global__ void __launch_bounds__(FW_INIT_BLOCK)
+#ifndef FW_INIT_MIN_BLOCKS
+#define FW_INIT_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(FW_INIT_BLOCK, FW_INIT_MIN_BLOCKS)
 fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   const int64_t env = (int64_t)blockIdx.x * FW_INIT_BLOCK + threadIdx.x;
   const bool valid = env < a.n;
