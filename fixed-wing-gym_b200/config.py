@@ -144,7 +144,7 @@ class CompiledConfig:
     """Holds the (mutable) parsed JSON configs, mirrors FixedWingAircraft's derived attributes and produces the POD."""
 
     def __init__(self, config_path=None, sim_config_path=None, sim_parameter_path=None, config_kw=None,
-                 sim_config_kw=None, precision="fp64"):
+                 sim_config_kw=None, precision="fp64", metrics=False):
         config_path = config_path or DEFAULT_ENV_CONFIG
         with open(config_path) as f:
             self.cfg = json.load(f)
@@ -159,6 +159,7 @@ class CompiledConfig:
         with open(sim_parameter_path or DEFAULT_SIM_PARAMS) as f:
             self.params = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
         self.precision = {"fp64": 0, "fp32": 1}[precision]
+        self.metrics = bool(metrics)   # stream the get_metric quantities on the device (fixed_wing.py:1095-1162)
         self.state = {v["name"]: SimVariable(v) for v in self.sim_cfg["variables"]}
         self.dt = self.sim_cfg["dt"]
         self._check_supported()
@@ -260,8 +261,13 @@ class CompiledConfig:
             self.action_bounds_max = np.full(3, cfg["action"].get("scale_high", 1)) * m
             self.action_bounds_min = np.full(3, cfg["action"].get("scale_low", -1)) * m
         self.goal_enabled = cfg["target"]["success_streak_req"] > 0
+        self._bounded_targets = {t["name"] for t in cfg["target"]["states"] if t.get("bound", None) is not None}
 
     # ------------------------------------------------------------------------------------ fixed_wing.py:224-285
+    def goal_has_bound(self, target_name):
+        """Is this target state part of the goal status (fixed_wing.py:916-931: only states with a bound are)?"""
+        return target_name in self._bounded_targets
+
     def set_curriculum_level(self, level):
         assert 0 <= level <= 1
         self._curriculum_level = level
@@ -479,6 +485,11 @@ class CompiledConfig:
         sf = r.get("step_fail", 0)
         e.step_fail_timesteps = 1 if sf == "timesteps" else 0
         e.step_fail_value = 0.0 if sf == "timesteps" else float(sf)
+        e.metrics_enabled = 1 if self.metrics else 0
+        e.rise_low, e.rise_high = 0.1, 0.9          # get_metric defaults (fixed_wing.py:1131)
+        for m in cfg.get("metrics", []):
+            if m.get("name") == "rise_time":
+                e.rise_low, e.rise_high = float(m.get("low", 0.1)), float(m.get("high", 0.9))
         e.n_terms = len(r["terms"])
         seen = set()
         for i, term in enumerate(r["terms"]):

@@ -409,6 +409,130 @@ __device__ __forceinline__ void fw_turb_advance(const fw_sim_t& P, const FwEnvCt
   for (int j = 0; j < 4; ++j) c.D(D_TU + j) = unew[j];
 }
 
+
+// ---- episode metrics: streaming forms of FixedWingAircraft.get_metric (fixed_wing.py:1095-1162) ---------------------
+// The reference recomputes every metric from the full per-episode history lists when an episode ends (it calls
+// get_metric from inside step(), :417-419).  Each of them has a forward, O(1)-state form:
+//   avg_error    |mean(e)/e0|            -> running sum of e, e0                        (nan if |e0| < 0.01)
+//   total_error  sum |e|                 -> running sum
+//   end_error    |mean(e[-50:])|         -> 50-entry ring
+//   overshoot    min / max of e vs e0    -> running min, max
+//   rise_time    the reference's backward scan without `break` keeps the EARLIEST index i with |e_i| >= lim and
+//                |e_{i+1}| < lim, for lim = low|e0| and high|e0|; rise_time = i_low - i_high (nan if either is missing)
+//   success / settling_time              -> first history index whose trailing `streak_req` goal bits have mean >=
+//                                           fraction, per bounded target state and for "all" (bit rings + counts)
+//   success_time_frac                    -> running count of goal bits / history length
+//   control_variation  sum |d command| / (3 dt (n_steps - 1)) over PyFly's constrained command history
+// History index 0 is the reset entry; entries are only appended on successful simulator steps, commands on every step.
+__device__ __forceinline__ double& fw_md(const FwLayout& L, const FwEnvCtx& c, int r) { return c.D(L.m_drow + r); }
+__device__ __forceinline__ int32_t& fw_mi(const FwLayout& L, const FwEnvCtx& c, int r) { return c.I(L.m_irow + r); }
+
+// append goal-history entry `idx` (bits from fw_goal_status; the "all" ring / count are maintained by the caller)
+__device__ __forceinline__ void fw_metrics_goal(const fw_env_t& E, const FwLayout& L, const FwEnvCtx& c, uint32_t gb,
+                                                int idx) {
+  const int req = E.streak_req;
+  if (req <= 0) return;
+  const int slot = idx % req, wd = slot >> 5, bit = slot & 31;
+  for (int k = 0; k < E.n_targets; ++k) {
+    if (!E.tgt[k].has_bound) continue;
+    const int nb = (gb >> k) & 1u;
+    uint32_t word = (uint32_t)fw_mi(L, c, MI_GRING + k * L.goal_words + wd);
+    const int ob = (word >> bit) & 1u;
+    word = (word & ~(1u << bit)) | ((uint32_t)nb << bit);
+    fw_mi(L, c, MI_GRING + k * L.goal_words + wd) = (int32_t)word;
+    const int cnt = fw_mi(L, c, MI_GCNT + k) + nb - ob;
+    fw_mi(L, c, MI_GCNT + k) = cnt;
+    fw_mi(L, c, MI_GSUM + k) += nb;
+    if (fw_mi(L, c, MI_SETTLE + k) < 0 && idx + 1 >= req && (double)cnt / (double)req >= E.streak_fraction)
+      fw_mi(L, c, MI_SETTLE + k) = idx;
+  }
+  fw_mi(L, c, MI_GSUM + 3) += (int)(gb >> 31);
+  if (fw_mi(L, c, MI_SETTLE + 3) < 0 && idx + 1 >= req &&
+      (double)c.I(I_GOALCNT) / (double)req >= E.streak_fraction)
+    fw_mi(L, c, MI_SETTLE + 3) = idx;
+}
+
+// append error-history entry `idx` of target k
+__device__ __forceinline__ void fw_metrics_error(const fw_env_t& E, const FwLayout& L, const FwEnvCtx& c, int k,
+                                                 double e, int idx) {
+  const double ae = fabs(e);
+  if (idx == 0) {
+    fw_md(L, c, MD_SUME + k) = e;
+    fw_md(L, c, MD_SUMABS + k) = ae;
+    fw_md(L, c, MD_MIN + k) = e;
+    fw_md(L, c, MD_MAX + k) = e;
+    fw_mi(L, c, MI_RISE_LO + k) = -1;
+    fw_mi(L, c, MI_RISE_HI + k) = -1;
+  } else {
+    fw_md(L, c, MD_SUME + k) += e;
+    fw_md(L, c, MD_SUMABS + k) += ae;
+    if (e < fw_md(L, c, MD_MIN + k)) fw_md(L, c, MD_MIN + k) = e;
+    if (e > fw_md(L, c, MD_MAX + k)) fw_md(L, c, MD_MAX + k) = e;
+    const double pa = fw_md(L, c, MD_PREVABS + k);     // |e_{idx-1}|
+    const double a0 = fabs(c.D(D_ERR0 + k));
+    const double lo = fabs(E.rise_low * c.D(D_ERR0 + k)), hi = fabs(E.rise_high * c.D(D_ERR0 + k));
+    (void)a0;
+    if (fw_mi(L, c, MI_RISE_LO + k) < 0 && pa >= lo && ae < lo) fw_mi(L, c, MI_RISE_LO + k) = idx - 1;
+    if (fw_mi(L, c, MI_RISE_HI + k) < 0 && pa >= hi && ae < hi) fw_mi(L, c, MI_RISE_HI + k) = idx - 1;
+  }
+  fw_md(L, c, MD_PREVABS + k) = ae;
+  c.D(L.end_row + (idx % FW_END_WINDOW) * E.n_targets + k) = e;
+}
+
+// every simulator step (also a failing one) appends the constrained commands to PyFly's actuator histories
+__device__ __forceinline__ void fw_metrics_command(const FwLayout& L, const FwEnvCtx& c, int n_steps) {
+  double s = 0.0;
+  for (int j = 0; j < 3; ++j) {
+    const double cmd = c.D(D_CMD + j);
+    if (n_steps > 1) s += fabs(cmd - fw_md(L, c, MD_PREVCMD + j));
+    fw_md(L, c, MD_PREVCMD + j) = cmd;
+  }
+  if (n_steps > 1) fw_md(L, c, MD_CV) += s;
+  else fw_md(L, c, MD_CV) = 0.0;
+}
+
+// episode end: one row of fw_episode_dim doubles (layout.h EP_*)
+__device__ __forceinline__ void fw_metrics_finish(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
+                                                  const FwEnvCtx& c, int n, int n_steps, double ep_return,
+                                                  double* __restrict__ out) {
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  out[EP_RETURN] = ep_return;
+  out[EP_LENGTH] = (double)n_steps;
+  out[EP_CV] = fw_md(L, c, MD_CV) / (3.0 * P.dt * (double)(n_steps - 1));   // 0/0 = nan for a 1-step episode
+  const bool goal = E.streak_req > 0;
+  out[EP_SUCCESS_ALL] = goal ? (fw_mi(L, c, MI_SETTLE + 3) >= 0 ? 1.0 : 0.0) : nan;
+  out[EP_SETTLE_ALL] = (goal && fw_mi(L, c, MI_SETTLE + 3) >= 0) ? (double)fw_mi(L, c, MI_SETTLE + 3) : nan;
+  out[EP_STF_ALL] = goal ? (double)fw_mi(L, c, MI_GSUM + 3) / (double)n : nan;
+  for (int k = 0; k < E.n_targets; ++k) {
+    double* o = out + EP_PER_TARGET + k * EPT_N;
+    const double e0 = c.D(D_ERR0 + k);
+    o[EPT_AVG] = fabs(e0) >= 0.01 ? fabs((fw_md(L, c, MD_SUME + k) / (double)n) / e0) : nan;
+    o[EPT_TOTAL] = fw_md(L, c, MD_SUMABS + k);
+    const int m = n < FW_END_WINDOW ? n : FW_END_WINDOW;
+    double s = 0.0;
+    for (int i = n - m; i < n; ++i) s += c.D(L.end_row + (i % FW_END_WINDOW) * E.n_targets + k);
+    o[EPT_END] = fabs(s / (double)m);
+    const int rl = fw_mi(L, c, MI_RISE_LO + k), rh = fw_mi(L, c, MI_RISE_HI + k);
+    o[EPT_RISE] = (rl >= 0 && rh >= 0) ? (double)(rl - rh) : nan;
+    const double opp = e0 > 0 ? fw_md(L, c, MD_MIN + k) : fw_md(L, c, MD_MAX + k);
+    const int so = (opp > 0) - (opp < 0), s0 = (e0 > 0) - (e0 < 0);
+    o[EPT_OVERSHOOT] = so == s0 ? nan : fabs(opp / e0);
+    const bool gk = goal && E.tgt[k].has_bound;
+    o[EPT_SUCCESS] = gk ? (fw_mi(L, c, MI_SETTLE + k) >= 0 ? 1.0 : 0.0) : nan;
+    o[EPT_SETTLE] = (gk && fw_mi(L, c, MI_SETTLE + k) >= 0) ? (double)fw_mi(L, c, MI_SETTLE + k) : nan;
+    o[EPT_STF] = gk ? (double)fw_mi(L, c, MI_GSUM + k) / (double)n : nan;
+  }
+}
+
+// histories restart at reset: entry 0
+__device__ __forceinline__ void fw_metrics_reset(const fw_env_t& E, const FwLayout& L, const FwEnvCtx& c, uint32_t gb) {
+  for (int r = 0; r < MI_GRING + 3 * L.goal_words; ++r) fw_mi(L, c, r) = 0;
+  for (int k = 0; k < 4; ++k) fw_mi(L, c, MI_SETTLE + k) = -1;
+  fw_md(L, c, MD_CV) = 0.0;
+  for (int k = 0; k < E.n_targets; ++k) fw_metrics_error(E, L, c, k, c.D(D_ERR0 + k), 0);
+  fw_metrics_goal(E, L, c, gb, 0);
+}
+
 // PyFly.reset + FixedWingAircraft.reset for one env.  init_state rows: FW_N_SV + 3 (wind n,e,d); NaN = sample.
 __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
                                           uint32_t k0, uint32_t k1, uint32_t genv, const double* __restrict__ init_state,
@@ -514,9 +638,11 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   if (L.sv_depth > 1)
     for (int v = 0; v < E.obs_nvar; ++v)
       if (E.obs[v].type == 0) fw_ring_put(c, L.sv_row, L.sv_depth, L.n_sv_obs, L.sv_slot[v], 0, fw_sv_value(c, E.obs[v].ref));
+  uint32_t gb0 = 0u;
   if (E.streak_req > 0) {
     for (int wd = 0; wd < L.goal_words; ++wd) c.I(I_GOALRING + wd) = 0;
     const uint32_t gb = fw_goal_status(E, c);
+    gb0 = gb;
     const int all = (int)(gb >> 31);
     if (all) c.I(I_GOALRING) = 1;
     c.I(I_GOALCNT) = all;
@@ -528,4 +654,5 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   c.I(I_STATUS) = 0;
   c.I(I_LASTK) = 0;
   c.D(D_EPRET) = 0.0;
+  if (L.met) fw_metrics_reset(E, L, c, gb0);
 }

@@ -38,6 +38,7 @@ struct fw_handle_s {
   cudaStream_t last_stream;
   int profiling;
   int generic;                   // 1: the configuration needs FwSpecGeneric (see dynamics.cuh)
+  double* ep_out;                // caller's episode-metric buffer (fw_set_episode_out)
   // init -> attempt -> env pipeline (see "dynamics kernels")
   double* carry_d;               // [CY_ROWS][stride]
   int32_t* carry_i;              // [CI_ROWS][stride]
@@ -364,6 +365,8 @@ struct FwEnvArgs {
   double* msum;
   const double* cd;    // carry rows written by the init / attempt kernels
   const int32_t* ci;
+  double* ep_out;      // [N, ep_dim] episode-metric rows (NULL: not requested)
+  int ep_dim;
 };
 
 // Env-side work of one env step for env `env` (fixed_wing.py:338-437 after the simulator call).  Episode-metric
@@ -391,6 +394,7 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   if (L.cmd_depth > 0)
     for (int j = 0; j < 3; ++j) fw_ring_put(c, L.cmd_row, L.cmd_depth, FW_N_ACT, j, steps, c.D(D_CMD + j));
   steps += 1;
+  if (L.met) fw_metrics_command(L, c, steps);
   int steps_tgt = c.I(I_STEPS_TGT) + 1;
   c.I(I_STEPS_TGT) = steps_tgt;
   const uint32_t tick = (uint32_t)c.I(I_TICK);
@@ -425,6 +429,7 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
         else if (E.on_success == 2) resample = true;
       }
     }
+    if (L.met) fw_metrics_goal(E, L, c, gb, hist_len);
     reward = fw_reward(E, P, L, c, flags, ar, achieved_on_step, steps, hist_len, gb);
     if (resample || (E.resample_every && steps_tgt >= E.resample_every)) {
       fw_sample_target(E, c, rng, flags, steps);
@@ -435,9 +440,11 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
     for (int k = 0; k < E.n_targets; ++k) {
       c.D(D_TARGET + k) = nt[k];
       if (L.tgt_depth > 0) fw_ring_put(c, L.tgt_row, L.tgt_depth, E.n_targets, k, hist_len, nt[k]);
-      if (L.err_depth > 0)
-        fw_ring_put(c, L.err_row, L.err_depth, E.n_targets, k, hist_len,
-                    fw_error(E.tgt[k], nt[k], fw_sv_value(c, E.tgt[k].sv)));
+      if (L.err_depth > 0 || L.met) {
+        const double err = fw_error(E.tgt[k], nt[k], fw_sv_value(c, E.tgt[k].sv));
+        if (L.err_depth > 0) fw_ring_put(c, L.err_row, L.err_depth, E.n_targets, k, hist_len, err);
+        if (L.met) fw_metrics_error(E, L, c, k, err, hist_len);
+      }
     }
     if (L.sv_depth > 1)
       for (int v = 0; v < E.obs_nvar; ++v)
@@ -461,6 +468,7 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   a.done_out[env] = done ? 1 : 0;
   a.term_out[env] = term;
   if (done) {
+    if (L.met && a.ep_out) fw_metrics_finish(E, P, L, c, hist_len, steps, epret, a.ep_out + env * (int64_t)a.ep_dim);
     m[MS_EPISODES] += 1.0;
     m[MS_RETURN] += epret;
     m[MS_LENGTH] += (double)steps;
@@ -635,9 +643,15 @@ static int make_layout(const fw_config_t& cfg, int64_t n, FwLayout& L) {
     L.err_row = row; row += L.err_depth * E.n_targets;
   }
   if (need_tgt) { L.tgt_depth = imax + 1; L.tgt_row = row; row += L.tgt_depth * E.n_targets; }
-  L.d_rows = row;
-  L.i_rows = I_FIXED;
   L.goal_words = (E.streak_req + 31) / 32;
+  L.i_rows = I_FIXED;
+  if (E.metrics_enabled) {
+    L.met = 1;
+    L.m_drow = row; row += MD_ROWS;
+    L.end_row = row; row += FW_END_WINDOW * E.n_targets;
+    L.m_irow = L.i_rows; L.i_rows += MI_GRING + 3 * L.goal_words;
+  }
+  L.d_rows = row;
   return FW_OK;
 }
 
@@ -706,6 +720,7 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   h->seed = 0;
   h->last_stream = nullptr;
   h->profiling = 0;
+  h->ep_out = nullptr;
   int rc = make_layout(h->cfg, n_envs, h->L);
   if (rc) { delete h; return rc; }
   const size_t db = (size_t)h->L.d_rows * h->L.stride * sizeof(double);
@@ -794,6 +809,15 @@ int fw_set_config(fw_handle h, const fw_config_t* cfg) {
 
 int64_t fw_num_envs(fw_handle h) { return h ? h->n : 0; }
 int fw_obs_dim(fw_handle h) { return h ? h->cfg.env.obs_len * h->cfg.env.obs_nvar : 0; }
+int fw_episode_dim(fw_handle h) {
+  return (h && h->cfg.env.metrics_enabled) ? EP_PER_TARGET + EPT_N * h->cfg.env.n_targets : 0;
+}
+int fw_set_episode_out(fw_handle h, double* ep_out) {
+  if (!h) return fail(FW_ERR_ARG, "null handle");
+  if (ep_out && !h->cfg.env.metrics_enabled) return fail(FW_ERR_CONFIG, "fw_set_episode_out: metrics are not enabled in this handle's configuration");
+  h->ep_out = ep_out;
+  return FW_OK;
+}
 int fw_launches_per_step(fw_handle h) { return h ? 3 : 0; }
 int64_t fw_state_rows(fw_handle h) { return h ? h->L.d_rows + h->L.i_rows : 0; }
 
@@ -858,7 +882,7 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   if (h->profiling) CK(cudaEventRecord(pe[1], s));
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
                term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum, h->carry_d,
-               h->carry_i};
+               h->carry_i, h->ep_out, fw_episode_dim(h)};
   const int egrid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
   fw_env_kernel<<<egrid, FW_ENV_BLOCK, 0, s>>>(h->cfg.env, h->cfg.sim, h->L, ea);
   CK(cudaGetLastError());

@@ -60,4 +60,14 @@ struct FwLayout {
   int32_t tgt_depth, tgt_row;     // target ring: tgt_depth x n_targets
   int32_t goal_words;
   int32_t sv_slot[FW_MAX_OBS_VARS];   // obs var index -> column in the sv ring (-1 if not a state var)
+  // episode metrics (only when fw_env_t.metrics_enabled): accumulator rows + the 50-entry error ring of end_error
+  int32_t met, m_drow, m_irow, end_row;
 };
+
+// metric accumulators, relative to FwLayout.m_drow (double) / m_irow (int32); k = target index
+#define FW_END_WINDOW 50
+enum { MD_SUME = 0, MD_SUMABS = 3, MD_MIN = 6, MD_MAX = 9, MD_PREVABS = 12, MD_CV = 15, MD_PREVCMD = 16, MD_ROWS = 19 };
+enum { MI_RISE_LO = 0, MI_RISE_HI = 3, MI_SETTLE = 6 /* k, 3 = all */, MI_GSUM = 10 /* k, 3 = all */, MI_GCNT = 14,
+       MI_GRING = 17 /* 3 x goal_words */ };
+enum { EP_RETURN = 0, EP_LENGTH, EP_CV, EP_SUCCESS_ALL, EP_SETTLE_ALL, EP_STF_ALL, EP_PER_TARGET = 6,
+       EPT_AVG = 0, EPT_TOTAL, EPT_END, EPT_RISE, EPT_OVERSHOOT, EPT_SUCCESS, EPT_SETTLE, EPT_STF, EPT_N = 8 };

@@ -45,9 +45,11 @@ def term_name(code):
 class VecInfos:
     """List-like `infos`: dict i is built on first access (one device->host copy for the whole batch)."""
 
-    def __init__(self, env, done, term, term_obs, targets):
+    def __init__(self, env, done, term, term_obs, targets, ep_out=None):
         self._env, self._done, self._term, self._term_obs, self._targets = env, done, term, term_obs, targets
+        self._ep_out = ep_out
         self._host = None
+        self._ep_host = None
 
     def __len__(self):
         return self._env.num_envs
@@ -65,7 +67,17 @@ class VecInfos:
             info["termination"] = term_name(int(term[i]))
             if tobs is not None:
                 info["terminal_observation"] = tobs[i].reshape(self._env.cc.obs_shape)
+            if self._ep_out is not None:
+                info.update(self._env.episode_info(self._episode_rows()[i]))
         return info
+
+    def _episode_rows(self):
+        """Episode-metric rows of the envs that finished in this step: one gather on the device, one copy."""
+        if self._ep_host is None:
+            idx = torch.nonzero(self._done).flatten()
+            rows = self._ep_out[idx].cpu().numpy()
+            self._ep_host = {int(e): rows[j] for j, e in enumerate(idx.cpu().numpy())}
+        return self._ep_host
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
@@ -74,7 +86,7 @@ class VecInfos:
 class FixedWingVecEnv:
     def __init__(self, config_path=None, num_envs=1, device="cuda:0", sampler=None, sim_config_path=None,
                  sim_parameter_path=None, config_kw=None, sim_config_kw=None, seed=0, precision="fp64",
-                 env_offset=0, auto_reset=True, keep_terminal_obs=False):
+                 env_offset=0, auto_reset=True, keep_terminal_obs=False, metrics=False, info_keywords=()):
         if sampler is not None:
             raise NotImplementedError("adaptive sampler hook is out of scope (SURVEY §2 #18)")
         self._lib = _capi.lib()   # raises if the CUDA extension is not built: no fallback
@@ -85,7 +97,10 @@ class FixedWingVecEnv:
         self.env_offset = int(env_offset)
         self.auto_reset = bool(auto_reset)
         self.keep_terminal_obs = bool(keep_terminal_obs)
-        self.cc = CompiledConfig(config_path, sim_config_path, sim_parameter_path, config_kw, sim_config_kw, precision)
+        self.metrics = bool(metrics)
+        self.info_keywords = tuple(info_keywords)
+        self.cc = CompiledConfig(config_path, sim_config_path, sim_parameter_path, config_kw, sim_config_kw, precision,
+                                 metrics=self.metrics)
         self.cfg = self.cc.cfg
         self.target_names = list(self.cc._target_props_init["states"].keys())
         self.observation_space = Box(self.cc.observation_low, self.cc.observation_high)
@@ -104,6 +119,11 @@ class FixedWingVecEnv:
         self._term_obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=d) if keep_terminal_obs else None
         self._obs64 = self._rew64 = None
         self._actions = None
+        self._ep_out = None
+        if self.metrics:
+            self.ep_dim = self._lib.fw_episode_dim(self._h)
+            self._ep_out = torch.full((n, self.ep_dim), float("nan"), dtype=torch.float64, device=d)
+            _capi.check(self._lib.fw_set_episode_out(self._h, self._ptr(self._ep_out)))
         self.training = True
         self.seed(seed)
 
@@ -201,12 +221,60 @@ class FixedWingVecEnv:
 
     def step_wait(self):
         obs, rew, done, term = self._pending
-        infos = VecInfos(self, done, term, self._term_obs, self.get_targets())
+        # the episode rows are snapshotted here: the next step may overwrite them
+        ep = self._ep_out.clone() if self._ep_out is not None else None
+        infos = VecInfos(self, done.clone(), term.clone(), self._term_obs, self.get_targets(), ep)
         return obs, rew, done.bool(), infos
 
     def step(self, actions):
         self.step_async(actions)
         return self.step_wait()
+
+    # ---------------------------------------------------------------------------------------- episode metrics
+    EP_FIXED = ("r", "l", "control_variation", "success_all", "settling_time_all", "success_time_frac_all")
+    EP_PER_TARGET = ("avg_error", "total_error", "end_error", "rise_time", "overshoot", "success", "settling_time",
+                     "success_time_frac")
+
+    def episode_metrics(self):
+        """Device tensor [N, ep_dim] of the last finished episode's metrics per env (NaN rows: none finished yet);
+        columns: episode_columns()."""
+        if self._ep_out is None:
+            raise _capi.FwError("construct the env with metrics=True")
+        return self._ep_out
+
+    def episode_columns(self):
+        cols = list(self.EP_FIXED)
+        for t in self.target_names:
+            cols += ["%s_%s" % (m, t) for m in self.EP_PER_TARGET]
+        return cols
+
+    def episode_info(self, row):
+        """One episode row -> the entries the reference puts into `info` when an episode ends (fixed_wing.py:417-419:
+        info[metric] = get_metric(metric) for every metric listed in the config) plus the Monitor-style
+        info["episode"] = {"r", "l", + info_keywords} (train_rl_controller.py:153,172)."""
+        nan = float("nan")
+        per = {m: {} for m in self.EP_PER_TARGET}
+        for k, t in enumerate(self.target_names):
+            base = len(self.EP_FIXED) + k * len(self.EP_PER_TARGET)
+            for j, m in enumerate(self.EP_PER_TARGET):
+                v = float(row[base + j])
+                if m in ("success", "settling_time", "success_time_frac") and not self.cc.goal_has_bound(t):
+                    continue   # the reference's goal history only has the states with a bound (fixed_wing.py:916-931)
+                per[m][t] = (v == 1.0) if m == "success" else v
+        if self.cc.goal_enabled:
+            per["success"]["all"] = bool(row[3] == 1.0)
+            per["settling_time"]["all"] = float(row[4])
+            per["success_time_frac"]["all"] = float(row[5])
+        else:
+            per["success"], per["settling_time"], per["success_time_frac"] = {}, {}, {}
+        per["control_variation"] = {"all": float(row[2])}
+        wanted = [m["name"] for m in self.cfg.get("metrics", [])]
+        info = {m: per[m] for m in wanted if m in per}
+        ep = {"r": float(row[0]), "l": int(row[1])}
+        for kw in self.info_keywords:
+            ep[kw] = per.get(kw, nan)
+        info["episode"] = ep
+        return info
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 6
+#define FW_ABI_VERSION 7
 
 /* ---------------------------------------------------------------------------------------------- limits */
 #define FW_MAX_OBS_VARS 32
@@ -153,6 +153,9 @@ typedef struct {
   int32_t term_fclass[FW_N_FCLASS];
   double term_weight[FW_N_FCLASS];
   fw_factor_t fac[FW_MAX_FACTORS];
+  /* episode metrics (FixedWingAircraft.get_metric, fixed_wing.py:1095-1162), streamed on the device when enabled */
+  int32_t metrics_enabled, _pad4;
+  double rise_low, rise_high;     /* rise_time thresholds (fractions of the initial error; config "metrics") */
 } fw_env_t;
 
 typedef struct {
@@ -228,6 +231,16 @@ int fw_profile(fw_handle h, double* dyn_ms, double* env_ms, int64_t* steps);
 /* Episode metric sums for a caller-side NCCL all-reduce: out double [FW_N_METRIC_SUMS] on the host. */
 #define FW_N_METRIC_SUMS 8   /* episodes, successes, sum_return, sum_length, failures, steps_term, success_term, goal_steps */
 int fw_metric_sums(fw_handle h, double* out_host);
+
+/* Episode metrics.  With cfg.env.metrics_enabled the env kernel keeps streaming forms of every
+ * FixedWingAircraft.get_metric quantity (fixed_wing.py:1095-1162, evaluated by the reference inside step() when an
+ * episode ends, :417-419) and, for every env whose episode ended in a step, writes one row of fw_episode_dim(h)
+ * doubles to the registered device buffer [N, dim] (rows of other envs untouched; done_out says which are fresh).
+ * Row layout: return, length, control_variation, success_all, settling_time_all, success_time_frac_all, then per
+ * target k: avg_error, total_error, end_error, rise_time, overshoot, success, settling_time, success_time_frac
+ * (NaN where the reference yields nan / has no entry). */
+int fw_episode_dim(fw_handle h);
+int fw_set_episode_out(fw_handle h, double* ep_out);
 
 /* Introspection */
 int64_t fw_num_envs(fw_handle h);

@@ -48,6 +48,8 @@ class OracleRunner:
         env.simulator.wind.np_random = self._wind_rng
         self.turbulence = bool(env.simulator.wind.turbulence)
         self.nfev = []          # RHS evaluations per step (attempts = (nfev - 2) / 6)
+        self.on_done = None     # optional callback(env, info) at episode end, before the auto-reset
+        self.ep_return = 0.0
 
     def _begin(self):
         t = self.tick
@@ -59,6 +61,7 @@ class OracleRunner:
         return t
 
     def reset(self, state=None, target=None):
+        self.ep_return = 0.0
         t = self._begin()
         kw = {}
         if self.turbulence:
@@ -71,6 +74,9 @@ class OracleRunner:
         self._begin()
         obs, rew, done, info = self.env.step(np.asarray(action, dtype=np.float64))
         self.nfev.append(self.env.simulator.last_step_nfev)
+        self.ep_return += float(rew)         # what a Monitor wrapper would report as episode "r"
+        if done and self.on_done is not None:
+            self.on_done(self.env, info)     # before the auto-reset wipes the episode's histories
         if done and self.auto_reset:
             info = dict(info)
             info["terminal_observation"] = obs

@@ -162,3 +162,62 @@ def test_single_env_facade(built_lib):
         assert pu.rel_err(obs, o, 1e-3).max() <= TOL and abs(rew - r) <= TOL and done == d
         assert set(info["target"]) == {"roll", "pitch", "Va"}
     env.close()
+
+
+@pytest.mark.parametrize("name", ["failure", "success_done", "norm_step2", "dev_history"])
+def test_episode_metrics_golden(built_lib, name):
+    """the device's streaming episode metrics against FixedWingAircraft.get_metric of the unmodified
+    reference file (fixtures: oracle/make_golden_metrics.py), at every episode end of the case.  Integer-valued
+    columns (length, success, settling_time, rise_time) exact, floats <= 1e-9 relative, NaN where the reference has
+    nan / no entry."""
+    c = CASES[name]
+    g = np.load(os.path.join(GOLDEN, "case_%s.npz" % name))
+    rows = np.load(os.path.join(GOLDEN, "metrics_%s.npz" % name))["rows"]
+    want = {(int(r[0]), int(r[1])): r[2:] for r in rows}
+    from fwgym_b200 import FixedWingVecEnv
+    vec = FixedWingVecEnv(harness.config_path(c["config"]), c["n"], config_kw=c["config_kw"], sim_config_kw=c["sim_kw"],
+                          seed=SEED, metrics=True)
+    cols = vec.episode_columns()
+    exact = [j for j, n in enumerate(cols) if n == "l" or n.split("_")[0] in ("success", "settling", "rise")
+             and "frac" not in n]
+    vec.reset()
+    seen = 0
+    for t, a in enumerate(g["actions"]):
+        _, _, done, _ = vec.step_tensors(torch.as_tensor(a, dtype=torch.float64, device=vec.device))
+        done = done.cpu().numpy().astype(bool)
+        assert np.array_equal(done, g["done"][t])
+        ep = vec.episode_metrics().cpu().numpy()
+        for i in np.nonzero(done)[0]:
+            got, ref = ep[i], want[(t, int(i))]
+            assert np.array_equal(np.isnan(got), np.isnan(ref)), (name, t, i, cols, got, ref)
+            ok = ~np.isnan(ref)
+            assert np.array_equal(got[exact][ok[exact]], ref[exact][ok[exact]]), (t, i, got[exact], ref[exact])
+            fin = ok & np.isfinite(ref)
+            assert np.array_equal(np.isinf(got), np.isinf(ref))
+            assert (np.abs(got[fin] - ref[fin]) <= TOL * np.maximum(np.abs(ref[fin]), 1e-3)).all(), \
+                (t, i, [(cols[j], got[j], ref[j]) for j in np.nonzero(fin)[0] if abs(got[j] - ref[j]) > TOL * max(abs(ref[j]), 1e-3)])
+            seen += 1
+    assert seen == len(want)
+    vec.close()
+
+
+def test_episode_info_dicts(built_lib):
+    """infos[i] of a finished env carries what the reference puts there (fixed_wing.py:417-419) + Monitor's episode."""
+    c = CASES["norm_step2"]
+    from fwgym_b200 import FixedWingVecEnv
+    vec = FixedWingVecEnv(harness.config_path(c["config"]), c["n"], config_kw=c["config_kw"], sim_config_kw=c["sim_kw"],
+                          seed=SEED, metrics=True, info_keywords=("success", "control_variation"))
+    vec.reset()
+    g = np.load(os.path.join(GOLDEN, "case_%s.npz" % "norm_step2"))
+    for t, a in enumerate(g["actions"]):
+        obs, rew, done, infos = vec.step(torch.as_tensor(a, dtype=torch.float64, device=vec.device))
+        if done.any():
+            i = int(torch.nonzero(done)[0])
+            info = infos[i]
+            assert set(info["success"]) == {"roll", "pitch", "Va", "all"}
+            assert info["episode"]["l"] == 30 and "control_variation" in info["episode"]
+            assert info["termination"] == "steps" and "rise_time" in info and "all" in info["control_variation"]
+            break
+    else:
+        raise AssertionError("no episode finished")
+    vec.close()
