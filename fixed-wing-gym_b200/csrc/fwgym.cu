@@ -561,6 +561,33 @@ fw_reset_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_s
   fw_reset_env(E, P, L, c, a.k0, a.k1, a.env_offset + (uint32_t)env, a.init_state, a.init_target, a.n, ow);
 }
 
+// ---- PID baseline controller (pyfly/pid_controller.py; evaluate_controller.py:141-151) ---------------------------
+__global__ void fw_pid_kernel(const double* __restrict__ d, int64_t stride, int64_t n, const fw_pid_gains_t g, double dt,
+                              int k_roll, int k_pitch, int k_va, double* __restrict__ integ,
+                              const uint8_t* __restrict__ reset_mask, double* __restrict__ actions) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  auto D = [&](int row) { return d[(int64_t)row * stride + env]; };
+  double i_va = integ[env], i_roll = integ[n + env], i_pitch = integ[2 * n + env];
+  if (reset_mask && reset_mask[env]) i_va = i_roll = i_pitch = 0.0;
+  const double e_va = D(D_VA) - D(D_TARGET + k_va);
+  const double e_phi = D(D_ROLL) - D(D_TARGET + k_roll);
+  const double e_th = D(D_PITCH) - D(D_TARGET + k_pitch);
+  i_va = i_va + dt * e_va;
+  i_roll = i_roll + dt * e_phi;
+  i_pitch = i_pitch + dt * e_th;
+  double dt_ = 0.0 - g.k_p_V * e_va - g.k_i_V * i_va;
+  double da = -g.k_p_phi * e_phi - g.k_i_phi * i_roll - g.k_d_phi * D(D_OMEGA + 0);
+  double de = 0.0 - g.k_p_theta * e_th - g.k_i_theta * i_pitch - g.k_d_theta * D(D_OMEGA + 1);
+  dt_ = fmin(fmax(dt_, g.delta_t_min), g.delta_t_max);
+  da = fmin(fmax(da, g.delta_a_min), g.delta_a_max);
+  de = fmin(fmax(de, g.delta_e_min), g.delta_e_max);
+  integ[env] = i_va; integ[n + env] = i_roll; integ[2 * n + env] = i_pitch;
+  actions[env * 3 + 0] = de;
+  actions[env * 3 + 1] = da;
+  actions[env * 3 + 2] = dt_;
+}
+
 // ---- state export / import: [rows_d + rows_i, N] doubles -----------------------------------------------------
 __global__ void fw_export_kernel(const double* d, const int32_t* i, int64_t stride, int64_t n, int rows_d, int rows_i,
                                  double* out) {
@@ -809,6 +836,24 @@ int fw_set_config(fw_handle h, const fw_config_t* cfg) {
 
 int64_t fw_num_envs(fw_handle h) { return h ? h->n : 0; }
 int fw_obs_dim(fw_handle h) { return h ? h->cfg.env.obs_len * h->cfg.env.obs_nvar : 0; }
+int fw_pid_step(fw_handle h, const fw_pid_gains_t* gains, double* integ, const uint8_t* reset_mask, double* actions_out,
+                void* stream) {
+  if (!h || !gains || !integ || !actions_out) return fail(FW_ERR_ARG, "fw_pid_step: null argument");
+  int k_roll = -1, k_pitch = -1, k_va = -1;
+  for (int k = 0; k < h->cfg.env.n_targets; ++k) {
+    if (h->cfg.env.tgt[k].sv == FW_SV_ROLL) k_roll = k;
+    if (h->cfg.env.tgt[k].sv == FW_SV_PITCH) k_pitch = k;
+    if (h->cfg.env.tgt[k].sv == FW_SV_VA) k_va = k;
+  }
+  if (k_roll < 0 || k_pitch < 0 || k_va < 0)
+    return fail(FW_ERR_CONFIG, "fw_pid_step: the PID controller needs roll, pitch and Va targets");
+  CK(cudaSetDevice(h->device));
+  const int grid = (int)((h->n + 127) / 128);
+  fw_pid_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h->d, h->L.stride, h->n, *gains, h->cfg.sim.dt, k_roll, k_pitch,
+                                                        k_va, integ, reset_mask, actions_out);
+  CK(cudaGetLastError());
+  return FW_OK;
+}
 int fw_episode_dim(fw_handle h) {
   return (h && h->cfg.env.metrics_enabled) ? EP_PER_TARGET + EPT_N * h->cfg.env.n_targets : 0;
 }

@@ -242,6 +242,21 @@ int fw_metric_sums(fw_handle h, double* out_host);
 int fw_episode_dim(fw_handle h);
 int fw_set_episode_out(fw_handle h, double* ep_out);
 
+/* PID baseline controller: pyfly/pid_controller.py as used by evaluate_controller.py:141-151,202.
+ * One call = PIDController.set_reference(current targets) + get_action(roll, pitch, Va, omega) for every env, read
+ * straight from the handle's state rows (the reference reads the same values out of the un-normalised, noise-free
+ * observation vector of its evaluation config).  integ: device double [3, N] integrators (Va, roll, pitch), owned by
+ * the caller; reset_mask: optional device uint8 [N], non-zero = PIDController.reset() first.  actions_out: device
+ * double [N, 3] = (elevator, aileron, throttle) in physical units (use an env with action.scale_space = false). */
+typedef struct {
+  double k_p_V, k_i_V;
+  double k_p_phi, k_i_phi, k_d_phi;
+  double k_p_theta, k_i_theta, k_d_theta;
+  double delta_a_min, delta_a_max, delta_e_min, delta_e_max, delta_t_min, delta_t_max;
+} fw_pid_gains_t;
+int fw_pid_step(fw_handle h, const fw_pid_gains_t* gains, double* integ, const uint8_t* reset_mask,
+                double* actions_out, void* stream);
+
 /* Introspection */
 int64_t fw_num_envs(fw_handle h);
 int fw_obs_dim(fw_handle h);

@@ -221,3 +221,44 @@ def test_episode_info_dicts(built_lib):
     else:
         raise AssertionError("no episode finished")
     vec.close()
+
+
+def test_pid_evaluation_harness(built_lib):
+    """batched scenario replay under the device PID controller against (a) the CPU oracle driven by
+    the restated pyfly PIDController on the same scenarios (<= 1e-9 on every reward until the episode ends, equal
+    lengths) and (b) the reference's published PID trace examples/evaluations/eval_res_PID_none.npy — the gap to (b)
+    is REPORTED, not asserted: it measures the recalled aircraft constants, not the kernels."""
+    from fwgym_b200 import evaluate
+    from oracle.pyfly_restated import PIDController
+    scen = evaluate.load_test_set(os.path.join(GOLDEN, "test_set_wind_none.npz"))
+    cfg = harness.config_path("fixed_wing_config_examples.json")
+    res, vec = evaluate.evaluate_on_set(scen, cfg, controller="pid", seed=1)
+    gold = np.load(os.path.join(GOLDEN, "eval_res_PID_none_rewards.npz"))
+    # (a) CPU oracle on the first scenarios
+    kw = dict(evaluate.EVAL_CONFIG_KW)
+    kw["action"] = {"scale_space": False}
+    for i in range(3):
+        env = harness.make_env("restated", cfg, kw, {"turbulence": False, "turbulence_intensity": "none"})
+        obs = env.reset(state=dict(scen[i]["state"]), target=dict(scen[i]["target"]))
+        pid = PIDController(env.simulator.dt)
+        pid.set_reference(env.target["roll"], env.target["pitch"], env.target["Va"])
+        rews, done = [], False
+        while not done:
+            obs, r, done, info = env.step(pid.get_action(obs[0], obs[1], obs[2], obs[3:6]))
+            pid.set_reference(info["target"]["roll"], info["target"]["pitch"], info["target"]["Va"])
+            rews.append(r)
+        assert len(rews) == res["lengths"][i]
+        assert pu.rel_err(res["rewards"][i], np.array(rews), 1e-3).max() <= TOL
+    # (b) published trace: report
+    off = np.concatenate([[0], np.cumsum(gold["lengths"])])
+    gaps = [np.abs(res["rewards"][i][:min(len(res["rewards"][i]), gold["lengths"][i])] -
+                   gold["rewards"][off[i]:off[i] + min(len(res["rewards"][i]), gold["lengths"][i])]).max()
+            for i in range(len(scen))]
+    same_len = int((res["lengths"] == gold["lengths"]).sum())
+    s = evaluate.summarise(res)
+    print("PID on test_set_wind_none (100 scenarios): success_all %.2f, mean length %.1f (published %.1f); max |reward "
+          "gap| to the published trace: median %.3g, worst %.3g; %d/100 episode lengths equal"
+          % (s.get("success_all", float("nan")), res["lengths"].mean(), gold["lengths"].mean(), np.median(gaps),
+             np.max(gaps), same_len))
+    assert np.isfinite(gaps).all()
+    vec.close()
