@@ -104,9 +104,11 @@ struct FwSpecGeneric {
   static constexpr bool generic = true;
 };
 
-// branch-free condition of the variable of rank R: violated constraints set bit R of failmask
-template <typename T, class Spec, int R>
+// branch-free condition of the variable of rank R: violated constraints set bit R of failmask.  RAW: no condition
+// at all (see fw_rhs).
+template <typename T, class Spec, int R, bool RAW = false>
 __device__ __forceinline__ T fw_cond_r(const fw_var_t& v, T x, uint32_t& failmask) {
+  if constexpr (RAW) return x;
   if constexpr ((Spec::cons >> R) & 1u) {
     const bool bad = (x < (T)v.clo) | (x > (T)v.chi);
     failmask |= bad ? FW_RB(R) : 0u;
@@ -120,26 +122,32 @@ __device__ __forceinline__ T fw_cond_r(const fw_var_t& v, T x, uint32_t& failmas
 
 // d/dt of the 19-state vector.  y is the RAW trial state; PyFly conditions every component (clip / constraint) before
 // use except the quaternion, which is used un-normalised (oracle/pyfly_restated.py: _dynamics, _forces).
-template <typename T, class Spec>
+//
+// RAW = the evaluation at t == 0: PyFly._dynamics only writes the trial state into its Variables (and thereby applies
+// their conditions) `if t > 0`; f(t0, y0) is computed from the stored values as they are.  Those are already
+// conditioned after a step, but NOT after a reset (Variable.reset draws init values without clipping or checking), so
+// the first right-hand side of an episode must not clip / check the state variables.  Va, alpha, beta (and the
+// elevator / aileron mapping) are conditioned in _forces at every evaluation.
+template <typename T, class Spec, bool RAW = false>
 __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in, const T (&y)[FW_N_ODE],
                                        T (&dy)[FW_N_ODE], uint32_t& failmask) {
   typedef FwMath<T> Mt;
   const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
-  const T p = fw_cond_r<T, Spec, FW_R_P>(P.var[FW_SV_OMEGA_P], y[4], failmask);
-  const T q = fw_cond_r<T, Spec, FW_R_Q>(P.var[FW_SV_OMEGA_Q], y[5], failmask);
-  const T r = fw_cond_r<T, Spec, FW_R_R>(P.var[FW_SV_OMEGA_R], y[6], failmask);
+  const T p = fw_cond_r<T, Spec, FW_R_P, RAW>(P.var[FW_SV_OMEGA_P], y[4], failmask);
+  const T q = fw_cond_r<T, Spec, FW_R_Q, RAW>(P.var[FW_SV_OMEGA_Q], y[5], failmask);
+  const T r = fw_cond_r<T, Spec, FW_R_R, RAW>(P.var[FW_SV_OMEGA_R], y[6], failmask);
   // position variables carry no limits (config.py rejects them): their stage states are never formed
-  const T u = fw_cond_r<T, Spec, FW_R_U>(P.var[FW_SV_VEL_U], y[10], failmask);
-  const T v = fw_cond_r<T, Spec, FW_R_V>(P.var[FW_SV_VEL_V], y[11], failmask);
-  const T w = fw_cond_r<T, Spec, FW_R_W>(P.var[FW_SV_VEL_W], y[12], failmask);
+  const T u = fw_cond_r<T, Spec, FW_R_U, RAW>(P.var[FW_SV_VEL_U], y[10], failmask);
+  const T v = fw_cond_r<T, Spec, FW_R_V, RAW>(P.var[FW_SV_VEL_V], y[11], failmask);
+  const T w = fw_cond_r<T, Spec, FW_R_W, RAW>(P.var[FW_SV_VEL_W], y[12], failmask);
   // actuators: value conditions + rate clip (ControlVariable.apply_conditions)
-  const T el = fw_cond_r<T, Spec, FW_R_EL>(P.var[FW_SV_ELEVON_L], y[13], failmask);
-  const T er = fw_cond_r<T, Spec, FW_R_ER>(P.var[FW_SV_ELEVON_R], y[14], failmask);
-  const T th = fw_cond_r<T, Spec, FW_R_TH>(P.var[FW_SV_THROTTLE], y[15], failmask);
+  const T el = fw_cond_r<T, Spec, FW_R_EL, RAW>(P.var[FW_SV_ELEVON_L], y[13], failmask);
+  const T er = fw_cond_r<T, Spec, FW_R_ER, RAW>(P.var[FW_SV_ELEVON_R], y[14], failmask);
+  const T th = fw_cond_r<T, Spec, FW_R_TH, RAW>(P.var[FW_SV_THROTTLE], y[15], failmask);
   T ad[3] = {y[16], y[17], y[18]};
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    if ((Spec::clip >> (FW_R_AD0 + i)) & 1u) {
+    if (!RAW && ((Spec::clip >> (FW_R_AD0 + i)) & 1u)) {
       const T m = P.act_has_dot_max[i] ? (T)P.act_dot_max[i] : (T)CUDART_INF;
       ad[i] = ad[i] < -m ? -m : (ad[i] > m ? m : ad[i]);
     }
@@ -328,7 +336,7 @@ __device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const FwStepIn<T>&
   const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
   const T inv_sqrtn = (T)(1.0 / 4.358898943540674);   // 1 / 19 ** 0.5
   uint32_t failmask = 0u;
-  fw_rhs<T, Spec>(P, in, y, f0, failmask);
+  fw_rhs<T, Spec, true>(P, in, y, f0, failmask);   // t == 0: stored state values, unconditioned
   if (failmask) return fw_fail_code<T>(failmask);
   T isc[FW_N_ODE];
   T s0 = 0, s1 = 0;

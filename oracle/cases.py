@@ -41,4 +41,11 @@ CASES = {
                                                         7: {"constraint_min": -70, "constraint_max": 70},
                                                         8: {"constraint_min": -70, "constraint_max": 70}}}},
                     sim_kw={"turbulence": False}, n=6, steps=60, amp=1.5),
+    # FwSpecGeneric paths no shipped configuration reaches: steady wind (rotated into the body frame in every RHS) and
+    # the polynomial drag model, plus a constraint on a variable the shipped instantiation does not check (velocity_u)
+    "wind": dict(config="fixed_wing_config.json", config_kw=None,
+                 sim_kw={"turbulence": True, "turbulence_intensity": "light", "wind_magnitude_min": 2,
+                         "wind_magnitude_max": 6}, n=4, steps=30, amp=1.0),
+    "poly_drag": dict(config="fixed_wing_config_constraints.json", config_kw=None,
+                      sim_kw={"turbulence": False, "drag_model": "polynomial"}, n=6, steps=40, amp=1.2),
 }
