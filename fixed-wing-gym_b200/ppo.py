@@ -1,0 +1,194 @@
+"""PPO training loop with a torch policy on the GPU and the batched VecEnv (BASELINE configs[3]).
+
+The reference trains with stable-baselines PPO2 over `VecNormalize(SubprocVecEnv([...]))`
+(examples/train_rl_controller.py:223-231: MlpPolicy, PPO2 defaults).  This is the same loop with everything resident
+on the device: observations never leave HBM, `DeviceVecNormalize` is the VecNormalize equivalent (running mean / var
+of observations and discounted returns, clip 10, gamma 0.99), the policy is SB2's MlpPolicy shape (separate 2x64 tanh
+networks for pi and vf, state-independent log-std), hyper-parameters are PPO2's defaults.  torch is used for the
+policy math (library GEMMs) — the env side is the CUDA hot path of this repo; `train()` reports how the wall time
+splits between the two.  Under torch.distributed (one process per GPU) gradients are averaged with an all-reduce
+(a ~10 k-parameter MLP: negligible over NVLink) and every rank steps its own shard of the envs.
+"""
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+class RunningMeanStd:
+    """Batched Welford update on the device (stable-baselines common/running_mean_std.py semantics)."""
+
+    def __init__(self, shape, device):
+        self.mean = torch.zeros(shape, dtype=torch.float64, device=device)
+        self.var = torch.ones(shape, dtype=torch.float64, device=device)
+        self.count = 1e-4
+
+    def update(self, x):
+        x = x.to(torch.float64)
+        bm, bv, bc = x.mean(0), x.var(0, unbiased=False), x.shape[0]
+        delta = bm - self.mean
+        tot = self.count + bc
+        self.mean = self.mean + delta * bc / tot
+        m2 = self.var * self.count + bv * bc + delta * delta * self.count * bc / tot
+        self.var = m2 / tot
+        self.count = tot
+
+
+class DeviceVecNormalize:
+    """VecNormalize(norm_obs=True, norm_reward=True, clip_obs=10, clip_reward=10, gamma=0.99) over device tensors."""
+
+    def __init__(self, venv, gamma=0.99, clip_obs=10.0, clip_reward=10.0, epsilon=1e-8):
+        self.venv, self.gamma, self.clip_obs, self.clip_reward, self.eps = venv, gamma, clip_obs, clip_reward, epsilon
+        self.num_envs, self.device = venv.num_envs, venv.device
+        self.obs_rms = RunningMeanStd((venv.obs_dim,), venv.device)
+        self.ret_rms = RunningMeanStd((), venv.device)
+        self.ret = torch.zeros(venv.num_envs, dtype=torch.float64, device=venv.device)
+        self.training = True
+
+    def _obs(self, obs):
+        o = obs.reshape(self.num_envs, -1)
+        if self.training:
+            self.obs_rms.update(o)
+        o = (o.to(torch.float64) - self.obs_rms.mean) / torch.sqrt(self.obs_rms.var + self.eps)
+        return torch.clamp(o, -self.clip_obs, self.clip_obs).to(torch.float32)
+
+    def reset(self):
+        self.ret.zero_()
+        return self._obs(self.venv.reset())
+
+    def step(self, actions):
+        obs, rew, done, term = self.venv.step_tensors(actions)
+        self.ret = self.ret * self.gamma + rew.to(torch.float64)
+        if self.training:
+            self.ret_rms.update(self.ret)
+        r = torch.clamp(rew.to(torch.float64) / torch.sqrt(self.ret_rms.var + self.eps), -self.clip_reward,
+                        self.clip_reward).to(torch.float32)
+        d = done.bool()
+        self.ret = torch.where(d, torch.zeros_like(self.ret), self.ret)
+        return self._obs(obs), r, d, rew
+
+
+class ActorCritic(nn.Module):
+    """SB2 MlpPolicy: pi and vf are separate 2 x 64 tanh MLPs; diagonal Gaussian with a state-independent log-std."""
+
+    def __init__(self, obs_dim, act_dim, hidden=64):
+        super().__init__()
+        mlp = lambda out: nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh(),
+                                        nn.Linear(hidden, out))
+        self.pi, self.vf = mlp(act_dim), mlp(1)
+        self.log_std = nn.Parameter(torch.zeros(act_dim))
+        for net, gain in ((self.pi, 0.01), (self.vf, 1.0)):
+            for i, m in enumerate(net):
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, gain if i == len(net) - 1 else np.sqrt(2))
+                    nn.init.zeros_(m.bias)
+
+    def dist(self, obs):
+        return torch.distributions.Normal(self.pi(obs), self.log_std.exp())
+
+    def value(self, obs):
+        return self.vf(obs).squeeze(-1)
+
+
+def _allreduce_grads(model):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        w = dist.get_world_size()
+        for p in model.parameters():
+            if p.grad is not None:
+                dist.all_reduce(p.grad)
+                p.grad /= w
+
+
+def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.5e-4, gamma=0.99, lam=0.95,
+          clip_range=0.2, ent_coef=0.01, vf_coef=0.5, max_grad_norm=0.5, seed=0, model=None, log=None):
+    """PPO2-default training on a FixedWingVecEnv.  Returns (model, normalizer, stats); stats has env-steps/s inside
+    training and the env / policy / update split of the wall time (CUDA-event timed)."""
+    dev = venv.device
+    torch.manual_seed(seed)
+    norm = DeviceVecNormalize(venv, gamma=gamma)
+    n, od = venv.num_envs, venv.obs_dim
+    model = model or ActorCritic(od, 3).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-5)
+    obs = norm.reset()
+    B = n_steps * n
+    buf = dict(obs=torch.zeros((n_steps, n, od), device=dev), act=torch.zeros((n_steps, n, 3), device=dev),
+               logp=torch.zeros((n_steps, n), device=dev), val=torch.zeros((n_steps, n), device=dev),
+               rew=torch.zeros((n_steps, n), device=dev), done=torch.zeros((n_steps, n), device=dev))
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    t_env = t_pol = t_upd = 0.0
+    iters = max(1, int(total_env_steps) // B)
+    stats = {"iterations": iters, "batch": B, "history": []}
+    torch.cuda.synchronize(dev)
+    wall0 = time.perf_counter()
+    for it in range(iters):
+        e = [ev() for _ in range(4)]
+        env_ms = pol_ms = 0.0
+        marks = []
+        for t in range(n_steps):
+            a0, a1, a2 = ev(), ev(), ev()
+            a0.record()
+            with torch.no_grad():
+                d = model.dist(obs)
+                act = d.sample()
+                buf["obs"][t], buf["act"][t] = obs, act
+                buf["logp"][t] = d.log_prob(act).sum(-1)
+                buf["val"][t] = model.value(obs)
+            a1.record()
+            obs, rew, done, raw = norm.step(act)
+            a2.record()
+            buf["rew"][t], buf["done"][t] = rew, done.float()
+            marks.append((a0, a1, a2))
+        e[0].record()
+        with torch.no_grad():
+            last_val = model.value(obs)
+            adv = torch.zeros_like(buf["rew"])
+            gae = torch.zeros(n, device=dev)
+            for t in reversed(range(n_steps)):
+                nv = last_val if t == n_steps - 1 else buf["val"][t + 1]
+                nonterm = 1.0 - buf["done"][t]
+                delta = buf["rew"][t] + gamma * nv * nonterm - buf["val"][t]
+                gae = delta + gamma * lam * nonterm * gae
+                adv[t] = gae
+            ret = adv + buf["val"]
+        flat = {k: v.reshape((B,) + v.shape[2:]) for k, v in buf.items()}
+        f_adv, f_ret = adv.reshape(B), ret.reshape(B)
+        mb = B // n_minibatches
+        for ep in range(n_epochs):
+            perm = torch.randperm(B, device=dev)
+            for k in range(n_minibatches):
+                idx = perm[k * mb:(k + 1) * mb]
+                d = model.dist(flat["obs"][idx])
+                logp = d.log_prob(flat["act"][idx]).sum(-1)
+                a = f_adv[idx]
+                a = (a - a.mean()) / (a.std() + 1e-8)
+                ratio = (logp - flat["logp"][idx]).exp()
+                pg = torch.max(-a * ratio, -a * torch.clamp(ratio, 1 - clip_range, 1 + clip_range)).mean()
+                v = model.value(flat["obs"][idx])
+                vclip = flat["val"][idx] + torch.clamp(v - flat["val"][idx], -clip_range, clip_range)
+                vl = 0.5 * torch.max((v - f_ret[idx]) ** 2, (vclip - f_ret[idx]) ** 2).mean()
+                loss = pg - ent_coef * d.entropy().sum(-1).mean() + vf_coef * vl
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                _allreduce_grads(model)
+                nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
+                opt.step()
+        e[1].record()
+        torch.cuda.synchronize(dev)
+        pol_ms = sum(a0.elapsed_time(a1) for a0, a1, _ in marks)
+        env_ms = sum(a1.elapsed_time(a2) for _, a1, a2 in marks)
+        upd_ms = e[0].elapsed_time(e[1])
+        t_env, t_pol, t_upd = t_env + env_ms, t_pol + pol_ms, t_upd + upd_ms
+        rec = {"iter": it, "loss": float(loss.detach()), "mean_norm_reward": float(buf["rew"].mean()),
+               "value_loss": float(vl.detach()), "env_ms": env_ms, "policy_ms": pol_ms, "update_ms": upd_ms}
+        stats["history"].append(rec)
+        if log:
+            log(rec)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - wall0
+    tot = t_env + t_pol + t_upd
+    stats.update(env_steps=iters * B, wall_s=wall, env_steps_per_s=iters * B / wall,
+                 time_fraction={"env": t_env / tot, "policy_forward": t_pol / tot, "ppo_update": t_upd / tot},
+                 episode_metrics=venv.metric_sums().tolist())
+    return model, norm, stats
