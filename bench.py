@@ -160,6 +160,10 @@ def run_gpu_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world != a.gpus and world > 1:
         a.gpus = world
     torch.cuda.set_device(local)
@@ -298,7 +302,8 @@ def run_gpu_arm(a):
         }
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(a.cpu_baseline_seconds)[0]
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -8,6 +8,16 @@
 #include "layout.h"
 #include "philox.cuh"
 #include "dynamics.cuh"
+#include "env_shapes.h"
+
+// Every function below is templated on a configuration shape SH (env_shapes.h).  Convention inside the bodies:
+//   Es / Ps / Ls : STRUCTURE (counts, kinds, flags, windows, row numbers) - literals when SH is a fixed shape;
+//   E  / P  / L  : the runtime configuration - numbers only (and L.stride through the row accessor).
+#define FW_SHAPE_REFS                          \
+  const fw_env_t& Es = SH::env(E);             \
+  const fw_sim_t& Ps = SH::sim(P);             \
+  const FwLayout& Ls = SH::lay(L);             \
+  (void)Es; (void)Ps; (void)Ls
 
 #define FW_TWO_PI 6.283185307179586
 
@@ -20,23 +30,24 @@ struct FwEnvCtx {
   __device__ __forceinline__ int32_t& I(int row) const { return i[(int64_t)row * stride + env]; }
 };
 
-struct FwEnvRng {
+template <bool INL>
+struct FwEnvRngT {
   FwRng g;
   uint32_t n_u, n_n;        // uniform / normal draws consumed in this tick
   double z_cached;
-  __device__ __forceinline__ double uniform(double lo, double hi) { return fw_uniform(g, FW_RS_ENV_U, n_u++, lo, hi); }
-  __device__ __forceinline__ double uniform01() { return fw_uniform01(g, FW_RS_ENV_U, n_u++); }
+  __device__ __forceinline__ double uniform(double lo, double hi) { return fw_uniform<INL>(g, FW_RS_ENV_U, n_u++, lo, hi); }
+  __device__ __forceinline__ double uniform01() { return fw_uniform01<INL>(g, FW_RS_ENV_U, n_u++); }
   __device__ __forceinline__ double normal(double mean, double std) {
     double z;
     if (n_n & 1u) z = z_cached;
-    else { double z1; fw_normal2(g, FW_RS_ENV_N, n_n >> 1, z, z1); z_cached = z1; }
+    else { double z1; fw_normal2_t<INL>(g, FW_RS_ENV_N, n_n >> 1, z, z1); z_cached = z1; }
     ++n_n;
     return mean + std * z;
   }
 };
 
 // current value of a PyFly state variable (`simulator.state[name].value`)
-__device__ __noinline__ double fw_sv_value(const FwEnvCtx& c, int sv) {
+__device__ __forceinline__ double fw_sv_value_inl(const FwEnvCtx& c, int sv) {
   switch (sv) {
     case FW_SV_ROLL: return c.D(D_ROLL);
     case FW_SV_PITCH: return c.D(D_PITCH);
@@ -62,59 +73,79 @@ __device__ __noinline__ double fw_sv_value(const FwEnvCtx& c, int sv) {
   }
   return 0.0;
 }
+__device__ __noinline__ double fw_sv_value(const FwEnvCtx& c, int sv) { return fw_sv_value_inl(c, sv); }
+// sv is a literal in a fixed shape: the switch folds to one row load
+template <class SH>
+__device__ __forceinline__ double fw_sv(const FwEnvCtx& c, int sv) {
+  if constexpr (SH::fixed) return fw_sv_value_inl(c, sv);
+  else return fw_sv_value(c, sv);
+}
 
 // python float floor-mod x % m for m > 0
-__device__ __noinline__ double fw_pymod(double x, double m) {
+__device__ __noinline__ double fw_pymod_slow(double x, double m) {
   double r = fmod(x, m);
   if (r != 0.0 && r < 0.0) r += m;
   return r;
 }
+// Same value without the fmod loop on the three periods around zero (every operand the env produces: angles and
+// targets live in [-pi, pi]): fmod(x, m) is x itself for |x| < m and the exact difference x - m for m <= x < 2m.
+__device__ __forceinline__ double fw_pymod(double x, double m) {
+  if (x >= 0.0 && x < m) return x;
+  if (x < 0.0 && x >= -m) return x + m;
+  if (x >= m && x < 2.0 * m) return x - m;
+  return fw_pymod_slow(x, m);
+}
 
 // fixed_wing.py:890-914
-__device__ __forceinline__ double fw_error(const fw_target_t& t, double target, double value) {
-  if (t.wrap) return fw_pymod(value - target + CUDART_PI, FW_TWO_PI) - CUDART_PI;
+__device__ __forceinline__ double fw_error(int wrap, double target, double value) {
+  if (wrap) return fw_pymod(value - target + CUDART_PI, FW_TWO_PI) - CUDART_PI;
   return target - value;
 }
 
 __device__ __forceinline__ int fw_tcls(uint32_t flags, int k) { return (flags >> (FWF_TCLS_SHIFT + 2 * k)) & 3u; }
 
 // fixed_wing.py:916-931 : bit k = |err_k| <= bound_k for targets with a bound; bit 31 = all()
+template <class SH>
 __device__ __forceinline__ uint32_t fw_goal_status(const fw_env_t& E, const FwEnvCtx& c) {
+  const fw_env_t& Es = SH::env(E);
   uint32_t bits = 0;
   bool all = true;
-  for (int k = 0; k < E.n_targets; ++k) {
-    if (!E.tgt[k].has_bound) continue;
-    const double err = fw_error(E.tgt[k], c.D(D_TARGET + k), fw_sv_value(c, E.tgt[k].sv));
+  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+    if (!Es.tgt[k].has_bound) return;
+    const double err = fw_error(Es.tgt[k].wrap, c.D(D_TARGET + k), fw_sv<SH>(c, Es.tgt[k].sv));
     const bool ok = fabs(err) <= E.tgt[k].bound;
     if (ok) bits |= 1u << k;
     all = all && ok;
-  }
+  });
   if (all) bits |= 1u << 31;
   return bits;
 }
 
 // fixed_wing.py:461-521
-__device__ __forceinline__ void fw_sample_target(const fw_env_t& E, const FwEnvCtx& c, FwEnvRng& rng,
-                                                 uint32_t& flags, int steps_count) {
+template <class SH, class RNG>
+__device__ __forceinline__ void fw_sample_target(const fw_env_t& E, const FwEnvCtx& c, RNG& rng, uint32_t& flags,
+                                                 int steps_count) {
+  const fw_env_t& Es = SH::env(E);
   c.I(I_STEPS_TGT) = 0;
-  for (int k = 0; k < E.n_targets; ++k) {
+  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
     const fw_target_t& t = E.tgt[k];
+    const fw_target_t& ts = Es.tgt[k];
     double low = t.low, high = t.high;
-    if (t.has_delta) {
-      const double v = fw_sv_value(c, t.sv);
+    if (ts.has_delta) {
+      const double v = fw_sv<SH>(c, ts.sv);
       low = fmax(low, v - t.delta);
       high = fmax(fmin(high, v + t.delta), low);
     }
     const double initial = rng.uniform(low, high);
-    flags = (flags & ~(3u << (FWF_TCLS_SHIFT + 2 * k))) | ((uint32_t)t.cls << (FWF_TCLS_SHIFT + 2 * k));
-    if (t.cls == 1) {   // linear
+    flags = (flags & ~(3u << (FWF_TCLS_SHIFT + 2 * k))) | ((uint32_t)ts.cls << (FWF_TCLS_SHIFT + 2 * k));
+    if (ts.cls == 1) {   // linear
       double slope = rng.uniform(t.slope_low, t.slope_high);
       if (rng.uniform01() < 0.5) slope *= -1.0;
-      if (t.to_radians) slope = slope * (CUDART_PI / 180.0);
+      if (ts.to_radians) slope = slope * (CUDART_PI / 180.0);
       c.D(D_TSLOPE + k) = slope;
-    } else if (t.cls == 2) {   // sinusoidal
+    } else if (ts.cls == 2) {   // sinusoidal
       double amp = rng.uniform(t.amp_low, t.amp_high);
-      if (t.to_radians) amp = amp * (CUDART_PI / 180.0);
+      if (ts.to_radians) amp = amp * (CUDART_PI / 180.0);
       const double period = rng.uniform(t.period_low, t.period_high);
       const double phase = rng.uniform(0.0, FW_TWO_PI) / (FW_TWO_PI / period);
       c.D(D_TAMP + k) = amp;
@@ -123,24 +154,28 @@ __device__ __forceinline__ void fw_sample_target(const fw_env_t& E, const FwEnvC
       c.D(D_TBIAS + k) = initial - amp * sin(FW_TWO_PI / period * ((double)steps_count + phase));
     }
     c.D(D_TARGET + k) = initial;
-  }
+  });
 }
 
-// fixed_wing.py:933-991 (all next targets are computed from the CURRENT targets, then assigned)
+// fixed_wing.py:933-991 (all next targets are computed from the CURRENT targets, then assigned).  A target's class is
+// its configured one unless reset(target=...) forced it to "constant" (flags), so a fixed shape only carries the
+// code of the classes it configures.
+template <class SH>
 __device__ __forceinline__ void fw_next_targets(const fw_env_t& E, const fw_sim_t& P, const FwEnvCtx& c,
                                                 uint32_t flags, int steps_count, int steps_tgt, double (&out)[FW_MAX_TARGETS]) {
+  const fw_env_t& Es = SH::env(E);
   int pitch_k = -1;
-  for (int k = 0; k < E.n_targets; ++k)
-    if (E.tgt[k].sv == FW_SV_PITCH) pitch_k = k;
-  for (int k = 0; k < E.n_targets; ++k) {
-    const fw_target_t& t = E.tgt[k];
+  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) { if (Es.tgt[k].sv == FW_SV_PITCH) pitch_k = k; });
+  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+    const fw_target_t& ts = Es.tgt[k];
+    const int cfg_cls = ts.cls;
     const int cls = fw_tcls(flags, k);
     const double cur = c.D(D_TARGET + k);
     double res = cur;
-    if (cls == 3 && pitch_k >= 0) {   // compensate (Va)
+    if (cfg_cls == 3 && cls == 3 && pitch_k >= 0) {   // compensate (Va)
       const int pc = fw_tcls(flags, pitch_k);
       const double pitch_cur = c.D(D_TARGET + pitch_k);
-      const double pitch_tar = (pc == 2) ? c.D(D_TBIAS + pitch_k) : pitch_cur;
+      const double pitch_tar = (Es.tgt[pitch_k >= 0 ? pitch_k : 0].cls == 2 && pc == 2) ? c.D(D_TBIAS + pitch_k) : pitch_cur;
       if (pitch_tar <= -2.5 * (CUDART_PI / 180.0)) {
         const double va_end = 28.434 - 40.0841 * pitch_tar;
         double slope = 0.0;
@@ -150,17 +185,17 @@ __device__ __forceinline__ void fw_next_targets(const fw_env_t& E, const fw_sim_
         const double va_end = 26.27 - 41.2529 * pitch_tar;
         if (cur > va_end) res = (steps_tgt < 750) ? cur + (va_end - cur) * 1.0 / 150.0 : va_end;
       }
-    } else if (cls == 1) {
+    } else if (cfg_cls == 1 && cls == 1) {
       res = cur + c.D(D_TSLOPE + k) * P.dt;
-    } else if (cls == 2) {
+    } else if (cfg_cls == 2 && cls == 2) {
       res = c.D(D_TAMP + k) * sin(FW_TWO_PI / c.D(D_TPERIOD + k) * ((double)steps_count + c.D(D_TPHASE + k))) + c.D(D_TBIAS + k);
     }
-    if (t.wrap && fabs(res) > CUDART_PI) {
+    if (ts.wrap && fabs(res) > CUDART_PI) {
       const double s = res > 0 ? 1.0 : -1.0;
       res = s * (fmod(fabs(res), CUDART_PI) - CUDART_PI);
     }
     out[k] = res;
-  }
+  });
 }
 
 // ---- history rings.  Entry e (0 = the reset entry) lives in slot e % depth. -------------------------------------
@@ -185,13 +220,38 @@ struct FwObsWriter {
   }
 };
 
-// One out-of-line copy serves the step, terminal-observation and reset call sites (instruction-cache footprint).
-__device__ __noinline__ void fw_observation(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
-                                            const FwEnvCtx& c, FwEnvRng& rng, uint32_t flags, int steps_count,
-                                            int hist_len, bool at_reset, const FwObsWriter& out) {
-  const int nv = E.obs_nvar, len = E.obs_len, step = E.obs_step;
-  const int W = E.integration_window;
-  for (int row = 0; row < len; ++row) {
+// sum_{e = lo+1}^{hi-1} |x_e - x_{e-1}| over one ring column, in increasing e (at most `window` - 1 terms), each ring
+// entry loaded once.  ACC = float reproduces np.sum(..., dtype=np.float32) (fixed_wing.py:826,828).
+template <class SH, class ACC, int NCOL>
+__device__ __forceinline__ void fw_ring_abs_diff(const FwEnvCtx& c, int row0, int depth, int col0, int lo, int hi,
+                                                 int window, ACC (&acc)[NCOL]) {
+  if (hi - lo < 2) return;
+  double prev[NCOL];
+#pragma unroll
+  for (int j = 0; j < NCOL; ++j) prev[j] = fw_ring_get(c, row0, depth, FW_N_ACT, col0 + j, lo);
+  fw_loop<SH, 8>(window - 1, [&](int t) {
+    const int e = lo + 1 + t;
+    if (e < hi) {
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) {
+        const double cur = fw_ring_get(c, row0, depth, FW_N_ACT, col0 + j, e);
+        acc[j] += (ACC)fabs(cur - prev[j]);
+        prev[j] = cur;
+      }
+    }
+  });
+}
+
+// Generic instantiation: one out-of-line copy serves the step, terminal-observation and reset call sites
+// (instruction-cache footprint).  Fixed shapes inline it (fw_observation).
+template <class SH, class RNG>
+__device__ __forceinline__ void fw_observation_body(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
+                                                    const FwEnvCtx& c, RNG& rng, uint32_t flags, int steps_count,
+                                                    int hist_len, bool at_reset, const FwObsWriter& out) {
+  FW_SHAPE_REFS;
+  const int nv = Es.obs_nvar, len = Es.obs_len, step = Es.obs_step;
+  const int W = Es.integration_window;
+  fw_loop<SH, 8>(len, [&](int row) {
     int i = 1 + row * step;
     double init_noise = 0.0;
     bool has_init_noise = false;
@@ -200,42 +260,43 @@ __device__ __noinline__ void fw_observation(const fw_env_t& E, const fw_sim_t& P
       if (len > 1) { init_noise = rng.uniform(-1.0, 1.0) * P.dt; has_init_noise = true; }
     }
     // index into PyFly / env histories; clamp for the failure step, where nothing was appended
-    int ih = i < hist_len ? i : hist_len;
-    for (int v = 0; v < nv; ++v) {
+    const int ih = i < hist_len ? i : hist_len;
+    fw_loop<SH, FW_MAX_OBS_VARS>(nv, [&](int v) {
       const fw_obs_var_t& ov = E.obs[v];
+      const fw_obs_var_t& os = Es.obs[v];
       double val;
       bool is_f32 = false;   // the action-delta value is an np.float32 in the reference (fixed_wing.py:826,828)
-      if (ov.type == 0) {
-        if (L.sv_depth <= 1 || ih == 1) val = fw_sv_value(c, ov.ref);
-        else val = fw_ring_get(c, L.sv_row, L.sv_depth, L.n_sv_obs, L.sv_slot[v], hist_len - ih);
-      } else if (ov.type == 1) {
-        const int k = ov.ref;
-        if (ov.value_kind == 0) {
-          if (i == 1) val = fw_error(E.tgt[k], c.D(D_TARGET + k), fw_sv_value(c, E.tgt[k].sv));
-          else val = fw_ring_get(c, L.err_row, L.err_depth, E.n_targets, k, hist_len - ih);
-        } else if (ov.value_kind == 1) {
+      if (os.type == 0) {
+        if (Ls.sv_depth <= 1 || ih == 1) val = fw_sv<SH>(c, os.ref);
+        else val = fw_ring_get(c, Ls.sv_row, Ls.sv_depth, Ls.n_sv_obs, Ls.sv_slot[v], hist_len - ih);
+      } else if (os.type == 1) {
+        const int k = os.ref;
+        if (os.value_kind == 0) {
+          if (i == 1) val = fw_error(Es.tgt[k].wrap, c.D(D_TARGET + k), fw_sv<SH>(c, Es.tgt[k].sv));
+          else val = fw_ring_get(c, Ls.err_row, Ls.err_depth, Es.n_targets, k, hist_len - ih);
+        } else if (os.value_kind == 1) {
           if (i == 1) val = c.D(D_TARGET + k);
-          else val = fw_ring_get(c, L.tgt_row, L.tgt_depth, E.n_targets, k, hist_len - ih);
+          else val = fw_ring_get(c, Ls.tgt_row, Ls.tgt_depth, Es.n_targets, k, hist_len - ih);
         } else {
           if (at_reset && !(flags & FWF_HIST_VALID)) {
-            val = fw_error(E.tgt[k], c.D(D_TARGET + k), fw_sv_value(c, E.tgt[k].sv)) * (double)W;
+            val = fw_error(Es.tgt[k].wrap, c.D(D_TARGET + k), fw_sv<SH>(c, Es.tgt[k].sv)) * (double)W;
           } else {
             // np.sum(history["error"][k][-W-i:-i]) : entries [max(0, n-W-i), n-i)
             const int n = hist_len;
             int hi = n - i, lo = n - W - i;
             if (lo < 0) lo = 0;
             double s = 0.0;
-            for (int e = lo; e < hi; ++e) s += fw_ring_get(c, L.err_row, L.err_depth, E.n_targets, k, e);
+            for (int e = lo; e < hi; ++e) s += fw_ring_get(c, Ls.err_row, Ls.err_depth, Es.n_targets, k, e);
             val = s;
             if (steps_count - i < W) val += (double)(W - (steps_count - i)) * c.D(D_ERR0 + k);
           }
         }
       } else {
-        const int a = ov.ref;
+        const int a = os.ref;
         if (steps_count - i < 0) {
           const int sv = a == 0 ? FW_SV_ELEVATOR : (a == 1 ? FW_SV_AILERON : FW_SV_THROTTLE);
-          val = fw_sv_value(c, sv);
-          if (P.scale_actions) {
+          val = fw_sv<SH>(c, sv);
+          if (Ps.scale_actions) {
             // linear_action_scaling(direction="backward") applied to a vector that is zero except at a
             const double omin = P.act_to_low[a], omax = P.act_to_high[a];
             val = (P.scale_high - P.scale_low) * (val - omin) / (omax - omin) + P.scale_low;
@@ -245,17 +306,13 @@ __device__ __noinline__ void fw_observation(const fw_env_t& E, const fw_sim_t& P
           // accumulated in float32 (np.sum(..., dtype=np.float32))
           const int n = steps_count;            // len(history["action"])
           const int hi = n - (i - 1);           // exclusive
-          int lo = n - ov.window - i + 1;
+          int lo = n - os.window - i + 1;
           if (lo < 0) lo = 0;
-          const int row0 = P.scale_actions ? L.act_row : L.cmd_row;
-          const int depth = P.scale_actions ? L.act_depth : L.cmd_depth;
-          float acc = 0.0f;
-          for (int e = lo + 1; e < hi; ++e) {
-            const double d1 = fw_ring_get(c, row0, depth, FW_N_ACT, a, e);
-            const double d0 = fw_ring_get(c, row0, depth, FW_N_ACT, a, e - 1);
-            acc += (float)fabs(d1 - d0);
-          }
-          val = (double)acc;
+          const int row0 = Ps.scale_actions ? Ls.act_row : Ls.cmd_row;
+          const int depth = Ps.scale_actions ? Ls.act_depth : Ls.cmd_depth;
+          float acc[1] = {0.0f};
+          fw_ring_abs_diff<SH, float, 1>(c, row0, depth, a, lo, hi, os.window, acc);
+          val = (double)acc[0];
           is_f32 = true;
         }
       }
@@ -264,101 +321,132 @@ __device__ __noinline__ void fw_observation(const fw_env_t& E, const fw_sim_t& P
         // noise of this variable are float32 operations in the oracle run; mirrored here.
         float v32 = (float)val;
         if (has_init_noise) v32 = v32 + (float)init_noise;
-        if (E.obs_norm && ov.norm) { v32 = v32 - (float)ov.mean; v32 = v32 / (float)ov.var; }
-        if (E.obs_noise) v32 = v32 + (float)rng.normal(E.obs_noise_mean, E.obs_noise_std);
+        if (Es.obs_norm && os.norm) { v32 = v32 - (float)ov.mean; v32 = v32 / (float)ov.var; }
+        if (Es.obs_noise) v32 = v32 + (float)rng.normal(E.obs_noise_mean, E.obs_noise_std);
         val = (double)v32;
       } else {
         if (has_init_noise) val += init_noise;
-        if (E.obs_norm && ov.norm) { val -= ov.mean; val /= ov.var; }
-        if (E.obs_noise) val += rng.normal(E.obs_noise_mean, E.obs_noise_std);
+        if (Es.obs_norm && os.norm) { val -= ov.mean; val /= ov.var; }
+        if (Es.obs_noise) val += rng.normal(E.obs_noise_mean, E.obs_noise_std);
       }
       out(row * nv + v, val);
-    }
-  }
+    });
+  });
+}
+__device__ __noinline__ void fw_observation_generic(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
+                                                    const FwEnvCtx& c, FwEnvRngT<false>& rng, uint32_t flags,
+                                                    int steps_count, int hist_len, bool at_reset,
+                                                    const FwObsWriter& out) {
+  fw_observation_body<FwShapeGeneric>(E, P, L, c, rng, flags, steps_count, hist_len, at_reset, out);
+}
+template <class SH, class RNG>
+__device__ __forceinline__ void fw_observation(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
+                                               const FwEnvCtx& c, RNG& rng, uint32_t flags, int steps_count,
+                                               int hist_len, bool at_reset, const FwObsWriter& out) {
+  if constexpr (SH::fixed) fw_observation_body<SH>(E, P, L, c, rng, flags, steps_count, hist_len, at_reset, out);
+  else fw_observation_generic(E, P, L, c, rng, flags, steps_count, hist_len, at_reset, out);
 }
 
 // fixed_wing.py:674-774.  a = raw action of this step; steps_count already incremented; error history not yet
 // extended with this step's entry (hist_len entries).
+template <class SH>
 __device__ __forceinline__ double fw_reward(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
                                             uint32_t& flags, const double (&a)[FW_N_ACT], bool success,
                                             int steps_count, int hist_len, uint32_t goal_bits) {
+  FW_SHAPE_REFS;
   double val_t[FW_N_FCLASS] = {0, 0, 0}, shp_t[FW_N_FCLASS] = {0, 0, 0};
-  for (int f = 0; f < E.n_factors; ++f) {
+  fw_loop<SH, FW_MAX_FACTORS>(Es.n_factors, [&](int f) {
     const fw_factor_t& F = E.fac[f];
+    const fw_factor_t& Fs = Es.fac[f];
     double val = 0.0;
-    if (F.cls == 0) {
-      if (F.type == 0) {
+    if (Fs.cls == 0) {
+      if (Fs.type == 0) {
         val = fabs(a[0]) + fabs(a[1]) + fabs(a[2]);
-      } else if (F.type == 1) {
+      } else if (Fs.type == 1) {
         if (steps_count > 1) {
-          int lo = steps_count - F.window;
+          int lo = steps_count - Fs.window;
           if (lo < 0) lo = 0;
-          for (int e = lo + 1; e < steps_count; ++e)
-            for (int j = 0; j < FW_N_ACT; ++j)
-              val += fabs(fw_ring_get(c, L.act_row, L.act_depth, FW_N_ACT, j, e) -
-                          fw_ring_get(c, L.act_row, L.act_depth, FW_N_ACT, j, e - 1));
+          // sum over (e, j) row-major of |a_e[j] - a_{e-1}[j]|, one running sum, each ring entry loaded once
+          if (steps_count - lo >= 2) {
+            double prev[FW_N_ACT];
+#pragma unroll
+            for (int j = 0; j < FW_N_ACT; ++j) prev[j] = fw_ring_get(c, Ls.act_row, Ls.act_depth, FW_N_ACT, j, lo);
+            fw_loop<SH, 8>(Fs.window - 1, [&](int t) {
+              const int e = lo + 1 + t;
+              if (e < steps_count) {
+#pragma unroll
+                for (int j = 0; j < FW_N_ACT; ++j) {
+                  const double cur = fw_ring_get(c, Ls.act_row, Ls.act_depth, FW_N_ACT, j, e);
+                  val += fabs(cur - prev[j]);
+                  prev[j] = cur;
+                }
+              }
+            });
+          }
         }
       } else {
         double hi = 0.0, lo = 0.0;
+#pragma unroll
         for (int j = 0; j < FW_N_ACT; ++j) {
           if (a[j] > E.bounds_max[j]) hi += fabs(a[j] - E.bounds_max[j]);
           if (a[j] < E.bounds_min[j]) lo += fabs(a[j] - E.bounds_min[j]);
         }
         val = hi + lo;
       }
-    } else if (F.cls == 1) {
-      if (F.type == 0) {
-        val = fw_sv_value(c, F.ref);
-      } else if (F.type == 1) {
-        val = fw_error(E.tgt[F.ref], c.D(D_TARGET + F.ref), fw_sv_value(c, E.tgt[F.ref].sv));
+    } else if (Fs.cls == 1) {
+      if (Fs.type == 0) {
+        val = fw_sv<SH>(c, Fs.ref);
+      } else if (Fs.type == 1) {
+        val = fw_error(Es.tgt[Fs.ref].wrap, c.D(D_TARGET + Fs.ref), fw_sv<SH>(c, Es.tgt[Fs.ref].sv));
       } else {
-        const int W = E.integration_window;
+        const int W = Es.integration_window;
         int lo = hist_len - W;
         if (lo < 0) lo = 0;
         if (W == 0) lo = 0;   // python: list[-0:] is the whole list
-        for (int e = lo; e < hist_len; ++e) val += fw_ring_get(c, L.err_row, L.err_depth, E.n_targets, F.ref, e);
-        if (steps_count < W) val += (double)(W - steps_count) * c.D(D_ERR0 + F.ref);
+        for (int e = lo; e < hist_len; ++e) val += fw_ring_get(c, Ls.err_row, Ls.err_depth, Es.n_targets, Fs.ref, e);
+        if (steps_count < W) val += (double)(W - steps_count) * c.D(D_ERR0 + Fs.ref);
       }
-    } else if (F.cls == 2) {
-      if (success) val = F.value_timesteps ? (double)(E.steps_max - steps_count) : F.value;
-    } else if (F.cls == 3) {
+    } else if (Fs.cls == 2) {
+      if (success) val = Fs.value_timesteps ? (double)(E.steps_max - steps_count) : F.value;
+    } else if (Fs.cls == 3) {
       val = F.value;
     } else {
-      if (F.type == 0) {
-        for (int k = 0; k < E.n_targets; ++k)
-          if (E.tgt[k].has_bound && ((goal_bits >> k) & 1u)) val += F.value / (double)E.n_targets;
+      if (Fs.type == 0) {
+        fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+          if (Es.tgt[k].has_bound && ((goal_bits >> k) & 1u)) val += F.value / (double)Es.n_targets;
+        });
       } else {
         if (goal_bits >> 31) val += F.value;
       }
     }
-    if (F.fclass == 0) {
+    if (Fs.fclass == 0) {
       val = fabs(val) / F.scaling;
       if (val < 0.0) val = 0.0;
-      if (F.has_max && val > F.max) val = F.max;
+      if (Fs.has_max && val > F.max) val = F.max;
     } else {
       val = val * val / F.scaling;
     }
-    if (F.shaping) shp_t[F.fclass] += val * F.sign;
-    else val_t[F.fclass] += val * F.sign;
-  }
+    if (Fs.shaping) shp_t[Fs.fclass] += val * F.sign;
+    else val_t[Fs.fclass] += val * F.sign;
+  });
   double reward = 0.0;
-  for (int ti = 0; ti < E.n_terms; ++ti) {
-    const int fc = E.term_fclass[ti];
+  fw_loop<SH, FW_N_FCLASS>(Es.n_terms, [&](int ti) {
+    const int fc = Es.term_fclass[ti];
     const bool has_prev = (flags >> (FWF_PREVSHAPE_SHIFT + fc)) & 1u;
     const double prev = c.D(D_PREVSHAPE + fc);
     double val;
     if (fc == 1) {
-      if (E.potential) val = has_prev ? -1.0 + exp(val_t[fc] + (shp_t[fc] - prev)) : -1.0 + exp(val_t[fc]);
+      if (Es.potential) val = has_prev ? -1.0 + exp(val_t[fc] + (shp_t[fc] - prev)) : -1.0 + exp(val_t[fc]);
       else val = -1.0 + exp(val_t[fc] + shp_t[fc]);
     } else {
       val = val_t[fc];
-      if (E.potential) { if (has_prev) val += shp_t[fc] - prev; }
+      if (Es.potential) { if (has_prev) val += shp_t[fc] - prev; }
       else val += shp_t[fc];
     }
     c.D(D_PREVSHAPE + fc) = shp_t[fc];
     flags |= 1u << (FWF_PREVSHAPE_SHIFT + fc);
     reward += E.term_weight[ti] * val;
-  }
+  });
   return reward;
 }
 
@@ -372,37 +460,47 @@ __device__ __forceinline__ void fw_rot_euler(double phi, double th, double psi, 
 }
 
 // Dryden white noise for sim step s of the episode keyed by eptick (4 streams, already scaled)
+template <bool INL>
 __device__ __forceinline__ void fw_turb_noise(const fw_sim_t& P, uint32_t k0, uint32_t k1, uint32_t genv, uint32_t eptick,
                                               int s, double (&u)[4]) {
   FwRng g{k0, k1, genv, eptick};
-  fw_normal2(g, FW_RS_TURB, 2u * (uint32_t)s, u[0], u[1]);
-  fw_normal2(g, FW_RS_TURB, 2u * (uint32_t)s + 1u, u[2], u[3]);
+  fw_normal2_t<INL>(g, FW_RS_TURB, 2u * (uint32_t)s, u[0], u[1]);
+  fw_normal2_t<INL>(g, FW_RS_TURB, 2u * (uint32_t)s + 1u, u[2], u[3]);
+#pragma unroll
   for (int j = 0; j < 4; ++j) u[j] *= P.turb_noise_scale;
 }
 
 // advance the six shaping filters by one sample (scipy lsim recurrence) and refresh the gust rows.  The host zero-pads
-// Ad / Bd0 / Bd1 / C of filters of order < 3 (config.py), so the loops are fixed-size and everything stays in registers.
+// Ad / Bd0 / Bd1 / C of filters of order < 3 (config.py), so the generic loops are fixed-size and everything stays in
+// registers; a fixed shape knows each filter's order and skips the padding (whose states stay exactly zero).
+template <class SH>
 __device__ __forceinline__ void fw_turb_advance(const fw_sim_t& P, const FwEnvCtx& c, const double (&unew)[4]) {
+  const fw_sim_t& Ps = SH::sim(P);
 #pragma unroll
   for (int f = 0; f < FW_N_FILT; ++f) {
     const fw_filter_t& F = P.filt[f];
-    const int st = F.stream;
+    const int st = Ps.filt[f].stream;
+    const int nf = SH::fixed ? Ps.filt[f].n : FW_FILT_MAXN;
     const double up = c.D(D_TU + st);
     const double un = st == 0 ? unew[0] : (st == 1 ? unew[1] : (st == 2 ? unew[2] : unew[3]));
     double x[FW_FILT_MAXN], xn[FW_FILT_MAXN];
 #pragma unroll
-    for (int a = 0; a < FW_FILT_MAXN; ++a) x[a] = c.D(D_TX + 3 * f + a);
+    for (int a = 0; a < FW_FILT_MAXN; ++a) x[a] = a < nf ? c.D(D_TX + 3 * f + a) : 0.0;
     double yv = F.D * un;
 #pragma unroll
     for (int b = 0; b < FW_FILT_MAXN; ++b) {
-      double s = up * F.Bd0[b] + un * F.Bd1[b];
+      if (b < nf) {
+        double s = up * F.Bd0[b] + un * F.Bd1[b];
 #pragma unroll
-      for (int a = 0; a < FW_FILT_MAXN; ++a) s += x[a] * F.Ad[a * FW_FILT_MAXN + b];
-      xn[b] = s;
-      yv += s * F.C[b];
+        for (int a = 0; a < FW_FILT_MAXN; ++a)
+          if (a < nf) s += x[a] * F.Ad[a * FW_FILT_MAXN + b];
+        xn[b] = s;
+        yv += s * F.C[b];
+      }
     }
 #pragma unroll
-    for (int b = 0; b < FW_FILT_MAXN; ++b) c.D(D_TX + 3 * f + b) = xn[b];
+    for (int b = 0; b < FW_FILT_MAXN; ++b)
+      if (b < nf) c.D(D_TX + 3 * f + b) = xn[b];
     c.D(D_GUST + f) = yv;
   }
 #pragma unroll
@@ -534,10 +632,14 @@ __device__ __forceinline__ void fw_metrics_reset(const fw_env_t& E, const FwLayo
 }
 
 // PyFly.reset + FixedWingAircraft.reset for one env.  init_state rows: FW_N_SV + 3 (wind n,e,d); NaN = sample.
+// SH-templated and out of line: episode ends are rare, so the step path of every instantiation keeps this code out
+// of its straight-line block; inside, a fixed shape still folds (the shape is taken from SH, not from arguments).
+template <class SH>
 __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
                                           uint32_t k0, uint32_t k1, uint32_t genv, const double* __restrict__ init_state,
                                           const double* __restrict__ init_target, int64_t in_stride,
                                           const FwObsWriter& out) {
+  FW_SHAPE_REFS;
   const uint32_t tick = (uint32_t)c.I(I_TICK);
   c.I(I_TICK) = (int32_t)(tick + 1u);
   c.I(I_EPTICK) = (int32_t)tick;
@@ -583,12 +685,17 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   // Dryden: x = 0, first sample drawn, gust = D*u0
   for (int j = 0; j < 18; ++j) c.D(D_TX + j) = 0.0;
   double gl[3] = {0, 0, 0};
-  if (P.turbulence) {
+  if (Ps.turbulence) {
     double u0[4];
-    fw_turb_noise(P, k0, k1, genv, tick, 0, u0);
+    fw_turb_noise<false>(P, k0, k1, genv, tick, 0, u0);
     for (int j = 0; j < 4; ++j) c.D(D_TU + j) = u0[j];
-    for (int f = 0; f < FW_N_FILT; ++f) c.D(D_GUST + f) = P.filt[f].D * u0[P.filt[f].stream];
-    for (int j = 0; j < 3; ++j) gl[j] = c.D(D_GUST + j);
+#pragma unroll
+    for (int f = 0; f < FW_N_FILT; ++f) {
+      const int st = Ps.filt[f].stream;
+      const double gv = P.filt[f].D * (st == 0 ? u0[0] : (st == 1 ? u0[1] : (st == 2 ? u0[2] : u0[3])));
+      c.D(D_GUST + f) = gv;
+      if (f < 3) gl[f] = gv;
+    }
   } else {
     for (int j = 0; j < 4; ++j) c.D(D_TU + j) = 0.0;
     for (int j = 0; j < 6; ++j) c.D(D_GUST + j) = 0.0;
@@ -613,10 +720,10 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   uint32_t flags = (uint32_t)c.I(I_FLAGS);
   const int old_hist_len = c.I(I_HISTLEN);
   c.I(I_STEPS) = 0;
-  FwEnvRng rng{g, 0u, 0u, 0.0};
-  fw_sample_target(E, c, rng, flags, 0);
+  FwEnvRngT<false> rng{g, 0u, 0u, 0.0};
+  fw_sample_target<SH>(E, c, rng, flags, 0);
   if (init_target) {
-    for (int k = 0; k < E.n_targets; ++k) {
+    for (int k = 0; k < Es.n_targets; ++k) {
       const double v = init_target[(int64_t)k * in_stride + c.env];
       if (isnan(v)) continue;
       const int cls = fw_tcls(flags, k);
@@ -626,22 +733,24 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   }
   // observation BEFORE the histories are rebuilt (fixed_wing.py:317 vs :318): the PyFly state histories are new
   // (hist_len 1) but the integrator still reads the previous episode's error history.
-  fw_observation(E, P, L, c, rng, flags, 0, (flags & FWF_HIST_VALID) ? old_hist_len : 1, true, out);
+  fw_observation<SH>(E, P, L, c, rng, flags, 0, (flags & FWF_HIST_VALID) ? old_hist_len : 1, true, out);
   // rebuild histories
   c.I(I_HISTLEN) = 1;
-  for (int k = 0; k < E.n_targets; ++k) {
-    const double err = fw_error(E.tgt[k], c.D(D_TARGET + k), fw_sv_value(c, E.tgt[k].sv));
+  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+    const double err = fw_error(Es.tgt[k].wrap, c.D(D_TARGET + k), fw_sv<SH>(c, Es.tgt[k].sv));
     c.D(D_ERR0 + k) = err;
-    if (L.err_depth > 0) fw_ring_put(c, L.err_row, L.err_depth, E.n_targets, k, 0, err);
-    if (L.tgt_depth > 0) fw_ring_put(c, L.tgt_row, L.tgt_depth, E.n_targets, k, 0, c.D(D_TARGET + k));
-  }
-  if (L.sv_depth > 1)
-    for (int v = 0; v < E.obs_nvar; ++v)
-      if (E.obs[v].type == 0) fw_ring_put(c, L.sv_row, L.sv_depth, L.n_sv_obs, L.sv_slot[v], 0, fw_sv_value(c, E.obs[v].ref));
+    if (Ls.err_depth > 0) fw_ring_put(c, Ls.err_row, Ls.err_depth, Es.n_targets, k, 0, err);
+    if (Ls.tgt_depth > 0) fw_ring_put(c, Ls.tgt_row, Ls.tgt_depth, Es.n_targets, k, 0, c.D(D_TARGET + k));
+  });
+  if (Ls.sv_depth > 1)
+    fw_loop<SH, FW_MAX_OBS_VARS>(Es.obs_nvar, [&](int v) {
+      if (Es.obs[v].type == 0)
+        fw_ring_put(c, Ls.sv_row, Ls.sv_depth, Ls.n_sv_obs, Ls.sv_slot[v], 0, fw_sv<SH>(c, Es.obs[v].ref));
+    });
   uint32_t gb0 = 0u;
-  if (E.streak_req > 0) {
-    for (int wd = 0; wd < L.goal_words; ++wd) c.I(I_GOALRING + wd) = 0;
-    const uint32_t gb = fw_goal_status(E, c);
+  if (Es.streak_req > 0) {
+    for (int wd = 0; wd < Ls.goal_words; ++wd) c.I(I_GOALRING + wd) = 0;
+    const uint32_t gb = fw_goal_status<SH>(E, c);
     gb0 = gb;
     const int all = (int)(gb >> 31);
     if (all) c.I(I_GOALRING) = 1;
@@ -654,5 +763,5 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   c.I(I_STATUS) = 0;
   c.I(I_LASTK) = 0;
   c.D(D_EPRET) = 0.0;
-  if (L.met) fw_metrics_reset(E, L, c, gb0);
+  if (Ls.met) fw_metrics_reset(E, L, c, gb0);
 }

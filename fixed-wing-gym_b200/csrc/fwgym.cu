@@ -38,6 +38,7 @@ struct fw_handle_s {
   cudaStream_t last_stream;
   int profiling;
   int generic;                   // 1: the configuration needs FwSpecGeneric (see dynamics.cuh)
+  int shape;                     // env / reset kernel instantiation: index into FW_SHAPE_LIST, -1 generic (env_shapes.h)
   double* ep_out;                // caller's episode-metric buffer (fw_set_episode_out)
   // init -> attempt -> env pipeline (see "dynamics kernels")
   double* carry_d;               // [CY_ROWS][stride]
@@ -279,9 +280,35 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
 }
 
 // ---- PyFly._set_states_from_ode_solution(save=True) + airspeed factors + next gust column (env kernel prologue) ----
+// PyFly Variable.apply_conditions with the variable's condition FLAGS taken from the shape (a literal in a fixed
+// shape: variables without a constraint / clip cost nothing) and the bounds from the runtime configuration.
+template <bool WRAP>
+__device__ __forceinline__ double fw_cond_s(uint32_t vflags, const fw_var_t& v, int sv, double x, int& fail) {
+  if (vflags & (FW_VC_CMIN | FW_VC_CMAX)) {
+    const bool bad = (x < v.clo) | (x > v.chi);
+    if (bad && !fail) fail = FW_TERM_FAIL_BASE + sv;
+  }
+  if (vflags & (FW_VC_VMIN | FW_VC_VMAX)) {
+    x = x < v.lo ? v.lo : x;     // compares keep NaN, like np.clip
+    x = x > v.hi ? v.hi : x;
+  }
+  if (WRAP && (vflags & FW_VC_WRAP)) {
+    const double ax = fabs(x);
+    if (ax > CUDART_PI) {   // np.sign(v) * (|v| % pi - pi)
+      const double s = x > 0 ? 1.0 : -1.0;
+      x = s * (fmod(ax, CUDART_PI) - CUDART_PI);
+    }
+  }
+  return x;
+}
+
+template <class SH>
 __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx& c, const double* __restrict__ cd,
                                                const int32_t* __restrict__ ci, int64_t stride, uint32_t k0, uint32_t k1,
                                                uint32_t genv, int& attempts_out, int& accepted_out) {
+  const fw_sim_t& Ps = SH::sim(P);
+#define FW_CS(SV, X) fw_cond_s<false>(Ps.var[SV].flags, P.var[SV], SV, X, failv)
+#define FW_CSW(SV, X) fw_cond_s<true>(Ps.var[SV].flags, P.var[SV], SV, X, failv)
   int failv = ci[CI_FAIL * stride];
   attempts_out = ci[CI_ATTEMPTS * stride];
   accepted_out = ci[CI_ACCEPTED * stride];
@@ -299,49 +326,51 @@ __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx
     const double sp = 2 * (e0 * e2 - e1 * e3);
     pitch = fwm_atan2(sp, fwm_sqrt((1 - sp) * (1 + sp)));
     yaw = fwm_atan2(2 * (e0 * e3 + e1 * e2), e0 * e0 + e1 * e1 - e2 * e2 - e3 * e3);
-    roll = fw_cond_wrap<double>(P.var[FW_SV_ROLL], FW_SV_ROLL, roll, failv);
-    pitch = fw_cond_wrap<double>(P.var[FW_SV_PITCH], FW_SV_PITCH, pitch, failv);
-    yaw = fw_cond_wrap<double>(P.var[FW_SV_YAW], FW_SV_YAW, yaw, failv);
+    roll = FW_CSW(FW_SV_ROLL, roll);
+    pitch = FW_CSW(FW_SV_PITCH, pitch);
+    yaw = FW_CSW(FW_SV_YAW, yaw);
 #pragma unroll
-    for (int j = 0; j < 9; ++j) yd[4 + j] = fw_cond<double>(P.var[FW_SV_OMEGA_P + j], FW_SV_OMEGA_P + j, yd[4 + j], failv);
-    yd[13] = fw_cond<double>(P.var[FW_SV_ELEVON_L], FW_SV_ELEVON_L, yd[13], failv);
-    yd[14] = fw_cond<double>(P.var[FW_SV_ELEVON_R], FW_SV_ELEVON_R, yd[14], failv);
-    yd[15] = fw_cond<double>(P.var[FW_SV_THROTTLE], FW_SV_THROTTLE, yd[15], failv);
+    for (int j = 0; j < 9; ++j) yd[4 + j] = FW_CS(FW_SV_OMEGA_P + j, yd[4 + j]);
+    yd[13] = FW_CS(FW_SV_ELEVON_L, yd[13]);
+    yd[14] = FW_CS(FW_SV_ELEVON_R, yd[14]);
+    yd[15] = FW_CS(FW_SV_THROTTLE, yd[15]);
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      if (P.act_has_dot_max[j]) yd[16 + j] = fmin(fmax(yd[16 + j], -P.act_dot_max[j]), P.act_dot_max[j]);
-    ail = fw_cond<double>(P.var[FW_SV_AILERON], FW_SV_AILERON, (-yd[14] + yd[13]) / 2, failv);
-    elev = fw_cond<double>(P.var[FW_SV_ELEVATOR], FW_SV_ELEVATOR, (yd[14] + yd[13]) / 2, failv);
+      if (Ps.act_has_dot_max[j]) yd[16 + j] = fmin(fmax(yd[16 + j], -P.act_dot_max[j]), P.act_dot_max[j]);
+    ail = FW_CS(FW_SV_AILERON, (-yd[14] + yd[13]) / 2);
+    elev = FW_CS(FW_SV_ELEVATOR, (yd[14] + yd[13]) / 2);
     double wb[3] = {0, 0, 0};
-    if (P.wind_enabled) {
+    if (Ps.wind_enabled) {
       const double wv[3] = {c.D(D_WIND + 0), c.D(D_WIND + 1), c.D(D_WIND + 2)};
       fw_rot_euler(roll, pitch, yaw, wv, wb);
     }
     double gl[3] = {0, 0, 0};
-    if (P.turbulence) { gl[0] = c.D(D_GUST + 0); gl[1] = c.D(D_GUST + 1); gl[2] = c.D(D_GUST + 2); }
+    if (Ps.turbulence) { gl[0] = c.D(D_GUST + 0); gl[1] = c.D(D_GUST + 1); gl[2] = c.D(D_GUST + 2); }
     const double ur = yd[10] - (wb[0] + gl[0]), vr = yd[11] - (wb[1] + gl[1]), wr = yd[12] - (wb[2] + gl[2]);
     const double hxz2 = ur * ur + wr * wr;
     Va = fwm_sqrt(hxz2 + vr * vr);
     alpha = fwm_atan2(wr, ur);
     beta = fwm_atan2(vr, fwm_sqrt(hxz2));   // asin(vr / Va)
-    Va = fw_cond<double>(P.var[FW_SV_VA], FW_SV_VA, Va, failv);
-    alpha = fw_cond<double>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, alpha, failv);
-    beta = fw_cond<double>(P.var[FW_SV_BETA], FW_SV_BETA, beta, failv);
+    Va = FW_CS(FW_SV_VA, Va);
+    alpha = FW_CS(FW_SV_ALPHA, alpha);
+    beta = FW_CS(FW_SV_BETA, beta);
     if (!failv) {
 #pragma unroll
       for (int j = 0; j < FW_N_ODE; ++j) c.D(j) = yd[j];
       c.D(D_ROLL) = roll; c.D(D_PITCH) = pitch; c.D(D_YAW) = yaw;
       c.D(D_VA) = Va; c.D(D_ALPHA) = alpha; c.D(D_BETA) = beta;
       c.D(D_ELEV) = elev; c.D(D_AIL) = ail;
-      if (P.turbulence) {   // gust column for the next sim step (cur_sim_step + 1)
+      if (Ps.turbulence) {   // gust column for the next sim step (cur_sim_step + 1)
         double un[4];
-        fw_turb_noise(P, k0, k1, genv, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
-        fw_turb_advance(P, c, un);
+        fw_turb_noise<SH::fixed>(P, k0, k1, genv, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
+        fw_turb_advance<SH>(P, c, un);
       }
     }
   }
   c.I(I_STATUS) = failv;
   c.I(I_LASTK) = attempts_out;
+#undef FW_CS
+#undef FW_CSW
 }
 
 // ---------------------------------------------------------------------------------------------------- env kernel
@@ -371,11 +400,13 @@ struct FwEnvArgs {
 
 // Env-side work of one env step for env `env` (fixed_wing.py:338-437 after the simulator call).  Episode-metric
 // contributions are returned in m[] / n_reset and summed per warp by the caller (one atomic per warp and metric).
+template <class SH>
 __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvArgs& a,
                                             int64_t env, double (&m)[FW_N_METRIC_SUMS], int& n_reset, int& attempts,
                                             int& accepted, int& failed) {
+  FW_SHAPE_REFS;
   FwEnvCtx c{a.d, a.i, L.stride, env};
-  fw_commit_step(P, c, a.cd + env, a.ci + env, L.stride, a.k0, a.k1, a.env_offset + (uint32_t)env, attempts, accepted);
+  fw_commit_step<SH>(P, c, a.cd + env, a.ci + env, L.stride, a.k0, a.k1, a.env_offset + (uint32_t)env, attempts, accepted);
   failed = c.I(I_STATUS) != 0;
   uint32_t flags = (uint32_t)c.I(I_FLAGS);
   int steps = c.I(I_STEPS);
@@ -389,18 +420,18 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
     ar[0] = p[0]; ar[1] = p[1]; ar[2] = p[2];
   }
   // history["action"].append(action) happens before the simulator step (fixed_wing.py:345)
-  if (L.act_depth > 0)
-    for (int j = 0; j < 3; ++j) fw_ring_put(c, L.act_row, L.act_depth, FW_N_ACT, j, steps, ar[j]);
-  if (L.cmd_depth > 0)
-    for (int j = 0; j < 3; ++j) fw_ring_put(c, L.cmd_row, L.cmd_depth, FW_N_ACT, j, steps, c.D(D_CMD + j));
+  if (Ls.act_depth > 0)
+    for (int j = 0; j < 3; ++j) fw_ring_put(c, Ls.act_row, Ls.act_depth, FW_N_ACT, j, steps, ar[j]);
+  if (Ls.cmd_depth > 0)
+    for (int j = 0; j < 3; ++j) fw_ring_put(c, Ls.cmd_row, Ls.cmd_depth, FW_N_ACT, j, steps, c.D(D_CMD + j));
   steps += 1;
-  if (L.met) fw_metrics_command(L, c, steps);
+  if (Ls.met) fw_metrics_command(L, c, steps);
   int steps_tgt = c.I(I_STEPS_TGT) + 1;
   c.I(I_STEPS_TGT) = steps_tgt;
   const uint32_t tick = (uint32_t)c.I(I_TICK);
   c.I(I_TICK) = (int32_t)(tick + 1u);
   const uint32_t genv = a.env_offset + (uint32_t)env;
-  FwEnvRng rng{FwRng{a.k0, a.k1, genv, tick}, 0u, 0u, 0.0};
+  FwEnvRngT<SH::fixed> rng{FwRng{a.k0, a.k1, genv, tick}, 0u, 0u, 0.0};
 
   bool done = false;
   int term = FW_TERM_NONE;
@@ -410,10 +441,10 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   FwObsWriter ow{a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim};
   FwObsWriter tw{a.term_obs_out, nullptr, env * (int64_t)a.obs_dim};
   if (status == 0) {
-    const uint32_t gb = fw_goal_status(E, c);
+    const uint32_t gb = fw_goal_status<SH>(E, c);
     bool achieved_on_step = false, resample = false;
-    if (E.streak_req > 0) {
-      const int slot = hist_len % E.streak_req;
+    if (Es.streak_req > 0) {
+      const int slot = hist_len % Es.streak_req;
       const int wd = slot >> 5, bit = slot & 31;
       uint32_t word = (uint32_t)c.I(I_GOALRING + wd);
       const int oldb = (word >> bit) & 1u, newb = (int)(gb >> 31);
@@ -422,44 +453,45 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
       const int cnt = c.I(I_GOALCNT) + newb - oldb;
       c.I(I_GOALCNT) = cnt;
       if (newb) m[MS_GOAL_STEPS] += 1.0;
-      if (steps_tgt >= E.streak_req && (double)cnt / (double)E.streak_req >= E.streak_fraction) {
+      if (steps_tgt >= Es.streak_req && (double)cnt / (double)Es.streak_req >= E.streak_fraction) {
         achieved_on_step = !(flags & FWF_GOAL_ACHIEVED);
         flags |= FWF_GOAL_ACHIEVED | FWF_EP_SUCCESS;
-        if (E.on_success == 1) { done = true; term = FW_TERM_SUCCESS; }
-        else if (E.on_success == 2) resample = true;
+        if (Es.on_success == 1) { done = true; term = FW_TERM_SUCCESS; }
+        else if (Es.on_success == 2) resample = true;
       }
     }
-    if (L.met) fw_metrics_goal(E, L, c, gb, hist_len);
-    reward = fw_reward(E, P, L, c, flags, ar, achieved_on_step, steps, hist_len, gb);
-    if (resample || (E.resample_every && steps_tgt >= E.resample_every)) {
-      fw_sample_target(E, c, rng, flags, steps);
+    if (Ls.met) fw_metrics_goal(E, L, c, gb, hist_len);
+    reward = fw_reward<SH>(E, P, L, c, flags, ar, achieved_on_step, steps, hist_len, gb);
+    if (resample || (Es.resample_every && steps_tgt >= Es.resample_every)) {
+      fw_sample_target<SH>(E, c, rng, flags, steps);
       steps_tgt = 0;
     }
     double nt[FW_MAX_TARGETS];
-    fw_next_targets(E, P, c, flags, steps, steps_tgt, nt);
-    for (int k = 0; k < E.n_targets; ++k) {
+    fw_next_targets<SH>(E, P, c, flags, steps, steps_tgt, nt);
+    fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
       c.D(D_TARGET + k) = nt[k];
-      if (L.tgt_depth > 0) fw_ring_put(c, L.tgt_row, L.tgt_depth, E.n_targets, k, hist_len, nt[k]);
-      if (L.err_depth > 0 || L.met) {
-        const double err = fw_error(E.tgt[k], nt[k], fw_sv_value(c, E.tgt[k].sv));
-        if (L.err_depth > 0) fw_ring_put(c, L.err_row, L.err_depth, E.n_targets, k, hist_len, err);
-        if (L.met) fw_metrics_error(E, L, c, k, err, hist_len);
+      if (Ls.tgt_depth > 0) fw_ring_put(c, Ls.tgt_row, Ls.tgt_depth, Es.n_targets, k, hist_len, nt[k]);
+      if (Ls.err_depth > 0 || Ls.met) {
+        const double err = fw_error(Es.tgt[k].wrap, nt[k], fw_sv<SH>(c, Es.tgt[k].sv));
+        if (Ls.err_depth > 0) fw_ring_put(c, Ls.err_row, Ls.err_depth, Es.n_targets, k, hist_len, err);
+        if (Ls.met) fw_metrics_error(E, L, c, k, err, hist_len);
       }
-    }
-    if (L.sv_depth > 1)
-      for (int v = 0; v < E.obs_nvar; ++v)
-        if (E.obs[v].type == 0)
-          fw_ring_put(c, L.sv_row, L.sv_depth, L.n_sv_obs, L.sv_slot[v], hist_len, fw_sv_value(c, E.obs[v].ref));
+    });
+    if (Ls.sv_depth > 1)
+      fw_loop<SH, FW_MAX_OBS_VARS>(Es.obs_nvar, [&](int v) {
+        if (Es.obs[v].type == 0)
+          fw_ring_put(c, Ls.sv_row, Ls.sv_depth, Ls.n_sv_obs, Ls.sv_slot[v], hist_len, fw_sv<SH>(c, Es.obs[v].ref));
+      });
     hist_len += 1;
     c.I(I_HISTLEN) = hist_len;
   } else {
     done = true;
-    reward = E.step_fail_timesteps ? (double)(steps - E.steps_max) : E.step_fail_value;
+    reward = Es.step_fail_timesteps ? (double)(steps - E.steps_max) : E.step_fail_value;
     term = status;
   }
   c.I(I_STEPS) = steps;
   const bool do_reset = done && a.auto_reset;
-  if (!do_reset || a.term_obs_out) fw_observation(E, P, L, c, rng, flags, steps, hist_len, false, do_reset ? tw : ow);
+  if (!do_reset || a.term_obs_out) fw_observation<SH>(E, P, L, c, rng, flags, steps, hist_len, false, do_reset ? tw : ow);
   c.I(I_FLAGS) = (int32_t)flags;
   const double epret = c.D(D_EPRET) + reward;
   c.D(D_EPRET) = epret;
@@ -468,7 +500,7 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   a.done_out[env] = done ? 1 : 0;
   a.term_out[env] = term;
   if (done) {
-    if (L.met && a.ep_out) fw_metrics_finish(E, P, L, c, hist_len, steps, epret, a.ep_out + env * (int64_t)a.ep_dim);
+    if (Ls.met && a.ep_out) fw_metrics_finish(E, P, L, c, hist_len, steps, epret, a.ep_out + env * (int64_t)a.ep_dim);
     m[MS_EPISODES] += 1.0;
     m[MS_RETURN] += epret;
     m[MS_LENGTH] += (double)steps;
@@ -479,7 +511,7 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   }
   if (do_reset) {
     n_reset += 1;
-    fw_reset_env(E, P, L, c, a.k0, a.k1, genv, nullptr, nullptr, 0, ow);
+    fw_reset_env<SH>(E, P, L, c, a.k0, a.k1, genv, nullptr, nullptr, 0, ow);
   }
 }
 
@@ -507,6 +539,7 @@ __device__ __forceinline__ void fw_flush_metrics(const FwEnvArgs& a, double (&m)
 #ifndef FW_ENV_MIN_BLOCKS
 #define FW_ENV_MIN_BLOCKS 4
 #endif
+template <class SH>
 __global__ void __launch_bounds__(FW_ENV_BLOCK, FW_ENV_MIN_BLOCKS)
 fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
               const FwEnvArgs a) {
@@ -515,7 +548,7 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
 #pragma unroll
   for (int k = 0; k < FW_N_METRIC_SUMS; ++k) m[k] = 0.0;
   int n_reset = 0, attempts = 0, accepted = 0, failed = 0, nv = 0;
-  if (env < a.n) { fw_env_step(E, P, L, a, env, m, n_reset, attempts, accepted, failed); nv = 1; }
+  if (env < a.n) { fw_env_step<SH>(E, P, L, a, env, m, n_reset, attempts, accepted, failed); nv = 1; }
   fw_flush_metrics(a, m, n_reset);
   // dopri5 counters (fw_counters): one atomic per warp
   const unsigned full = 0xffffffffu;
@@ -549,6 +582,7 @@ struct FwResetArgs {
   unsigned long long* ctr;
 };
 
+template <class SH>
 __global__ void __launch_bounds__(FW_ENV_BLOCK)
 fw_reset_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
                 const FwResetArgs a) {
@@ -558,7 +592,41 @@ fw_reset_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_s
   FwEnvCtx c{a.d, a.i, L.stride, env};
   FwObsWriter ow{a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim};
   atomicAdd(a.ctr + CTR_RESETS, 1ull);
-  fw_reset_env(E, P, L, c, a.k0, a.k1, a.env_offset + (uint32_t)env, a.init_state, a.init_target, a.n, ow);
+  fw_reset_env<SH>(E, P, L, c, a.k0, a.k1, a.env_offset + (uint32_t)env, a.init_state, a.init_target, a.n, ow);
+}
+
+// ---- shape dispatch: index into FW_SHAPE_LIST (fw_find_shape), -1 = generic -----------------------------------------
+static cudaError_t launch_env(int shape, int grid, cudaStream_t s, const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
+                              const FwEnvArgs& a) {
+  int idx = 0;
+#define FW_LAUNCH_SHAPE(NAME)                                                           \
+  if (shape == idx++) { fw_env_kernel<FwShape_##NAME><<<grid, FW_ENV_BLOCK, 0, s>>>(E, P, L, a); return cudaGetLastError(); }
+  FW_SHAPE_LIST(FW_LAUNCH_SHAPE)
+#undef FW_LAUNCH_SHAPE
+  fw_env_kernel<FwShapeGeneric><<<grid, FW_ENV_BLOCK, 0, s>>>(E, P, L, a);
+  return cudaGetLastError();
+}
+static cudaError_t launch_reset(int shape, int grid, cudaStream_t s, const fw_env_t& E, const fw_sim_t& P,
+                                const FwLayout& L, const FwResetArgs& a) {
+  int idx = 0;
+#define FW_LAUNCH_SHAPE(NAME)                                                           \
+  if (shape == idx++) { fw_reset_kernel<FwShape_##NAME><<<grid, FW_ENV_BLOCK, 0, s>>>(E, P, L, a); return cudaGetLastError(); }
+  FW_SHAPE_LIST(FW_LAUNCH_SHAPE)
+#undef FW_LAUNCH_SHAPE
+  fw_reset_kernel<FwShapeGeneric><<<grid, FW_ENV_BLOCK, 0, s>>>(E, P, L, a);
+  return cudaGetLastError();
+}
+static const char* shape_name(int shape) {
+  int idx = 0;
+#define FW_NAME_SHAPE(NAME) if (shape == idx++) return #NAME;
+  FW_SHAPE_LIST(FW_NAME_SHAPE)
+#undef FW_NAME_SHAPE
+  return "generic";
+}
+static int pick_shape(const fw_config_t& cfg) {
+  const char* force = getenv("FWGYM_FORCE_GENERIC");
+  if (force && force[0] == '1') return -1;
+  return fw_find_shape(cfg.env, cfg.sim);
 }
 
 // ---- PID baseline controller (pyfly/pid_controller.py; evaluate_controller.py:141-151) ---------------------------
@@ -625,60 +693,8 @@ __global__ void __launch_bounds__(256) fw_dfma_kernel(double* out, int iters, do
 
 // ------------------------------------------------------------------------------------------------------- host side
 static int make_layout(const fw_config_t& cfg, int64_t n, FwLayout& L) {
-  const fw_env_t& E = cfg.env;
-  memset(&L, 0, sizeof(L));
-  L.n = n;
-  L.stride = (n + 31) / 32 * 32;
-  if (E.obs_len < 1 || E.obs_step < 1 || E.obs_nvar < 1 || E.obs_nvar > FW_MAX_OBS_VARS)
-    return fail(FW_ERR_CONFIG, "bad observation length/step/nvar");
-  if (E.n_targets < 0 || E.n_targets > FW_MAX_TARGETS) return fail(FW_ERR_CONFIG, "bad n_targets");
-  if (E.n_factors < 0 || E.n_factors > FW_MAX_FACTORS) return fail(FW_ERR_CONFIG, "bad n_factors");
-  if (E.streak_req > 32 * FW_MAX_GOAL_WORDS) return fail(FW_ERR_CONFIG, "success_streak_req > 256 unsupported");
-  const int imax = (E.obs_len - 1) * E.obs_step + 1;   // deepest history index used by an observation row
-  int row = D_FIXED;
-  int act_need = 0, win_obs = 0;
-  bool need_err = false, need_tgt = false, integ = false;
-  for (int v = 0; v < E.obs_nvar; ++v) {
-    L.sv_slot[v] = -1;
-    const fw_obs_var_t& ov = E.obs[v];
-    if (ov.type == 0) L.sv_slot[v] = L.n_sv_obs++;
-    if (ov.type == 1 && ov.value_kind == 0 && E.obs_len > 1) need_err = true;
-    if (ov.type == 1 && ov.value_kind == 1 && E.obs_len > 1) need_tgt = true;
-    if (ov.type == 1 && ov.value_kind == 2) { need_err = true; integ = true; }
-    if (ov.type == 2) win_obs = ov.window > win_obs ? ov.window : win_obs;
-  }
-  if (win_obs > 0) act_need = win_obs + imax;
-  bool int_err = false;
-  for (int f = 0; f < E.n_factors; ++f) {
-    const fw_factor_t& F = E.fac[f];
-    if (F.cls == 0 && F.type == 1) act_need = F.window + 1 > act_need ? F.window + 1 : act_need;
-    if (F.cls == 1 && F.type == 2) { need_err = true; int_err = true; }
-  }
-  if ((integ || int_err) && E.integration_window <= 0)
-    return fail(FW_ERR_CONFIG, "integrator observation / int_error reward need integration_window > 0");
-  if (act_need > 0) {
-    const bool raw = cfg.sim.scale_actions != 0;
-    // reward "delta" always reads the raw action history; action observations read raw actions when scale_actions
-    // and PyFly's constrained command history otherwise (fixed_wing.py:824-828)
-    L.act_depth = act_need; L.act_row = row; row += act_need * FW_N_ACT;
-    if (!raw && win_obs > 0) { L.cmd_depth = act_need; L.cmd_row = row; row += act_need * FW_N_ACT; }
-  }
-  if (E.obs_len > 1 && L.n_sv_obs > 0) { L.sv_depth = imax + 1; L.sv_row = row; row += L.sv_depth * L.n_sv_obs; }
-  else L.sv_depth = 1;
-  if (need_err) {
-    L.err_depth = ((integ || int_err) ? E.integration_window : 0) + imax + 2;
-    L.err_row = row; row += L.err_depth * E.n_targets;
-  }
-  if (need_tgt) { L.tgt_depth = imax + 1; L.tgt_row = row; row += L.tgt_depth * E.n_targets; }
-  L.goal_words = (E.streak_req + 31) / 32;
-  L.i_rows = I_FIXED;
-  if (E.metrics_enabled) {
-    L.met = 1;
-    L.m_drow = row; row += MD_ROWS;
-    L.end_row = row; row += FW_END_WINDOW * E.n_targets;
-    L.m_irow = L.i_rows; L.i_rows += MI_GRING + 3 * L.goal_words;
-  }
-  L.d_rows = row;
+  const int rc = fw_layout_build(cfg.env, cfg.sim.scale_actions, n, L);
+  if (rc) return fail(FW_ERR_CONFIG, "%s", fw_layout_error(rc));
   return FW_OK;
 }
 
@@ -780,6 +796,7 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   CK(cudaMemset(h->ctr, 0, CTR_N * sizeof(unsigned long long)));
   CK(cudaMemset(h->msum, 0, FW_N_METRIC_SUMS * sizeof(double)));
   h->generic = needs_generic(h->cfg.sim);
+  h->shape = pick_shape(h->cfg);
   {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -820,6 +837,7 @@ int fw_set_config(fw_handle h, const fw_config_t* cfg) {
   if (L.d_rows != h->L.d_rows || memcmp(&L, &h->L, sizeof(L)) != 0)
     return fail(FW_ERR_CONFIG, "fw_set_config: new config changes the state layout; create a new handle");
   h->cfg = *cfg;
+  h->shape = pick_shape(h->cfg);
   if (needs_generic(h->cfg.sim) != h->generic) {
     h->generic = !h->generic;
     cudaDeviceProp prop;
@@ -864,6 +882,12 @@ int fw_set_episode_out(fw_handle h, double* ep_out) {
   return FW_OK;
 }
 int fw_launches_per_step(fw_handle h) { return h ? 3 : 0; }
+const char* fw_kernel_variant(fw_handle h) {
+  static thread_local char buf[96];
+  if (!h) return "";
+  snprintf(buf, sizeof(buf), "dyn=%s env=%s", h->generic ? "generic" : "shipped", shape_name(h->shape));
+  return buf;
+}
 int64_t fw_state_rows(fw_handle h) { return h ? h->L.d_rows + h->L.i_rows : 0; }
 
 const char* fw_state_row_name(fw_handle h, int64_t r) {
@@ -895,8 +919,7 @@ int fw_reset(fw_handle h, const uint8_t* mask, const double* init_state, const d
   FwResetArgs a{h->d, h->i, h->n, mask, init_state, init_target, (uint32_t)h->seed, (uint32_t)(h->seed >> 32),
                 (uint32_t)h->offset, obs_out, obs64_out, fw_obs_dim(h), h->ctr};
   const int grid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
-  fw_reset_kernel<<<grid, FW_ENV_BLOCK, 0, s>>>(h->cfg.env, h->cfg.sim, h->L, a);
-  CK(cudaGetLastError());
+  CK(launch_reset(h->shape, grid, s, h->cfg.env, h->cfg.sim, h->L, a));
   h->last_stream = s;
   return FW_OK;
 }
@@ -929,8 +952,7 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
                term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum, h->carry_d,
                h->carry_i, h->ep_out, fw_episode_dim(h)};
   const int egrid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
-  fw_env_kernel<<<egrid, FW_ENV_BLOCK, 0, s>>>(h->cfg.env, h->cfg.sim, h->L, ea);
-  CK(cudaGetLastError());
+  CK(launch_env(h->shape, egrid, s, h->cfg.env, h->cfg.sim, h->L, ea));
   if (h->profiling) CK(cudaEventRecord(pe[2], s));
   h->last_stream = s;
   return FW_OK;

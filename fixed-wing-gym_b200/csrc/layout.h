@@ -71,3 +71,72 @@ enum { MI_RISE_LO = 0, MI_RISE_HI = 3, MI_SETTLE = 6 /* k, 3 = all */, MI_GSUM =
        MI_GRING = 17 /* 3 x goal_words */ };
 enum { EP_RETURN = 0, EP_LENGTH, EP_CV, EP_SUCCESS_ALL, EP_SETTLE_ALL, EP_STF_ALL, EP_PER_TARGET = 6,
        EPT_AVG = 0, EPT_TOTAL, EPT_END, EPT_RISE, EPT_OVERSHOOT, EPT_SUCCESS, EPT_SETTLE, EPT_STF, EPT_N = 8 };
+
+// Layout of the variable part.  constexpr so that the SAME function sizes a handle on the host (make_layout, fwgym.cu)
+// and folds the row numbers of a compile-time configuration shape into the specialised env kernels (env_shapes.h).
+// Returns 0 or a 1-based error number (messages: fw_layout_error).
+constexpr int fw_layout_build(const fw_env_t& E, int scale_actions, int64_t n, FwLayout& L) {
+  L = FwLayout{};
+  L.n = n;
+  L.stride = (n + 31) / 32 * 32;
+  if (E.obs_len < 1 || E.obs_step < 1 || E.obs_nvar < 1 || E.obs_nvar > FW_MAX_OBS_VARS) return 1;
+  if (E.n_targets < 0 || E.n_targets > FW_MAX_TARGETS) return 2;
+  if (E.n_factors < 0 || E.n_factors > FW_MAX_FACTORS) return 3;
+  if (E.streak_req > 32 * FW_MAX_GOAL_WORDS) return 4;
+  const int imax = (E.obs_len - 1) * E.obs_step + 1;   // deepest history index used by an observation row
+  int row = D_FIXED;
+  int act_need = 0, win_obs = 0;
+  bool need_err = false, need_tgt = false, integ = false;
+  for (int v = 0; v < E.obs_nvar; ++v) {
+    L.sv_slot[v] = -1;
+    const fw_obs_var_t& ov = E.obs[v];
+    if (ov.type == 0) L.sv_slot[v] = L.n_sv_obs++;
+    if (ov.type == 1 && ov.value_kind == 0 && E.obs_len > 1) need_err = true;
+    if (ov.type == 1 && ov.value_kind == 1 && E.obs_len > 1) need_tgt = true;
+    if (ov.type == 1 && ov.value_kind == 2) { need_err = true; integ = true; }
+    if (ov.type == 2) win_obs = ov.window > win_obs ? ov.window : win_obs;
+  }
+  if (win_obs > 0) act_need = win_obs + imax;
+  bool int_err = false;
+  for (int f = 0; f < E.n_factors; ++f) {
+    const fw_factor_t& F = E.fac[f];
+    if (F.cls == 0 && F.type == 1) act_need = F.window + 1 > act_need ? F.window + 1 : act_need;
+    if (F.cls == 1 && F.type == 2) { need_err = true; int_err = true; }
+  }
+  if ((integ || int_err) && E.integration_window <= 0) return 5;
+  if (act_need > 0) {
+    const bool raw = scale_actions != 0;
+    // reward "delta" always reads the raw action history; action observations read raw actions when scale_actions
+    // and PyFly's constrained command history otherwise (fixed_wing.py:824-828)
+    L.act_depth = act_need; L.act_row = row; row += act_need * FW_N_ACT;
+    if (!raw && win_obs > 0) { L.cmd_depth = act_need; L.cmd_row = row; row += act_need * FW_N_ACT; }
+  }
+  if (E.obs_len > 1 && L.n_sv_obs > 0) { L.sv_depth = imax + 1; L.sv_row = row; row += L.sv_depth * L.n_sv_obs; }
+  else L.sv_depth = 1;
+  if (need_err) {
+    L.err_depth = ((integ || int_err) ? E.integration_window : 0) + imax + 2;
+    L.err_row = row; row += L.err_depth * E.n_targets;
+  }
+  if (need_tgt) { L.tgt_depth = imax + 1; L.tgt_row = row; row += L.tgt_depth * E.n_targets; }
+  L.goal_words = (E.streak_req + 31) / 32;
+  L.i_rows = I_FIXED;
+  if (E.metrics_enabled) {
+    L.met = 1;
+    L.m_drow = row; row += MD_ROWS;
+    L.end_row = row; row += FW_END_WINDOW * E.n_targets;
+    L.m_irow = L.i_rows; L.i_rows += MI_GRING + 3 * L.goal_words;
+  }
+  L.d_rows = row;
+  return 0;
+}
+inline const char* fw_layout_error(int code) {
+  switch (code) {
+    case 1: return "bad observation length/step/nvar";
+    case 2: return "bad n_targets";
+    case 3: return "bad n_factors";
+    case 4: return "success_streak_req > 256 unsupported";
+    case 5: return "integrator observation / int_error reward need integration_window > 0";
+  }
+  return "";
+}
+

@@ -16,10 +16,12 @@
 #define FW_RS_ENV_U 3   // env-side uniform draws in call order (target sampling, init noise)
 #define FW_RS_ENV_N 4   // env-side normal draws in call order (observation noise), two per block
 
-// Out of line on purpose: ~100 instructions x ~25 call sites would otherwise dominate the env kernel's code size,
-// and that kernel is bound by instruction fetch.
-__device__ __noinline__ void fw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+// Two forms of every generator.  INL = false (generic, table-walking env kernels): out of line on purpose, ~100
+// instructions x ~25 call sites would otherwise dominate that kernel's code size.  INL = true (shape-specialised
+// kernels, env_shapes.h): inlined, so the independent draws of one env step (7 noise pairs + 2 gust pairs)
+// interleave instead of running as serial calls.
+__device__ __forceinline__ void fw_philox4x32_10_inl(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     uint32_t k0, uint32_t k1, uint32_t out[4]) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -32,6 +34,11 @@ __device__ __noinline__ void fw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+__device__ __noinline__ void fw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  fw_philox4x32_10_inl(c0, c1, c2, c3, k0, k1, out);
+}
+
 struct FwRng {
   uint32_t k0, k1, env, tick;
 };
@@ -41,20 +48,23 @@ __device__ __forceinline__ double fw_u53(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+template <bool INL = false>
 __device__ __forceinline__ double fw_uniform01(const FwRng& g, uint32_t stream, uint32_t idx) {
   uint32_t w[4];
-  fw_philox4x32_10(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+  if constexpr (INL) fw_philox4x32_10_inl(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+  else fw_philox4x32_10(g.env, g.tick, stream, idx, g.k0, g.k1, w);
   return fw_u53(w[0], w[1]);
 }
 
+template <bool INL = false>
 __device__ __forceinline__ double fw_uniform(const FwRng& g, uint32_t stream, uint32_t idx, double lo, double hi) {
-  return lo + (hi - lo) * fw_uniform01(g, stream, idx);   // numpy: low + (high-low)*random_sample()
+  return lo + (hi - lo) * fw_uniform01<INL>(g, stream, idx);   // numpy: low + (high-low)*random_sample()
 }
 
 // two standard normals per Philox block (Box-Muller); u1 in (0,1] so the log is finite
-__device__ __noinline__ void fw_normal2(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
+__device__ __forceinline__ void fw_normal2_inl(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
   uint32_t w[4];
-  fw_philox4x32_10(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+  fw_philox4x32_10_inl(g.env, g.tick, stream, idx, g.k0, g.k1, w);
   double u1 = 1.0 - fw_u53(w[0], w[1]);
   double u2 = fw_u53(w[2], w[3]);
   // branch-free fwmath routines (csrc/fwmath.cuh): 14 observation-noise draws + 4 gust draws per env step make
@@ -64,4 +74,12 @@ __device__ __noinline__ void fw_normal2(const FwRng& g, uint32_t stream, uint32_
   fwm_sincospi(2.0 * u2, &s, &c);
   z0 = r * c;
   z1 = r * s;
+}
+__device__ __noinline__ void fw_normal2(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
+  fw_normal2_inl(g, stream, idx, z0, z1);
+}
+template <bool INL>
+__device__ __forceinline__ void fw_normal2_t(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
+  if constexpr (INL) fw_normal2_inl(g, stream, idx, z0, z1);
+  else fw_normal2(g, stream, idx, z0, z1);
 }

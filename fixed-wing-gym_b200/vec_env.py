@@ -326,6 +326,10 @@ class FixedWingVecEnv:
     def reset_counters(self):
         _capi.check(self._lib.fw_reset_counters(self._h))
 
+    def kernel_variant(self):
+        """Which kernel instantiations the configuration selected, e.g. "dyn=shipped env=default_turb"."""
+        return self._lib.fw_kernel_variant(self._h).decode()
+
     def set_profiling(self, on=True):
         _capi.check(self._lib.fw_set_profiling(self._h, 1 if on else 0))
 

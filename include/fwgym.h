@@ -262,6 +262,9 @@ int64_t fw_num_envs(fw_handle h);
 int fw_obs_dim(fw_handle h);
 /* Kernel launches one fw_step issues: the dynamics stages (staged re-grouping, FWGYM_STAGES) + the env kernel. */
 int fw_launches_per_step(fw_handle h);
+/* Which kernel instantiations this handle's configuration selected: "dyn=<shipped|generic> env=<shape name|generic>"
+ * (dynamics.cuh "kernel specialisation", env_shapes.h).  Valid until the next call on the calling thread. */
+const char* fw_kernel_variant(fw_handle h);
 
 /* Micro-benchmark: sustained DFMA throughput of this GPU in FLOP/s (roofline denominator, bench.py). */
 int fw_dfma_peak(int device, double* flops_out, double* ms_out);

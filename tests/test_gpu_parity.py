@@ -55,13 +55,33 @@ def test_golden_fixture(built_lib, name):
     vec.close()
 
 
-@pytest.mark.parametrize("name", ["turb_noise", "failure"])
+@pytest.mark.parametrize("name", ["default", "turb_noise", "examples", "failure"])
 def test_generic_kernel_instantiation(built_lib, name, monkeypatch):
     """The dynamics kernel has two instantiations (dynamics.cuh): FwSpecShipped covers the shipped configurations and
-    FwSpecGeneric everything else (any variable clipped / constrained, steady wind, polynomial drag).  Force the
-    generic one and hold it to the same fixtures."""
+    FwSpecGeneric everything else (any variable clipped / constrained, steady wind, polynomial drag).  The env / reset
+    kernels have one instantiation per shipped configuration SHAPE plus the table-walking generic one
+    (env_shapes.h).  These four cases normally run on the specialised kernels; force the generic ones and hold them
+    to the same fixtures."""
     monkeypatch.setenv("FWGYM_FORCE_GENERIC", "1")
+    vec = make_vec(CASES[name])
+    assert vec.kernel_variant() == "dyn=generic env=generic"
+    vec.close()
     test_golden_fixture(built_lib, name)
+
+
+def test_kernel_variant_selection(built_lib):
+    """The host picks the specialised instantiations exactly for the configurations whose structure they were
+    generated from; numbers (noise level, constraint values, curriculum level) do not change the choice."""
+    want = {"default": "dyn=shipped env=default", "turb_noise": "dyn=shipped env=default_turb",
+            "examples": "dyn=shipped env=examples_turb", "failure": "dyn=shipped env=default",
+            "dev_history": "generic", "success_new": "generic", "wind": "dyn=generic env=generic"}
+    for name, v in want.items():
+        vec = make_vec(CASES[name])
+        assert vec.kernel_variant().endswith(v), (name, vec.kernel_variant())
+        if name == "default":
+            vec.set_curriculum_level(0.5)
+            assert vec.kernel_variant().endswith(v)
+        vec.close()
 
 
 def test_live_oracle_64_envs(built_lib):
