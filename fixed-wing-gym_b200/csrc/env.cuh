@@ -110,7 +110,7 @@ __device__ __forceinline__ uint32_t fw_goal_status(const fw_env_t& E, const FwEn
   const fw_env_t& Es = SH::env(E);
   uint32_t bits = 0;
   bool all = true;
-  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+  fw_loop<SH, FW_CNT(n_targets)>(Es.n_targets, [&](int k) FW_LAMBDA_INLINE {
     if (!Es.tgt[k].has_bound) return;
     const double err = fw_error(Es.tgt[k].wrap, c.D(D_TARGET + k), fw_sv<SH>(c, Es.tgt[k].sv));
     const bool ok = fabs(err) <= E.tgt[k].bound;
@@ -127,7 +127,7 @@ __device__ __forceinline__ void fw_sample_target(const fw_env_t& E, const FwEnvC
                                                  int steps_count) {
   const fw_env_t& Es = SH::env(E);
   c.I(I_STEPS_TGT) = 0;
-  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+  fw_loop<SH, FW_CNT(n_targets)>(Es.n_targets, [&](int k) FW_LAMBDA_INLINE {
     const fw_target_t& t = E.tgt[k];
     const fw_target_t& ts = Es.tgt[k];
     double low = t.low, high = t.high;
@@ -165,8 +165,8 @@ __device__ __forceinline__ void fw_next_targets(const fw_env_t& E, const fw_sim_
                                                 uint32_t flags, int steps_count, int steps_tgt, double (&out)[FW_MAX_TARGETS]) {
   const fw_env_t& Es = SH::env(E);
   int pitch_k = -1;
-  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) { if (Es.tgt[k].sv == FW_SV_PITCH) pitch_k = k; });
-  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+  fw_loop<SH, FW_CNT(n_targets)>(Es.n_targets, [&](int k) FW_LAMBDA_INLINE { if (Es.tgt[k].sv == FW_SV_PITCH) pitch_k = k; });
+  fw_loop<SH, FW_CNT(n_targets)>(Es.n_targets, [&](int k) FW_LAMBDA_INLINE {
     const fw_target_t& ts = Es.tgt[k];
     const int cfg_cls = ts.cls;
     const int cls = fw_tcls(flags, k);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void fw_ring_abs_diff(const FwEnvCtx& c, int row0, in
   double prev[NCOL];
 #pragma unroll
   for (int j = 0; j < NCOL; ++j) prev[j] = fw_ring_get(c, row0, depth, FW_N_ACT, col0 + j, lo);
-  fw_loop<SH, 8>(window - 1, [&](int t) {
+  fw_loop_le<SH, 8>(window - 1, [&](int t) FW_LAMBDA_INLINE {
     const int e = lo + 1 + t;
     if (e < hi) {
 #pragma unroll
@@ -251,7 +251,7 @@ __device__ __forceinline__ void fw_observation_body(const fw_env_t& E, const fw_
   FW_SHAPE_REFS;
   const int nv = Es.obs_nvar, len = Es.obs_len, step = Es.obs_step;
   const int W = Es.integration_window;
-  fw_loop<SH, 8>(len, [&](int row) {
+  fw_loop<SH, FW_CNT(obs_len)>(len, [&](int row) FW_LAMBDA_INLINE {
     int i = 1 + row * step;
     double init_noise = 0.0;
     bool has_init_noise = false;
@@ -261,7 +261,7 @@ __device__ __forceinline__ void fw_observation_body(const fw_env_t& E, const fw_
     }
     // index into PyFly / env histories; clamp for the failure step, where nothing was appended
     const int ih = i < hist_len ? i : hist_len;
-    fw_loop<SH, FW_MAX_OBS_VARS>(nv, [&](int v) {
+    fw_loop<SH, FW_CNT(obs_nvar)>(nv, [&](int v) FW_LAMBDA_INLINE {
       const fw_obs_var_t& ov = E.obs[v];
       const fw_obs_var_t& os = Es.obs[v];
       double val;
@@ -355,7 +355,7 @@ __device__ __forceinline__ double fw_reward(const fw_env_t& E, const fw_sim_t& P
                                             int steps_count, int hist_len, uint32_t goal_bits) {
   FW_SHAPE_REFS;
   double val_t[FW_N_FCLASS] = {0, 0, 0}, shp_t[FW_N_FCLASS] = {0, 0, 0};
-  fw_loop<SH, FW_MAX_FACTORS>(Es.n_factors, [&](int f) {
+  fw_loop<SH, FW_CNT(n_factors)>(Es.n_factors, [&](int f) FW_LAMBDA_INLINE {
     const fw_factor_t& F = E.fac[f];
     const fw_factor_t& Fs = Es.fac[f];
     double val = 0.0;
@@ -371,7 +371,7 @@ __device__ __forceinline__ double fw_reward(const fw_env_t& E, const fw_sim_t& P
             double prev[FW_N_ACT];
 #pragma unroll
             for (int j = 0; j < FW_N_ACT; ++j) prev[j] = fw_ring_get(c, Ls.act_row, Ls.act_depth, FW_N_ACT, j, lo);
-            fw_loop<SH, 8>(Fs.window - 1, [&](int t) {
+            fw_loop_le<SH, 8>(Fs.window - 1, [&](int t) FW_LAMBDA_INLINE {
               const int e = lo + 1 + t;
               if (e < steps_count) {
 #pragma unroll
@@ -412,7 +412,7 @@ __device__ __forceinline__ double fw_reward(const fw_env_t& E, const fw_sim_t& P
       val = F.value;
     } else {
       if (Fs.type == 0) {
-        fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+        fw_loop<SH, FW_CNT(n_targets)>(Es.n_targets, [&](int k) FW_LAMBDA_INLINE {
           if (Es.tgt[k].has_bound && ((goal_bits >> k) & 1u)) val += F.value / (double)Es.n_targets;
         });
       } else {
@@ -430,7 +430,7 @@ __device__ __forceinline__ double fw_reward(const fw_env_t& E, const fw_sim_t& P
     else val_t[Fs.fclass] += val * F.sign;
   });
   double reward = 0.0;
-  fw_loop<SH, FW_N_FCLASS>(Es.n_terms, [&](int ti) {
+  fw_loop<SH, FW_CNT(n_terms)>(Es.n_terms, [&](int ti) FW_LAMBDA_INLINE {
     const int fc = Es.term_fclass[ti];
     const bool has_prev = (flags >> (FWF_PREVSHAPE_SHIFT + fc)) & 1u;
     const double prev = c.D(D_PREVSHAPE + fc);
@@ -736,14 +736,14 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   fw_observation<SH>(E, P, L, c, rng, flags, 0, (flags & FWF_HIST_VALID) ? old_hist_len : 1, true, out);
   // rebuild histories
   c.I(I_HISTLEN) = 1;
-  fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+  fw_loop<SH, FW_CNT(n_targets)>(Es.n_targets, [&](int k) FW_LAMBDA_INLINE {
     const double err = fw_error(Es.tgt[k].wrap, c.D(D_TARGET + k), fw_sv<SH>(c, Es.tgt[k].sv));
     c.D(D_ERR0 + k) = err;
     if (Ls.err_depth > 0) fw_ring_put(c, Ls.err_row, Ls.err_depth, Es.n_targets, k, 0, err);
     if (Ls.tgt_depth > 0) fw_ring_put(c, Ls.tgt_row, Ls.tgt_depth, Es.n_targets, k, 0, c.D(D_TARGET + k));
   });
   if (Ls.sv_depth > 1)
-    fw_loop<SH, FW_MAX_OBS_VARS>(Es.obs_nvar, [&](int v) {
+    fw_loop<SH, FW_CNT(obs_nvar)>(Es.obs_nvar, [&](int v) FW_LAMBDA_INLINE {
       if (Es.obs[v].type == 0)
         fw_ring_put(c, Ls.sv_row, Ls.sv_depth, Ls.n_sv_obs, Ls.sv_slot[v], 0, fw_sv<SH>(c, Es.obs[v].ref));
     });

@@ -18,6 +18,7 @@
 
 struct FwShapeGeneric {
   static constexpr bool fixed = false;
+  static constexpr fw_env_t cenv{};
   static __device__ __forceinline__ const fw_env_t& env(const fw_env_t& E) { return E; }
   static __device__ __forceinline__ const fw_sim_t& sim(const fw_sim_t& P) { return P; }
   static __device__ __forceinline__ const FwLayout& lay(const FwLayout& L) { return L; }
@@ -35,6 +36,7 @@ constexpr FwLayout fw_shape_layout(const fw_env_t& e, const fw_sim_t& s) {
   __device__ const FwLayout kShapeLay_##NAME = fw_shape_layout(fw_shape_env_##NAME(), fw_shape_sim_##NAME()); \
   struct FwShape_##NAME {                                                                                  \
     static constexpr bool fixed = true;                                                                    \
+    static constexpr fw_env_t cenv = fw_shape_env_##NAME();   /* for constant expressions (loop trip counts) */ \
     static __device__ __forceinline__ const fw_env_t& env(const fw_env_t&) { return kShapeEnv_##NAME; }    \
     static __device__ __forceinline__ const fw_sim_t& sim(const fw_sim_t&) { return kShapeSim_##NAME; }    \
     static __device__ __forceinline__ const FwLayout& lay(const FwLayout&) { return kShapeLay_##NAME; }    \
@@ -42,21 +44,45 @@ constexpr FwLayout fw_shape_layout(const fw_env_t& e, const fw_sim_t& s) {
 FW_SHAPE_LIST(FW_DEFINE_SHAPE)
 #undef FW_DEFINE_SHAPE
 
-// Loop over i in [0, n).  Fixed shapes: n folds to a literal and the body is instantiated per index, so everything
-// indexed by i (shape tables, local arrays) folds too; MAXN bounds the unrolled form.
-template <class SH, int MAXN, class F>
+// Loop over i in [0, n).  Fixed shapes: the body is instantiated per index by template recursion, so everything
+// indexed by i (shape tables, local arrays) folds to literals.  (Not `#pragma unroll`: the compiler declines to unroll
+// a loop around a body as large as one observation variable, and then nothing indexed by i folds.)
+//   fw_loop<SH, N>(n, f)      N = the exact trip count as a constant expression for fixed shapes (FW_CNT below):
+//                             exactly N bodies are instantiated;
+//   fw_loop_le<SH, MAXN>(n, f) small inner loops whose count is only a literal after inlining (a window size of the
+//                             enclosing table entry): MAXN guarded bodies, the dead ones fold away.
+template <int I, int N, bool GUARD, class F>
+__device__ __forceinline__ void fw_static_for(int n, F& f) {
+  if constexpr (I < N) {
+    if (!GUARD || I < n) f(I);
+    fw_static_for<I + 1, N, GUARD>(n, f);
+  }
+}
+template <class SH, int N, class F>
 __device__ __forceinline__ void fw_loop(int n, F&& f) {
   if constexpr (SH::fixed) {
+    fw_static_for<0, N, false>(n, f);
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) f(i);
+  }
+}
+template <class SH, int MAXN, class F>
+__device__ __forceinline__ void fw_loop_le(int n, F&& f) {
+  if constexpr (SH::fixed) {
     if (n <= MAXN) {
-#pragma unroll
-      for (int i = 0; i < MAXN; ++i)
-        if (i < n) f(i);
+      fw_static_for<0, MAXN, true>(n, f);
       return;
     }
   }
 #pragma unroll 1
   for (int i = 0; i < n; ++i) f(i);
 }
+// loop bodies are lambdas; without this the inliner may keep a large body out of line, and then the shape is read
+// through a pointer at run time instead of folding
+#define FW_LAMBDA_INLINE __attribute__((always_inline))
+// trip count of a loop over a table of the env configuration, as a constant expression
+#define FW_CNT(FIELD) (SH::fixed ? SH::cenv.FIELD : 0)
 
 // ---- host side: does a runtime configuration have this shape? -------------------------------------------------------
 inline bool fw_env_same_shape(const fw_env_t& a, const fw_env_t& b) {

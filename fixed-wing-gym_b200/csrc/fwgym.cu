@@ -439,7 +439,6 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   double reward;
   int hist_len = c.I(I_HISTLEN);
   FwObsWriter ow{a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim};
-  FwObsWriter tw{a.term_obs_out, nullptr, env * (int64_t)a.obs_dim};
   if (status == 0) {
     const uint32_t gb = fw_goal_status<SH>(E, c);
     bool achieved_on_step = false, resample = false;
@@ -468,7 +467,7 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
     }
     double nt[FW_MAX_TARGETS];
     fw_next_targets<SH>(E, P, c, flags, steps, steps_tgt, nt);
-    fw_loop<SH, FW_MAX_TARGETS>(Es.n_targets, [&](int k) {
+    fw_loop<SH, FW_CNT(n_targets)>(Es.n_targets, [&](int k) FW_LAMBDA_INLINE {
       c.D(D_TARGET + k) = nt[k];
       if (Ls.tgt_depth > 0) fw_ring_put(c, Ls.tgt_row, Ls.tgt_depth, Es.n_targets, k, hist_len, nt[k]);
       if (Ls.err_depth > 0 || Ls.met) {
@@ -478,7 +477,7 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
       }
     });
     if (Ls.sv_depth > 1)
-      fw_loop<SH, FW_MAX_OBS_VARS>(Es.obs_nvar, [&](int v) {
+      fw_loop<SH, FW_CNT(obs_nvar)>(Es.obs_nvar, [&](int v) FW_LAMBDA_INLINE {
         if (Es.obs[v].type == 0)
           fw_ring_put(c, Ls.sv_row, Ls.sv_depth, Ls.n_sv_obs, Ls.sv_slot[v], hist_len, fw_sv<SH>(c, Es.obs[v].ref));
       });
@@ -491,7 +490,11 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   }
   c.I(I_STEPS) = steps;
   const bool do_reset = done && a.auto_reset;
-  if (!do_reset || a.term_obs_out) fw_observation<SH>(E, P, L, c, rng, flags, steps, hist_len, false, do_reset ? tw : ow);
+  if (!do_reset || a.term_obs_out) {
+    // an env that is about to be reset writes its terminal observation (float32 only) to term_obs_out instead
+    const FwObsWriter w{do_reset ? a.term_obs_out : a.obs_out, do_reset ? nullptr : a.obs64_out, ow.base};
+    fw_observation<SH>(E, P, L, c, rng, flags, steps, hist_len, false, w);
+  }
   c.I(I_FLAGS) = (int32_t)flags;
   const double epret = c.D(D_EPRET) + reward;
   c.D(D_EPRET) = epret;
@@ -635,7 +638,7 @@ __global__ void fw_pid_kernel(const double* __restrict__ d, int64_t stride, int6
                               const uint8_t* __restrict__ reset_mask, double* __restrict__ actions) {
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n) return;
-  auto D = [&](int row) { return d[(int64_t)row * stride + env]; };
+  auto D = [&](int row) FW_LAMBDA_INLINE { return d[(int64_t)row * stride + env]; };
   double i_va = integ[env], i_roll = integ[n + env], i_pitch = integ[2 * n + env];
   if (reset_mask && reset_mask[env]) i_va = i_roll = i_pitch = 0.0;
   const double e_va = D(D_VA) - D(D_TARGET + k_va);
