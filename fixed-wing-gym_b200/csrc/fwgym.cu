@@ -22,7 +22,7 @@
 #define FW_DYN_MIN_BLOCKS 8
 #define FW_ENV_BLOCK 128
 
-enum { CTR_ENV_STEPS = 0, CTR_ATTEMPTS, CTR_ACCEPTED, CTR_WARP_MAX, CTR_WARP_STEPS, CTR_FAILURES, CTR_RESETS, CTR_N };
+enum { CTR_ENV_STEPS = 0, CTR_ATTEMPTS, CTR_ACCEPTED, CTR_WARP_MAX, CTR_WARP_STEPS, CTR_FAILURES, CTR_RESETS, CTR_WATCHDOG, CTR_N };
 enum { MS_EPISODES = 0, MS_SUCCESS, MS_RETURN, MS_LENGTH, MS_FAILURES, MS_STEPS_TERM, MS_SUCCESS_TERM, MS_GOAL_STEPS };
 
 struct fw_handle_s {
@@ -38,6 +38,8 @@ struct fw_handle_s {
   cudaStream_t last_stream;
   int profiling;
   int generic;                   // 1: the configuration needs FwSpecGeneric (see dynamics.cuh)
+  int overlap;                   // launch the env kernel as a programmatic dependent of the attempt kernel
+  int64_t q_len;                 // ints in `queue`: Q_N + chunks
   int shape;                     // env / reset kernel instantiation: index into FW_SHAPE_LIST, -1 generic (env_shapes.h)
   double* ep_out;                // caller's episode-metric buffer (fw_set_episode_out)
   // init -> attempt -> env pipeline (see "dynamics kernels")
@@ -79,6 +81,11 @@ enum {
 };
 enum { CI_FAIL = 0, CI_ATTEMPTS, CI_ACCEPTED, CI_ROWS };
 enum { Q_LONG_COUNT = 0, Q_LONG_CURSOR, Q_NAT_CURSOR, Q_N };
+// Behind the Q_N queue counters the same buffer holds one "aircraft finished" counter per chunk of FW_ENV_BLOCK
+// consecutive envs (zeroed with the queue at the start of every step).  The env kernel is launched as a programmatic
+// dependent of the attempt kernel: its blocks become resident as attempt warps retire and each one waits for ITS chunk
+// only, so the env-side work of the early chunks runs in the shadow of the attempt kernel's tail.
+#define FW_CHUNK_DONE(q, env) ((q) + Q_N + (int)((env) / FW_ENV_BLOCK))
 
 struct FwDynArgs {
   double* d;
@@ -90,7 +97,7 @@ struct FwDynArgs {
   double* cd;          // carry rows [CY_ROWS][stride]
   int32_t* ci;         // carry int rows [CI_ROWS][stride]
   int32_t* long_list;  // [stride] aircraft to start first
-  int32_t* q;          // [Q_N] queue counters, zeroed at the start of every step
+  int32_t* q;          // [Q_N + chunks] queue counters + per-chunk finished counters, zeroed at the start of every step
   double long_h;       // initial step sizes below this go on the priority list
 };
 
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(FW_INIT_BLOCK, FW_INIT_MIN_BLOCKS)
 fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   const int64_t env = (int64_t)blockIdx.x * FW_INIT_BLOCK + threadIdx.x;
   const bool valid = env < a.n;
-  bool is_long = false;
+  bool is_long = false, init_failed = false;
   if (valid) {
     FwEnvCtx c{a.d, a.i, a.stride, env};
     double cmd[3];
@@ -166,9 +173,14 @@ fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
     ci[CI_ATTEMPTS * a.stride] = 0;
     ci[CI_ACCEPTED * a.stride] = 0;
     is_long = !failv && (double)h_abs < a.long_h;
+    init_failed = failv != 0;
   }
-  // priority list: one atomic per warp
   const unsigned full = 0xffffffffu;
+  // aircraft that raised inside RK45.__init__ are finished as far as the env kernel is concerned (a warp's envs are
+  // consecutive and FW_ENV_BLOCK is a multiple of 32: one chunk, one atomic)
+  const unsigned fm = __ballot_sync(full, valid && init_failed);
+  if (fm && (threadIdx.x & 31) == 0) atomicAdd(FW_CHUNK_DONE(a.q, env), __popc(fm));
+  // priority list: one atomic per warp
   const unsigned lm = __ballot_sync(full, is_long);
   if (lm) {
     const int lane = threadIdx.x & 31;
@@ -184,6 +196,9 @@ __global__ void __launch_bounds__(FW_DYN_BLOCK, FW_DYN_MIN_BLOCKS)
 fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwKStore<T, FW_DYN_BLOCK> K{reinterpret_cast<T*>(smem_raw)};
+  // Every warp of this (fully resident) grid is on an SM by now: let the env kernel's blocks queue up behind us.  They
+  // synchronise on the per-chunk counters below, not on this kernel's completion.
+  asm volatile("griddepcontrol.launch_dependents;");
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int n_long = a.q[Q_LONG_COUNT];     // final: the init kernel has completed
@@ -267,6 +282,8 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
         ci[CI_FAIL * a.stride] = S.fail;
         ci[CI_ATTEMPTS * a.stride] = S.attempts;
         ci[CI_ACCEPTED * a.stride] = S.accepted;
+        __threadfence();                               // results before the count (release)
+        atomicAdd(FW_CHUNK_DONE(a.q, env), 1);
       }
     }
   }
@@ -309,13 +326,14 @@ __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx
   const fw_sim_t& Ps = SH::sim(P);
 #define FW_CS(SV, X) fw_cond_s<false>(Ps.var[SV].flags, P.var[SV], SV, X, failv)
 #define FW_CSW(SV, X) fw_cond_s<true>(Ps.var[SV].flags, P.var[SV], SV, X, failv)
-  int failv = ci[CI_FAIL * stride];
-  attempts_out = ci[CI_ATTEMPTS * stride];
-  accepted_out = ci[CI_ACCEPTED * stride];
+  // carry rows: written by the attempt kernel, which may still be running on other chunks -> read past L1 (ld.cg)
+  int failv = __ldcg(ci + CI_FAIL * stride);
+  attempts_out = __ldcg(ci + CI_ATTEMPTS * stride);
+  accepted_out = __ldcg(ci + CI_ACCEPTED * stride);
   if (!failv) {
     double yd[FW_N_ODE];
 #pragma unroll
-    for (int j = 0; j < FW_N_ODE; ++j) yd[j] = cd[(CY_RES + j) * stride];
+    for (int j = 0; j < FW_N_ODE; ++j) yd[j] = __ldcg(cd + (CY_RES + j) * stride);
     double roll = 0, pitch = 0, yaw = 0, Va = 0, alpha = 0, beta = 0, elev = 0, ail = 0;
     // quaternion / |quaternion|, Euler angles: fwmath routines (asin(x) = atan2(x, sqrt((1 - x)(1 + x))))
     double qn, iqn;
@@ -396,6 +414,7 @@ struct FwEnvArgs {
   const int32_t* ci;
   double* ep_out;      // [N, ep_dim] episode-metric rows (NULL: not requested)
   int ep_dim;
+  int32_t* q;          // queue buffer of the dynamics kernels: per-chunk finished counters behind Q_N
 };
 
 // Env-side work of one env step for env `env` (fixed_wing.py:338-437 after the simulator call).  Episode-metric
@@ -547,6 +566,22 @@ __global__ void __launch_bounds__(FW_ENV_BLOCK, FW_ENV_MIN_BLOCKS)
 fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
               const FwEnvArgs a) {
   const int64_t env = (int64_t)blockIdx.x * FW_ENV_BLOCK + threadIdx.x;
+  // Wait until every aircraft of this block's chunk has been parked by the dynamics kernels (acquire side of the
+  // release in fw_attempt_kernel).  One polling thread per block; the others sleep on the barrier.  The attempt kernel
+  // never waits for anything, so this cannot deadlock; the watchdog turns a lost update into an error flag
+  // (fw_counters reports it) instead of a hung GPU.
+  if (threadIdx.x == 0) {
+    const int64_t first = (int64_t)blockIdx.x * FW_ENV_BLOCK;
+    const int need = (int)((a.n - first) < FW_ENV_BLOCK ? (a.n - first) : FW_ENV_BLOCK);
+    const volatile int32_t* cnt = FW_CHUNK_DONE(a.q, first);
+    unsigned spins = 0;
+    while (*cnt < need) {
+      __nanosleep(256);
+      if (++spins > (1u << 22)) { atomicAdd(a.ctr + CTR_WATCHDOG, 1ull); break; }   // ~1 s
+    }
+    __threadfence();
+  }
+  __syncthreads();
   double m[FW_N_METRIC_SUMS];
 #pragma unroll
   for (int k = 0; k < FW_N_METRIC_SUMS; ++k) m[k] = 0.0;
@@ -599,15 +634,30 @@ fw_reset_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_s
 }
 
 // ---- shape dispatch: index into FW_SHAPE_LIST (fw_find_shape), -1 = generic -----------------------------------------
-static cudaError_t launch_env(int shape, int grid, cudaStream_t s, const fw_env_t& E, const fw_sim_t& P, const FwLayout& L,
-                              const FwEnvArgs& a) {
+// overlap != 0: programmatic dependent launch - the kernel may start while the preceding kernel of the stream (the
+// attempt kernel) is still running; it synchronises on the per-chunk counters
+template <class SH>
+static cudaError_t launch_env_t(int grid, cudaStream_t s, int overlap, const fw_env_t& E, const fw_sim_t& P,
+                                const FwLayout& L, const FwEnvArgs& a) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(FW_ENV_BLOCK);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = overlap ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, fw_env_kernel<SH>, E, P, L, a);
+}
+static cudaError_t launch_env(int shape, int grid, cudaStream_t s, int overlap, const fw_env_t& E, const fw_sim_t& P,
+                              const FwLayout& L, const FwEnvArgs& a) {
   int idx = 0;
-#define FW_LAUNCH_SHAPE(NAME)                                                           \
-  if (shape == idx++) { fw_env_kernel<FwShape_##NAME><<<grid, FW_ENV_BLOCK, 0, s>>>(E, P, L, a); return cudaGetLastError(); }
+#define FW_LAUNCH_SHAPE(NAME) if (shape == idx++) return launch_env_t<FwShape_##NAME>(grid, s, overlap, E, P, L, a);
   FW_SHAPE_LIST(FW_LAUNCH_SHAPE)
 #undef FW_LAUNCH_SHAPE
-  fw_env_kernel<FwShapeGeneric><<<grid, FW_ENV_BLOCK, 0, s>>>(E, P, L, a);
-  return cudaGetLastError();
+  return launch_env_t<FwShapeGeneric>(grid, s, overlap, E, P, L, a);
 }
 static cudaError_t launch_reset(int shape, int grid, cudaStream_t s, const fw_env_t& E, const fw_sim_t& P,
                                 const FwLayout& L, const FwResetArgs& a) {
@@ -781,7 +831,7 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   if (cudaMalloc(&h->carry_d, (size_t)CY_ROWS * h->L.stride * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->carry_i, (size_t)CI_ROWS * h->L.stride * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->long_list, (size_t)h->L.stride * sizeof(int32_t)) != cudaSuccess ||
-      cudaMalloc(&h->queue, Q_N * sizeof(int32_t)) != cudaSuccess) {
+      cudaMalloc(&h->queue, (size_t)(h->q_len = Q_N + (h->L.stride + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK) * sizeof(int32_t)) != cudaSuccess) {
     delete h;
     return fail(FW_ERR_ALLOC, "cudaMalloc (carry) failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
@@ -800,6 +850,10 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   CK(cudaMemset(h->msum, 0, FW_N_METRIC_SUMS * sizeof(double)));
   h->generic = needs_generic(h->cfg.sim);
   h->shape = pick_shape(h->cfg);
+  {
+    const char* e = getenv("FWGYM_OVERLAP");
+    h->overlap = e ? atoi(e) : 1;
+  }
   {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -942,7 +996,7 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
     CK(cudaEventRecord(pe[0], s));
   }
-  CK(cudaMemsetAsync(h->queue, 0, Q_N * sizeof(int32_t), s));
+  CK(cudaMemsetAsync(h->queue, 0, (size_t)h->q_len * sizeof(int32_t), s));
   if (h->cfg.precision == 0) {
     CK((h->generic ? launch_dyn<double, FwSpecGeneric>(h->cfg.sim, da, h->attempt_grid, s)
                    : launch_dyn<double, FwSpecShipped>(h->cfg.sim, da, h->attempt_grid, s)));
@@ -953,9 +1007,10 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   if (h->profiling) CK(cudaEventRecord(pe[1], s));
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
                term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum, h->carry_d,
-               h->carry_i, h->ep_out, fw_episode_dim(h)};
+               h->carry_i, h->ep_out, fw_episode_dim(h), h->queue};
   const int egrid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
-  CK(launch_env(h->shape, egrid, s, h->cfg.env, h->cfg.sim, h->L, ea));
+  // with per-kernel profiling on, an event sits between the two kernels, so they are serialised anyway
+  CK(launch_env(h->shape, egrid, s, h->overlap && !h->profiling, h->cfg.env, h->cfg.sim, h->L, ea));
   if (h->profiling) CK(cudaEventRecord(pe[2], s));
   h->last_stream = s;
   return FW_OK;
@@ -1026,6 +1081,7 @@ int fw_counters(fw_handle h, fw_counters_t* out) {
   out->failures = c[CTR_FAILURES];
   out->resets = c[CTR_RESETS];
   out->rhs_evals = 2 * c[CTR_ENV_STEPS] + 6 * c[CTR_ATTEMPTS];
+  out->watchdog = c[CTR_WATCHDOG];
   return FW_OK;
 }
 

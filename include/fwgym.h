@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 7
+#define FW_ABI_VERSION 8
 
 /* ---------------------------------------------------------------------------------------------- limits */
 #define FW_MAX_OBS_VARS 32
@@ -174,6 +174,7 @@ typedef struct {
   uint64_t failures;         /* env steps that ended in a constraint failure */
   uint64_t resets;           /* auto + explicit episode resets */
   uint64_t rhs_evals;        /* RHS evaluations = 2*env_steps + 6*attempts */
+  uint64_t watchdog;         /* env-kernel blocks that gave up waiting for their chunk's aircraft (must stay 0) */
 } fw_counters_t;
 
 typedef struct fw_handle_s* fw_handle;

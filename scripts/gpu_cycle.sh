@@ -12,7 +12,7 @@ python - <<P
 import json
 d=json.load(open("gpurun_out/bench_$TAG.json"))
 r=d["roofline"]
-print("value %.4g e2e %.4g dyn_ms %.4f env_ms %.4f frac %.4f k %.3f lane_eff %.3f" % (d["value"], d["e2e"]["value"], r["kernel_ms_per_launch"], d["env_kernel"]["ms_per_launch"], r["frac"], r["mean_attempts_per_env_step"], r["warp_divergence"]["lane_efficiency"]))
+print("value %.4g ms_step %.4f e2e %.4g dyn_ms %.4f env_ms %.4f frac %.4f k %.3f lane_eff %.3f" % (d["value"], d["ms_per_step"], d["e2e"]["value"], r["kernel_ms_per_launch"], d["env_kernel"]["ms_per_launch"], r["frac"], r["mean_attempts_per_env_step"], r["warp_divergence"]["lane_efficiency"]))
 P
 if [[ "$*" != *noncu* ]]; then
   timeout 600 ncu --set full --import-source on --clock-control none -k regex:fw_dyn_kernel -s 12 -c 1 -o gpurun_out/prof_dyn_$TAG -f \

@@ -133,6 +133,26 @@ def test_scenario_injection(built_lib):
         assert pu.rel_err(vec._rew64.cpu().numpy(), np.array([r[1] for r in res]), 1e-3).max() <= TOL
 
 
+def test_overlapped_env_kernel_is_bitwise_identical(built_lib, monkeypatch):
+    """The env kernel normally runs as a programmatic dependent of the attempt kernel (its blocks start while the
+    attempt kernel's tail is still running and wait on per-chunk completion counters).  Serialised launches
+    (FWGYM_OVERLAP=0) must give bitwise identical states, and no block may ever have given up waiting."""
+    c = CASES["turb_noise"]
+    n = 4096 + 77      # several chunks per SM and a ragged last chunk
+    acts = torch.rand((12, n, 3), dtype=torch.float64, device="cuda") * 2 - 1
+    states = []
+    for overlap in ("1", "0"):
+        monkeypatch.setenv("FWGYM_OVERLAP", overlap)
+        vec = make_vec(c, n=n, seed=33)
+        vec.reset()
+        for a in acts:
+            vec.step_tensors(a)
+        states.append(vec.get_state().cpu().numpy())
+        assert vec.counters()["watchdog"] == 0
+        vec.close()
+    assert np.array_equal(states[0], states[1], equal_nan=True)
+
+
 def test_sharding_invariance(built_lib):
     """RNG is keyed by the GLOBAL env id: one handle of 32 envs == two handles of 16 with offsets 0 and 16, bitwise."""
     c = CASES["turb_noise"]
