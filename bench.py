@@ -233,7 +233,7 @@ def run_gpu_arm(a):
     # are on the host.
     from fwgym_b200 import HostStepper
     stepper = HostStepper(vec, depth=2)
-    host_actions = (torch.rand((a.steps + 4, n, 3)) * 2 - 1)
+    host_actions = (torch.rand((a.steps + 4, n, 3)) * 2 - 1).pin_memory()
     e2e_steps = a.steps
     checksum = 0.0
 
@@ -292,7 +292,7 @@ def run_gpu_arm(a):
             "clocks": clocks,
             "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes,
-                    "how": "HostStepper(depth=2): pinned host buffers, copies on their own streams, wall clock"},
+                    "how": "C-ABI fw_host_submit / fw_host_wait (HostStepper, depth 2): actions from pinned host memory, observations / rewards / dones / termination codes to pinned host memory every step, copies on their own streams, wall clock"},
             "gpu_launches": int(vec.launches_per_step * a.steps),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fl.value / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / (fl.value / 1e12), "traffic": traffic,

@@ -20,7 +20,9 @@
 
 #define FW_DYN_BLOCK 32
 #define FW_DYN_MIN_BLOCKS 8
+#ifndef FW_ENV_BLOCK
 #define FW_ENV_BLOCK 128
+#endif
 
 enum { CTR_ENV_STEPS = 0, CTR_ATTEMPTS, CTR_ACCEPTED, CTR_WARP_MAX, CTR_WARP_STEPS, CTR_FAILURES, CTR_RESETS, CTR_WATCHDOG, CTR_N };
 enum { MS_EPISODES = 0, MS_SUCCESS, MS_RETURN, MS_LENGTH, MS_FAILURES, MS_STEPS_TERM, MS_SUCCESS_TERM, MS_GOAL_STEPS };
@@ -50,6 +52,16 @@ struct fw_handle_s {
   int attempt_grid;              // persistent warps of the attempt kernel (resident capacity of the device)
   double long_div, long_h;       // priority threshold on the initial step size: long_h = dt / long_div
   std::vector<cudaEvent_t> ev;   // 3 events per profiled step: before dyn, between, after env
+  // host-buffer pipeline (fw_host_*): `depth` slots of device staging + pinned host result buffers, copy streams
+  struct HostSlot {
+    float* d_act; float* d_obs; float* d_rew; uint8_t* d_done; int32_t* d_term;
+    float* h_obs; float* h_rew; uint8_t* h_done; int32_t* h_term;
+    cudaEvent_t e_in, e_step, e_out;
+    int busy;
+  };
+  std::vector<HostSlot> hs;
+  cudaStream_t hs_in, hs_out;
+  int64_t hs_next;
 };
 
 static thread_local char g_err[512] = "";
@@ -799,6 +811,8 @@ static cudaError_t prepare_dyn(int sm_count, int* grid_out) {
 
 extern "C" {
 
+static void host_free(fw_handle h);
+
 const char* fw_last_error(void) { return g_err; }
 int fw_abi_version(void) { return FW_ABI_VERSION; }
 int64_t fw_config_sizeof(void) { return (int64_t)sizeof(fw_config_t); }
@@ -874,6 +888,7 @@ int fw_destroy(fw_handle h) {
   cudaSetDevice(h->device);
   cudaFree(h->d); cudaFree(h->i); cudaFree(h->ctr); cudaFree(h->msum);
   cudaFree(h->carry_d); cudaFree(h->carry_i); cudaFree(h->long_list); cudaFree(h->queue);
+  host_free(h);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
   return FW_OK;
@@ -1013,6 +1028,97 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   CK(launch_env(h->shape, egrid, s, h->overlap && !h->profiling, h->cfg.env, h->cfg.sim, h->L, ea));
   if (h->profiling) CK(cudaEventRecord(pe[2], s));
   h->last_stream = s;
+  return FW_OK;
+}
+
+// ---- host-buffer stepping ---------------------------------------------------------------------------------------
+static void host_free(fw_handle h) {
+  for (auto& sl : h->hs) {
+    cudaFree(sl.d_act); cudaFree(sl.d_obs); cudaFree(sl.d_rew); cudaFree(sl.d_done); cudaFree(sl.d_term);
+    cudaFreeHost(sl.h_obs); cudaFreeHost(sl.h_rew); cudaFreeHost(sl.h_done); cudaFreeHost(sl.h_term);
+    if (sl.e_in) cudaEventDestroy(sl.e_in);
+    if (sl.e_step) cudaEventDestroy(sl.e_step);
+    if (sl.e_out) cudaEventDestroy(sl.e_out);
+  }
+  if (!h->hs.empty()) { cudaStreamDestroy(h->hs_in); cudaStreamDestroy(h->hs_out); }
+  h->hs.clear();
+}
+
+int fw_host_open(fw_handle h, int depth) {
+  if (!h || depth < 1 || depth > 8) return fail(FW_ERR_ARG, "fw_host_open: bad argument");
+  CK(cudaSetDevice(h->device));
+  host_free(h);
+  const size_t n = (size_t)h->n, od = (size_t)fw_obs_dim(h);
+  CK(cudaStreamCreateWithFlags(&h->hs_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->hs_out, cudaStreamNonBlocking));
+  h->hs_next = 0;
+  for (int k = 0; k < depth; ++k) {
+    fw_handle_s::HostSlot sl = {};
+    h->hs.push_back(sl);
+    fw_handle_s::HostSlot& r = h->hs.back();
+    if (cudaMalloc(&r.d_act, n * FW_N_ACT * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&r.d_obs, n * od * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&r.d_rew, n * sizeof(float)) != cudaSuccess || cudaMalloc(&r.d_done, n) != cudaSuccess ||
+        cudaMalloc(&r.d_term, n * sizeof(int32_t)) != cudaSuccess ||
+        cudaMallocHost(&r.h_obs, n * od * sizeof(float)) != cudaSuccess ||
+        cudaMallocHost(&r.h_rew, n * sizeof(float)) != cudaSuccess || cudaMallocHost(&r.h_done, n) != cudaSuccess ||
+        cudaMallocHost(&r.h_term, n * sizeof(int32_t)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r.e_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r.e_step, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r.e_out, cudaEventDisableTiming) != cudaSuccess) {
+      const char* msg = cudaGetErrorString(cudaGetLastError());
+      host_free(h);
+      return fail(FW_ERR_ALLOC, "fw_host_open: allocation failed: %s", msg);
+    }
+  }
+  return FW_OK;
+}
+
+int fw_host_close(fw_handle h) {
+  if (!h) return FW_OK;
+  cudaSetDevice(h->device);
+  host_free(h);
+  return FW_OK;
+}
+
+int fw_host_submit(fw_handle h, const float* actions_host, void* stream, int* slot_out) {
+  if (!h || !actions_host || !slot_out) return fail(FW_ERR_ARG, "fw_host_submit: null argument");
+  if (h->hs.empty()) return fail(FW_ERR_ARG, "fw_host_submit: call fw_host_open first");
+  const int k = (int)(h->hs_next % (int64_t)h->hs.size());
+  fw_handle_s::HostSlot& sl = h->hs[k];
+  if (sl.busy) return fail(FW_ERR_ARG, "fw_host_submit: every slot is in flight; fw_host_wait the oldest one first");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)h->n, od = (size_t)fw_obs_dim(h);
+  CK(cudaMemcpyAsync(sl.d_act, actions_host, n * FW_N_ACT * sizeof(float), cudaMemcpyHostToDevice, h->hs_in));
+  CK(cudaEventRecord(sl.e_in, h->hs_in));
+  CK(cudaStreamWaitEvent(s, sl.e_in, 0));
+  int rc = fw_step(h, sl.d_act, 0, sl.d_obs, sl.d_rew, sl.d_done, sl.d_term, nullptr, nullptr, nullptr, 1, stream);
+  if (rc) return rc;
+  CK(cudaEventRecord(sl.e_step, s));
+  CK(cudaStreamWaitEvent(h->hs_out, sl.e_step, 0));
+  CK(cudaMemcpyAsync(sl.h_obs, sl.d_obs, n * od * sizeof(float), cudaMemcpyDeviceToHost, h->hs_out));
+  CK(cudaMemcpyAsync(sl.h_rew, sl.d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs_out));
+  CK(cudaMemcpyAsync(sl.h_done, sl.d_done, n, cudaMemcpyDeviceToHost, h->hs_out));
+  CK(cudaMemcpyAsync(sl.h_term, sl.d_term, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->hs_out));
+  CK(cudaEventRecord(sl.e_out, h->hs_out));
+  sl.busy = 1;
+  h->hs_next += 1;
+  *slot_out = k;
+  return FW_OK;
+}
+
+int fw_host_wait(fw_handle h, int slot, const float** obs, const float** rew, const uint8_t** done,
+                 const int32_t** term) {
+  if (!h || slot < 0 || slot >= (int)h->hs.size()) return fail(FW_ERR_ARG, "fw_host_wait: bad slot");
+  fw_handle_s::HostSlot& sl = h->hs[slot];
+  if (!sl.busy) return fail(FW_ERR_ARG, "fw_host_wait: slot was not submitted");
+  CK(cudaEventSynchronize(sl.e_out));
+  sl.busy = 0;
+  if (obs) *obs = sl.h_obs;
+  if (rew) *rew = sl.h_rew;
+  if (done) *done = sl.h_done;
+  if (term) *term = sl.h_term;
   return FW_OK;
 }
 

@@ -389,63 +389,63 @@ class FixedWingVecEnv:
 
 
 class HostStepper:
-    """Host-buffer stepping for callers whose policy lives on the CPU: actions come from (pinned) host memory and
-    observations / rewards / dones land in pinned host memory, every step.  The copies run on their own CUDA streams
-    and the device-side buffers are double-buffered, so with `depth` submissions in flight the PCIe traffic of step t
-    overlaps the kernels of step t+1 (the SubprocVecEnv reference overlaps its pipe traffic with env work the same
-    way, one process per env).  submit() never blocks on the GPU; wait() blocks until that step's results are on the
-    host.  With depth=1 this is a plain synchronous host step."""
+    """Host-buffer stepping for callers whose policy lives on the CPU: actions come from host memory and observations
+    / rewards / dones land in pinned host memory, every step.  Thin wrapper over the C-ABI pipeline (fw_host_open /
+    fw_host_submit / fw_host_wait, include/fwgym.h): the copies run on their own CUDA streams and the device-side
+    buffers are `depth`-buffered, so with `depth` submissions in flight the PCIe traffic of step t overlaps the kernels
+    of step t+1 (the SubprocVecEnv reference overlaps its pipe traffic with env work the same way, one process per
+    env).  submit() never blocks on the GPU; wait() blocks until that step's results are on the host.  With depth=1
+    this is a plain synchronous host step."""
 
     def __init__(self, vec, depth=2):
         self.vec, self.depth = vec, int(depth)
-        n, d, od = vec.num_envs, vec.device, vec.obs_dim
-        self.s_in, self.s_out = torch.cuda.Stream(d), torch.cuda.Stream(d)
-        mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-        self.slots = []
-        for _ in range(self.depth):
-            self.slots.append(dict(
-                h_act=mk((n, 3), torch.float32), h_obs=mk((n, od), torch.float32), h_rew=mk((n,), torch.float32),
-                h_done=mk((n,), torch.uint8),
-                d_act=torch.empty((n, 3), dtype=torch.float32, device=d),
-                d_obs=torch.empty((n, od), dtype=torch.float32, device=d),
-                d_rew=torch.empty(n, dtype=torch.float32, device=d), d_done=torch.empty(n, dtype=torch.uint8, device=d),
-                d_term=torch.empty(n, dtype=torch.int32, device=d),
-                e_in=torch.cuda.Event(), e_step=torch.cuda.Event(), e_out=torch.cuda.Event(), busy=False))
-        self.k = 0
+        n, od = vec.num_envs, vec.obs_dim
+        _capi.check(vec._lib.fw_host_open(vec._h, self.depth))
+        self._views = {}
         self.h2d_bytes = n * 3 * 4
-        self.d2h_bytes = n * (od * 4 + 4 + 1)
+        self.d2h_bytes = n * (od * 4 + 4 + 1 + 4)
 
     def submit(self, actions):
-        """actions: [N, 3] float32 numpy array or CPU tensor.  Returns the slot to wait() on."""
+        """actions: [N, 3] float32 numpy array or CPU tensor (pinned memory makes the upload asynchronous).  Returns
+        the slot to wait() on."""
         v = self.vec
-        sl = self.slots[self.k % self.depth]
-        if sl["busy"]:
-            raise RuntimeError("HostStepper: wait() for the oldest submission before submitting again")
-        a = actions if torch.is_tensor(actions) else torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32))
-        sl["h_act"].copy_(a)
-        cur = torch.cuda.current_stream(v.device)
-        with torch.cuda.stream(self.s_in):
-            sl["d_act"].copy_(sl["h_act"], non_blocking=True)
-            sl["e_in"].record(self.s_in)
-        cur.wait_event(sl["e_in"])
-        v.step_tensors(sl["d_act"], out=(sl["d_obs"], sl["d_rew"], sl["d_done"], sl["d_term"]))
-        sl["e_step"].record(cur)
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(sl["e_step"])
-            sl["h_obs"].copy_(sl["d_obs"], non_blocking=True)
-            sl["h_rew"].copy_(sl["d_rew"], non_blocking=True)
-            sl["h_done"].copy_(sl["d_done"], non_blocking=True)
-            sl["e_out"].record(self.s_out)
-        sl["busy"] = True
-        self.k += 1
-        return sl
+        if torch.is_tensor(actions):
+            if actions.dtype != torch.float32 or not actions.is_contiguous():
+                actions = actions.float().contiguous()
+            ptr = actions.data_ptr()
+        else:
+            actions = np.ascontiguousarray(actions, dtype=np.float32)
+            ptr = actions.ctypes.data
+        if tuple(actions.shape) != (v.num_envs, 3):
+            raise ValueError("actions must have shape (%d, 3)" % v.num_envs)
+        slot = ctypes.c_int()
+        _capi.check(v._lib.fw_host_submit(v._h, ptr, v._stream(), ctypes.byref(slot)))
+        self._keep = actions
+        return slot.value
 
-    def wait(self, sl):
+    def wait(self, slot):
         """-> (obs [N, obs_dim] float32, reward [N] float32, done [N] uint8) numpy views of the slot's pinned buffers
-        (valid until the slot is submitted again)."""
-        sl["e_out"].synchronize()
-        sl["busy"] = False
-        return sl["h_obs"].numpy(), sl["h_rew"].numpy(), sl["h_done"].numpy()
+        (valid until the slot is submitted again); the termination codes are in self.term(slot)."""
+        v = self.vec
+        po, pr, pd, pt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _capi.check(v._lib.fw_host_wait(v._h, int(slot), ctypes.byref(po), ctypes.byref(pr), ctypes.byref(pd),
+                                        ctypes.byref(pt)))
+        views = self._views.get(slot)
+        if views is None:
+            n, od = v.num_envs, v.obs_dim
+            mk = lambda p, ct, shape: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ct)), shape=shape)
+            views = (mk(po, ctypes.c_float, (n, od)), mk(pr, ctypes.c_float, (n,)), mk(pd, ctypes.c_uint8, (n,)),
+                     mk(pt, ctypes.c_int32, (n,)))
+            self._views[slot] = views
+        return views[0], views[1], views[2]
+
+    def term(self, slot):
+        return self._views[slot][3]
+
+    def close(self):
+        self._views = {}
+        if self.vec._h:
+            self.vec._lib.fw_host_close(self.vec._h)
 
 
 class SimulatorView:

@@ -210,6 +210,22 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
             int32_t* term_out, double* obs64_out, double* rew64_out, float* term_obs_out, int auto_reset,
             void* stream);
 
+/* Host-buffer stepping: the call a policy living on the CPU makes (the reference's VecEnv.step takes and returns
+ * host numpy arrays, train_rl_controller.py:223).  fw_host_open allocates `depth` slots of device staging and PINNED
+ * host result buffers plus two copy streams.  fw_host_submit enqueues, without blocking on the GPU,
+ *     H2D(actions_host) on the input copy stream -> fw_step on `stream` -> D2H(obs, reward, done, term) on the output
+ *     copy stream,
+ * and returns the slot; fw_host_wait blocks until that slot's results are on the host and returns pointers to them
+ * (valid until the slot is submitted again: depth submissions later).  With depth >= 2 the PCIe traffic of step t
+ * overlaps the kernels of step t+1.  actions_host: [N, FW_N_ACT] float32; pinned memory makes the upload asynchronous,
+ * pageable memory is staged by the driver before the call returns.  Results: obs float [N, obs_dim], reward float
+ * [N], done uint8 [N], term int32 [N] (FW_TERM_*), auto-reset semantics as fw_step(auto_reset = 1). */
+int fw_host_open(fw_handle h, int depth);
+int fw_host_close(fw_handle h);
+int fw_host_submit(fw_handle h, const float* actions_host, void* stream, int* slot_out);
+int fw_host_wait(fw_handle h, int slot, const float** obs, const float** rew, const uint8_t** done,
+                 const int32_t** term);
+
 /* Full per-env state for parity, checkpoint/resume: device double [fw_state_rows(h), N]. */
 int64_t fw_state_rows(fw_handle h);
 int fw_get_state(fw_handle h, double* out, void* stream);

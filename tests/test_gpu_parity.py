@@ -153,6 +153,44 @@ def test_overlapped_env_kernel_is_bitwise_identical(built_lib, monkeypatch):
     assert np.array_equal(states[0], states[1], equal_nan=True)
 
 
+def test_host_buffer_pipeline_matches_device_step(built_lib):
+    """fw_host_submit / fw_host_wait (HostStepper): host actions in, host results out, two submissions in flight -
+    the same numbers as stepping on device tensors, ragged env count, pageable and pinned action buffers."""
+    from fwgym_b200 import HostStepper
+    c = CASES["turb_noise"]
+    n, steps = 1000, 9
+    acts = (torch.rand((steps, n, 3)) * 2 - 1)
+    ref = make_vec(c, n=n, seed=17)
+    ref.reset()
+    want = []
+    for a in acts:
+        o, r, d, t = ref.step_tensors(a.cuda())
+        want.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy(), t.cpu().numpy().copy()))
+    ref.close()
+    vec = make_vec(c, n=n, seed=17)
+    vec.reset()
+    hs = HostStepper(vec, depth=2)
+    pinned = acts.pin_memory()
+    pending, got = [], []
+    for i in range(steps):
+        pending.append(hs.submit(pinned[i] if i % 2 else acts[i].numpy()))
+        if len(pending) == 2:
+            s = pending.pop(0)
+            o, r, d = hs.wait(s)
+            got.append((o.copy(), r.copy(), d.copy(), hs.term(s).copy()))
+    while pending:
+        s = pending.pop(0)
+        o, r, d = hs.wait(s)
+        got.append((o.copy(), r.copy(), d.copy(), hs.term(s).copy()))
+    with pytest.raises(Exception):
+        hs.wait(0)          # nothing in flight in that slot
+    for w, g in zip(want, got):
+        for x, y in zip(w, g):
+            assert np.array_equal(x.reshape(y.shape), y, equal_nan=True)
+    hs.close()
+    vec.close()
+
+
 def test_sharding_invariance(built_lib):
     """RNG is keyed by the GLOBAL env id: one handle of 32 envs == two handles of 16 with offsets 0 and 16, bitwise."""
     c = CASES["turb_noise"]
