@@ -189,11 +189,87 @@ class CompiledConfig:
                                   "never formed in the integrator)" % n)
         if self.cfg["reward"].get("randomize_scaling", False):
             raise ConfigError("reward.randomize_scaling is not supported yet (SURVEY §8f)")
-        for key in self.cfg["simulator"]:
-            if key != "states":
-                raise ConfigError("simulator.%s randomisation is not supported yet (SURVEY §8f #4)" % key)
+        self._rand_plan()   # raises on simulator-parameter randomisation entries the device path cannot honour
         if self.sim_cfg["turbulence"] and not self.cfg["steps_max"] > 0:
             raise ConfigError("turbulence needs steps_max > 0 (turbulence_sim_length = steps_max, fixed_wing.py:40)")
+
+    # --------------------------------------------------- fixed_wing.py:523-570 (sample_simulator_parameters) as a table
+    LIVE_PARAMS = ("mass", "S_wing", "b", "c", "S_prop", "k_motor", "k_T_P", "k_Omega", "C_prop", "e", "M", "a_0", "ar",
+                   "C_L_0", "C_L_alpha", "C_L_q", "C_L_delta_e", "C_D_p", "C_D_0", "C_D_alpha1", "C_D_alpha2",
+                   "C_D_beta1", "C_D_beta2", "C_D_q", "C_D_delta_e", "C_m_0", "C_m_alpha", "C_m_q", "C_m_delta_e",
+                   "C_m_fp", "C_Y_0", "C_Y_beta", "C_Y_p", "C_Y_r", "C_Y_delta_a", "C_Y_delta_r", "C_l_0", "C_l_beta",
+                   "C_l_p", "C_l_r", "C_l_delta_a", "C_l_delta_r", "C_n_0", "C_n_beta", "C_n_p", "C_n_r",
+                   "C_n_delta_a", "C_n_delta_r")
+    SIM_ATTRS = ("rho", "g")     # PyFly attributes the right-hand side reads at every evaluation
+
+    @staticmethod
+    def par_id(name):
+        """model parameter / simulator attribute name -> fw_par id (include/fwgym.h)"""
+        key = "C_L_ROLL_" + name[4:].upper() if name.startswith("C_l_") else name.upper()
+        return _capi.ENUMS["FW_PAR_" + key]
+
+    def _rand_plan(self):
+        """The draws FixedWingAircraft.sample_simulator_parameters makes at every reset, in its order: one entry per
+        draw = dict(name, par (fw_par id or -1), dist, orig, var, clip).  Entries whose parameter the dynamics never
+        read (inertia: PyFly folds it into gammas at construction) keep their draw and have par -1."""
+        plan = []
+        params = dict(self.params)
+        params["ar"] = params["b"] ** 2 / params["S_wing"]
+        for key, value in self.cfg["simulator"].items():
+            if key == "states":
+                continue
+            if key == "model":
+                dist_type = value.get("distribution", "gaussian")
+                if dist_type not in ("gaussian", "uniform"):
+                    raise ConfigError("Unexpected distribution type {}".format(dist_type))
+                for pa in value["parameters"]:
+                    name = pa["name"]
+                    if name not in params:
+                        raise ConfigError("simulator.model: unknown parameter %r" % name)
+                    orig = pa.get("original", None)
+                    if orig is None:
+                        orig = params[name]
+                    if orig == 0:
+                        continue        # fixed_wing.py:541-542: no draw at all
+                    var = pa.get("var", value["var"])
+                    rel = value["var_type"] == "relative"
+                    if rel:
+                        var = var * abs(orig)
+                    clip = pa.get("clip", value.get("clip", None)) if dist_type == "gaussian" else None
+                    if clip is not None and rel:
+                        clip = clip * orig        # signed, as the reference (:550)
+                    plan.append(dict(name=name, par=self.par_id(name) if name in self.LIVE_PARAMS else -1,
+                                     dist=0 if dist_type == "gaussian" else 1, orig=float(orig), var=float(var),
+                                     clip=clip))
+            else:
+                if key not in self.SIM_ATTRS:
+                    raise ConfigError("simulator.%s randomisation is not supported: only the model parameters and the "
+                                      "simulator attributes %s reach the dynamics" % (key, ", ".join(self.SIM_ATTRS)))
+                if "values" in value or isinstance(value["low"], bool):
+                    raise ConfigError("simulator.%s: only low/high (uniform) ranges are supported" % key)
+                plan.append(dict(name=key, par=self.par_id(key), dist=2, orig=float(value["low"]),
+                                 var=float(value["high"]), clip=None))
+        if len(plan) > _capi.DEFINES["FW_MAX_RAND"]:
+            raise ConfigError("more than %d randomised simulator parameters" % _capi.DEFINES["FW_MAX_RAND"])
+        return plan
+
+    def _rand_slots(self):
+        """-> (plan, slot1 of every fw_par id, number of per-env parameter rows).  A parameter drawn twice keeps one
+        row (the last draw wins, as the reference's dict assignment); derived rows follow the drawn ones."""
+        plan = self._rand_plan()
+        slot1 = [0] * _capi.ENUMS["FW_PAR_N"]
+        n = 0
+        for ent in plan:
+            if ent["par"] >= 0 and not slot1[ent["par"]]:
+                n += 1
+                slot1[ent["par"]] = n
+        E = _capi.ENUMS
+        for derived, sources in ((E["FW_PAR_INV_MASS"], ("MASS",)), (E["FW_PAR_INV_PI_E_AR"], ("E", "AR")),
+                                 (E["FW_PAR_EXP_2MA0"], ("M", "A_0"))):
+            if any(slot1[E["FW_PAR_" + s_]] for s_ in sources):
+                n += 1
+                slot1[derived] = n
+        return plan, slot1, n
 
     # ------------------------------------------------------------------------- fixed_wing.py:57-191 (spaces etc.)
     def _build_spaces(self):
@@ -413,6 +489,9 @@ class CompiledConfig:
         for j in range(3):
             s.act_to_low[j] = float(self.action_scale_to_low[j])
             s.act_to_high[j] = float(self.action_scale_to_high[j])
+        _, slot1, _ = self._rand_slots()
+        for i, v in enumerate(slot1):
+            s.par_slot1[i] = v
 
     def _fill_env(self, e):
         cfg = self.cfg
@@ -485,6 +564,15 @@ class CompiledConfig:
         sf = r.get("step_fail", 0)
         e.step_fail_timesteps = 1 if sf == "timesteps" else 0
         e.step_fail_value = 0.0 if sf == "timesteps" else float(sf)
+        plan, slot1, n_rows = self._rand_slots()
+        e.n_rand, e.n_par_rows = len(plan), n_rows
+        for j, ent in enumerate(plan):
+            rd = e.rand[j]
+            rd.par, rd.dist = ent["par"], ent["dist"]
+            rd.slot1 = slot1[ent["par"]] if ent["par"] >= 0 else 0
+            rd.orig, rd.var = ent["orig"], ent["var"]
+            rd.has_clip = 1 if ent["clip"] is not None else 0
+            rd.clip = float(ent["clip"]) if ent["clip"] is not None else 0.0
         e.metrics_enabled = 1 if self.metrics else 0
         e.rise_low, e.rise_high = 0.1, 0.9          # get_metric defaults (fixed_wing.py:1131)
         for m in cfg.get("metrics", []):

@@ -98,10 +98,56 @@ struct FwSpecShipped {
                                    FW_RB(FW_R_ELEV) | FW_RB(FW_R_VA) | FW_RB(FW_R_AD0) | FW_RB(FW_R_AD1);
   static constexpr uint32_t cons = FW_RB(FW_R_P) | FW_RB(FW_R_Q) | FW_RB(FW_R_R) | FW_RB(FW_R_VA);
   static constexpr bool generic = false;
+  static constexpr bool rand = false;
 };
 struct FwSpecGeneric {
   static constexpr uint32_t clip = 0xffffffffu, cons = 0xffffffffu;
   static constexpr bool generic = true;
+  static constexpr bool rand = false;
+};
+//   FwSpecRand    : FwSpecGeneric + model parameters that differ per aircraft (simulator-parameter randomisation,
+//                   fixed_wing.py:523-570): every live parameter is read through FwPar below.
+struct FwSpecRand {
+  static constexpr uint32_t clip = 0xffffffffu, cons = 0xffffffffu;
+  static constexpr bool generic = true;
+  static constexpr bool rand = true;
+};
+
+// ---- live model parameters ---------------------------------------------------------------------------------------
+// (fw_par id, fw_sim_t field).  PyFly reads these from its params dict / attributes at every RHS evaluation, so
+// FixedWingAircraft.sample_simulator_parameters can change them per episode.  RAND = false: the shared value, a
+// constant-bank operand.  RAND = true: parameters the configuration randomises live in per-env rows
+// (P.par_slot1[id] - 1, a warp-uniform test per read); the others still come from the constant bank.
+#define FW_LIVE_PARAMS(X)                                                                                             \
+  X(MASS, mass) X(S_WING, S_wing) X(B, b) X(C, c) X(S_PROP, S_prop) X(K_MOTOR, k_motor) X(K_T_P, k_T_P)               \
+  X(K_OMEGA, k_Omega) X(C_PROP, C_prop) X(E, e) X(M, M) X(A_0, a_0) X(AR, ar)                                         \
+  X(C_L_0, C_L_0) X(C_L_ALPHA, C_L_alpha) X(C_L_Q, C_L_q) X(C_L_DELTA_E, C_L_delta_e)                                 \
+  X(C_D_P, C_D_p) X(C_D_0, C_D_0) X(C_D_ALPHA1, C_D_alpha1) X(C_D_ALPHA2, C_D_alpha2) X(C_D_BETA1, C_D_beta1)         \
+  X(C_D_BETA2, C_D_beta2) X(C_D_Q, C_D_q) X(C_D_DELTA_E, C_D_delta_e)                                                 \
+  X(C_M_0, C_m_0) X(C_M_ALPHA, C_m_alpha) X(C_M_Q, C_m_q) X(C_M_DELTA_E, C_m_delta_e) X(C_M_FP, C_m_fp)               \
+  X(C_Y_0, C_Y_0) X(C_Y_BETA, C_Y_beta) X(C_Y_P, C_Y_p) X(C_Y_R, C_Y_r) X(C_Y_DELTA_A, C_Y_delta_a)                   \
+  X(C_Y_DELTA_R, C_Y_delta_r)                                                                                         \
+  X(C_L_ROLL_0, C_l_0) X(C_L_ROLL_BETA, C_l_beta) X(C_L_ROLL_P, C_l_p) X(C_L_ROLL_R, C_l_r)                           \
+  X(C_L_ROLL_DELTA_A, C_l_delta_a) X(C_L_ROLL_DELTA_R, C_l_delta_r)                                                   \
+  X(C_N_0, C_n_0) X(C_N_BETA, C_n_beta) X(C_N_P, C_n_p) X(C_N_R, C_n_r) X(C_N_DELTA_A, C_n_delta_a)                   \
+  X(C_N_DELTA_R, C_n_delta_r)                                                                                         \
+  X(RHO, rho) X(G, g) X(INV_MASS, inv_mass) X(INV_PI_E_AR, inv_pi_e_ar) X(EXP_2MA0, exp_2Ma0)
+static_assert(FW_PAR_N == FW_N_PAR, "FW_N_PAR in fwgym.h must equal the number of fw_par ids");
+
+template <typename T, bool RAND> struct FwPar {
+  const fw_sim_t& P;
+  const double* base;   // RAND: this aircraft's element of parameter row 0
+  int64_t stride;
+#define FW_PAR_GETTER(ID, F)                                                      \
+  __device__ __forceinline__ T F() const {                                        \
+    if constexpr (RAND) {                                                         \
+      const int s1 = P.par_slot1[FW_PAR_##ID];                                    \
+      if (s1) return (T)base[(int64_t)(s1 - 1) * stride];                         \
+    }                                                                             \
+    return (T)P.F;                                                                \
+  }
+  FW_LIVE_PARAMS(FW_PAR_GETTER)
+#undef FW_PAR_GETTER
 };
 
 // branch-free condition of the variable of rank R: violated constraints set bit R of failmask.  RAW: no condition
@@ -129,8 +175,8 @@ __device__ __forceinline__ T fw_cond_r(const fw_var_t& v, T x, uint32_t& failmas
 // the first right-hand side of an episode must not clip / check the state variables.  Va, alpha, beta (and the
 // elevator / aileron mapping) are conditioned in _forces at every evaluation.
 template <typename T, class Spec, bool RAW = false>
-__device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in, const T (&y)[FW_N_ODE],
-                                       T (&dy)[FW_N_ODE], uint32_t& failmask) {
+__device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwPar<T, Spec::rand>& PP, const FwStepIn<T>& in,
+                                       const T (&y)[FW_N_ODE], T (&dy)[FW_N_ODE], uint32_t& failmask) {
   typedef FwMath<T> Mt;
   const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
   const T p = fw_cond_r<T, Spec, FW_R_P, RAW>(P.var[FW_SV_OMEGA_P], y[4], failmask);
@@ -181,25 +227,25 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
   beta = fw_cond_r<T, Spec, FW_R_BETA>(P.var[FW_SV_BETA], beta, failmask);
 
   // ---- forces and moments (PyFly._forces) ----
-  const T pre = (T)0.5 * (T)P.rho * Va * Va * (T)P.S_wing;
-  const T mg = (T)P.mass * (T)P.g;
+  const T pre = (T)0.5 * PP.rho() * Va * Va * PP.S_wing();
+  const T mg = PP.mass() * PP.g();
   const T fgx = mg * (2 * (e1 * e3 - e2 * e0));
   const T fgy = mg * (2 * (e2 * e3 + e1 * e0));
   const T fgz = mg * (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2);
 
-  const T CLlin = (T)P.C_L_0 + (T)P.C_L_alpha * alpha;
+  const T CLlin = PP.C_L_0() + PP.C_L_alpha() * alpha;
   // sigma = (1 + e1 + e2) / ((1 + e1)(1 + e2)), e1 = exp(-M(alpha - a0)), e2 = exp(M(alpha + a0)).  e1 * e2 is the
   // constant exp(2 M a0) (host-computed), so fp64 needs ONE exponential: with e2 = C / e1 the quotient becomes
   // (e1 + e1^2 + C) / ((1 + e1)(e1 + C)); |alpha| <= pi keeps e1^2 far inside the fp64 range.
   T sigma;
   if constexpr (sizeof(T) == 8) {
-    const T x1 = Mt::exp_(-(T)P.M * (alpha - (T)P.a_0));
-    const T C = (T)P.exp_2Ma0;
+    const T x1 = Mt::exp_(-PP.M() * (alpha - PP.a_0()));
+    const T C = PP.exp_2Ma0();
     sigma = Mt::div_(fma(x1, x1, x1) + C, (1 + x1) * (x1 + C));
   } else {
     // fp32: (1+e1)(1+e2) must stay below FLT_MAX, so both exponents are clamped (e1 * e2 is constant)
-    const T ex1 = Mt::exp_(fminf(-(T)P.M * (alpha - (T)P.a_0), 80.0f));
-    const T ex2 = Mt::exp_(fminf((T)P.M * (alpha + (T)P.a_0), 80.0f));
+    const T ex1 = Mt::exp_(fminf(-PP.M() * (alpha - PP.a_0()), 80.0f));
+    const T ex2 = Mt::exp_(fminf(PP.M() * (alpha + PP.a_0()), 80.0f));
     sigma = (1 + ex1 + ex2) / ((1 + ex1) * (1 + ex2));
   }
   // sin/cos of alpha and beta follow algebraically from the airspeed components (beta = asin(v_r / |v_r|) uses the
@@ -218,31 +264,31 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
   const T sgn = alpha > 0 ? (T)1 : (alpha < 0 ? (T)-1 : (T)0);
   const T CL = (1 - sigma) * CLlin + sigma * (2 * sgn * sa * sa * ca);
   const T inv2Va = (T)0.5 * invVa;
-  const T c2Va = (T)P.c * inv2Va, b2Va = (T)P.b * inv2Va;
-  const T lift = pre * (CL + (T)P.C_L_q * c2Va * qa + (T)P.C_L_delta_e * elev);
+  const T c2Va = PP.c() * inv2Va, b2Va = PP.b() * inv2Va;
+  const T lift = pre * (CL + PP.C_L_q() * c2Va * qa + PP.C_L_delta_e() * elev);
   T CDa;
   if (!Spec::generic || P.drag_model == 0)
-    CDa = (T)P.C_D_p + (1 - sigma) * CLlin * CLlin * (T)P.inv_pi_e_ar + sigma * (2 * sgn * sa * sa * sa);
+    CDa = PP.C_D_p() + (1 - sigma) * CLlin * CLlin * PP.inv_pi_e_ar() + sigma * (2 * sgn * sa * sa * sa);
   else
-    CDa = (T)P.C_D_0 + (T)P.C_D_alpha1 * alpha + (T)P.C_D_alpha2 * alpha * alpha;
-  const T CDb = (T)P.C_D_beta1 * beta + (T)P.C_D_beta2 * beta * beta;
-  const T drag = pre * (CDa + CDb + (T)P.C_D_q * c2Va * qa + (T)P.C_D_delta_e * elev * elev);
-  const T Cm = (1 - sigma) * ((T)P.C_m_0 + (T)P.C_m_alpha * alpha) + sigma * ((T)P.C_m_fp * sgn * sa * sa);
-  const T mm = pre * (T)P.c * (Cm + (T)P.C_m_q * b2Va * qa + (T)P.C_m_delta_e * elev);
-  const T fy = pre * ((T)P.C_Y_0 + (T)P.C_Y_beta * beta + (T)P.C_Y_p * b2Va * pa + (T)P.C_Y_r * b2Va * ra +
-                      (T)P.C_Y_delta_a * ail + (T)P.C_Y_delta_r * rud);
-  const T ll = pre * (T)P.b * ((T)P.C_l_0 + (T)P.C_l_beta * beta + (T)P.C_l_p * b2Va * pa + (T)P.C_l_r * b2Va * ra +
-                               (T)P.C_l_delta_a * ail + (T)P.C_l_delta_r * rud);
-  const T nn = pre * (T)P.b * ((T)P.C_n_0 + (T)P.C_n_beta * beta + (T)P.C_n_p * b2Va * pa + (T)P.C_n_r * b2Va * ra +
-                               (T)P.C_n_delta_a * ail + (T)P.C_n_delta_r * rud);
+    CDa = PP.C_D_0() + PP.C_D_alpha1() * alpha + PP.C_D_alpha2() * alpha * alpha;
+  const T CDb = PP.C_D_beta1() * beta + PP.C_D_beta2() * beta * beta;
+  const T drag = pre * (CDa + CDb + PP.C_D_q() * c2Va * qa + PP.C_D_delta_e() * elev * elev);
+  const T Cm = (1 - sigma) * (PP.C_m_0() + PP.C_m_alpha() * alpha) + sigma * (PP.C_m_fp() * sgn * sa * sa);
+  const T mm = pre * PP.c() * (Cm + PP.C_m_q() * b2Va * qa + PP.C_m_delta_e() * elev);
+  const T fy = pre * (PP.C_Y_0() + PP.C_Y_beta() * beta + PP.C_Y_p() * b2Va * pa + PP.C_Y_r() * b2Va * ra +
+                      PP.C_Y_delta_a() * ail + PP.C_Y_delta_r() * rud);
+  const T ll = pre * PP.b() * (PP.C_l_0() + PP.C_l_beta() * beta + PP.C_l_p() * b2Va * pa + PP.C_l_r() * b2Va * ra +
+                               PP.C_l_delta_a() * ail + PP.C_l_delta_r() * rud);
+  const T nn = pre * PP.b() * (PP.C_n_0() + PP.C_n_beta() * beta + PP.C_n_p() * b2Va * pa + PP.C_n_r() * b2Va * ra +
+                               PP.C_n_delta_a() * ail + PP.C_n_delta_r() * rud);
   // f_aero = R(0, alpha, beta) * [-D, Y, -L]
   const T fax = ca * cb * (-drag) + ca * sb * fy + sa * lift;
   const T fay = sb * drag + cb * fy;
   const T faz = sa * cb * (-drag) + sa * sb * fy - ca * lift;
-  const T Vd = Va + th * ((T)P.k_motor - Va);
-  const T fprop = (T)0.5 * (T)P.rho * (T)P.S_prop * (T)P.C_prop * Vd * (Vd - Va);
-  const T kot = (T)P.k_Omega * th;
-  const T tprop = -(T)P.k_T_P * kot * kot;
+  const T Vd = Va + th * (PP.k_motor() - Va);
+  const T fprop = (T)0.5 * PP.rho() * PP.S_prop() * PP.C_prop() * Vd * (Vd - Va);
+  const T kot = PP.k_Omega() * th;
+  const T tprop = -PP.k_T_P() * kot * kot;
   const T fx = fprop + fgx + fax, fyy = fgy + fay, fz = fgz + faz;
   const T tl = ll + tprop, tm = mm, tn = nn;
 
@@ -258,7 +304,7 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwStepIn<T>& in,
   dy[7] = (e1 * e1 + e0 * e0 - e2 * e2 - e3 * e3) * u + 2 * (e1 * e2 - e3 * e0) * v + 2 * (e1 * e3 + e2 * e0) * w;
   dy[8] = 2 * (e1 * e2 + e3 * e0) * u + (e2 * e2 + e0 * e0 - e1 * e1 - e3 * e3) * v + 2 * (e2 * e3 - e1 * e0) * w;
   dy[9] = 2 * (e1 * e3 - e2 * e0) * u + 2 * (e2 * e3 + e1 * e0) * v + (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2) * w;
-  const T im = (T)P.inv_mass;
+  const T im = PP.inv_mass();
   dy[10] = r * v - q * w + fx * im;
   dy[11] = p * w - r * u + fyy * im;
   dy[12] = q * u - p * v + fz * im;
@@ -330,13 +376,13 @@ __device__ __forceinline__ int fw_fail_code(uint32_t failmask) {
 // initial step size (clamped to the interval; the min_step clamp of the first _step_impl call is applied by
 // fw_ivp_attempt like for every other entry).
 template <typename T, class Spec>
-__device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const FwStepIn<T>& in, const T (&y)[FW_N_ODE],
-                                           T (&f0)[FW_N_ODE], T& h_abs) {
+__device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const FwPar<T, Spec::rand>& PP, const FwStepIn<T>& in,
+                                           const T (&y)[FW_N_ODE], T (&f0)[FW_N_ODE], T& h_abs) {
   typedef FwMath<T> Mt;
   const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
   const T inv_sqrtn = (T)(1.0 / 4.358898943540674);   // 1 / 19 ** 0.5
   uint32_t failmask = 0u;
-  fw_rhs<T, Spec, true>(P, in, y, f0, failmask);   // t == 0: stored state values, unconditioned
+  fw_rhs<T, Spec, true>(P, PP, in, y, f0, failmask);   // t == 0: stored state values, unconditioned
   if (failmask) return fw_fail_code<T>(failmask);
   T isc[FW_N_ODE];
   T s0 = 0, s1 = 0;
@@ -354,7 +400,7 @@ __device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const FwStepIn<T>&
   T y1[FW_N_ODE], f1[FW_N_ODE];
 #pragma unroll
   for (int c = 0; c < FW_N_ODE; ++c) y1[c] = y[c] + h0 * f0[c];
-  fw_rhs<T, Spec>(P, in, y1, f1, failmask);
+  fw_rhs<T, Spec>(P, PP, in, y1, f1, failmask);
   if (failmask) return fw_fail_code<T>(failmask);
   T s2 = 0;
 #pragma unroll
@@ -381,8 +427,8 @@ __device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const FwStepIn<T>&
 // acceptance); sets S.status to FINISHED when t reaches t_bound or an RHS evaluation raises, TOO_SMALL when the step
 // size underflows.
 template <typename T, class Spec, int BLOCK>
-__device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const FwStepIn<T>& in, FwIvp<T>& S,
-                                               FwKStore<T, BLOCK> K) {
+__device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const FwPar<T, Spec::rand>& PP,
+                                               const FwStepIn<T>& in, FwIvp<T>& S, FwKStore<T, BLOCK> K) {
   typedef FwMath<T> Mt;
   const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
   const T inv_sqrtn = (T)(1.0 / 4.358898943540674);
@@ -418,7 +464,7 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const FwStepIn
       for (int j = 0; j < 3; ++j) ys[7 + j] = S.y[7 + j] + h * accB[j];
     }
     uint32_t failmask = 0u;
-    fw_rhs<T, Spec>(P, in, ys, f, failmask);
+    fw_rhs<T, Spec>(P, PP, in, ys, f, failmask);
     if (failmask) {
       S.fail = fw_fail_code<T>(failmask);
       S.status = FW_STATUS_FINISHED;

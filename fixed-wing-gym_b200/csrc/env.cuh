@@ -721,6 +721,33 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   const int old_hist_len = c.I(I_HISTLEN);
   c.I(I_STEPS) = 0;
   FwEnvRngT<false> rng{g, 0u, 0u, 0.0};
+  // sample_simulator_parameters (fixed_wing.py:523-570) runs between simulator.reset and sample_target (:308-310) and
+  // draws from the env's generator in table order.  Fixed shapes have no table (n_rand == 0).
+  if (Es.n_rand > 0) {
+    for (int j = 0; j < E.n_rand; ++j) {
+      const fw_rand_t& r = E.rand[j];
+      double v;
+      if (r.dist == 0) {
+        v = rng.normal(r.orig, r.var);
+        if (r.has_clip) { v = fmax(v, r.orig - r.clip); v = fmin(v, r.orig + r.clip); }   // np.clip order
+      } else if (r.dist == 1) {
+        v = rng.uniform(r.orig - r.var, r.orig + r.var);
+      } else {
+        v = rng.uniform(r.orig, r.var);
+      }
+      if (r.slot1) c.D(Ls.par_row + r.slot1 - 1) = v;
+    }
+    // derived rows: what the right-hand side multiplies by instead of dividing / exponentiating at every evaluation
+    auto par = [&](int id, double shared) -> double {
+      const int s1 = P.par_slot1[id];
+      return s1 ? c.D(Ls.par_row + s1 - 1) : shared;
+    };
+    if (P.par_slot1[FW_PAR_INV_MASS]) c.D(Ls.par_row + P.par_slot1[FW_PAR_INV_MASS] - 1) = 1.0 / par(FW_PAR_MASS, P.mass);
+    if (P.par_slot1[FW_PAR_INV_PI_E_AR])
+      c.D(Ls.par_row + P.par_slot1[FW_PAR_INV_PI_E_AR] - 1) = 1.0 / (CUDART_PI * par(FW_PAR_E, P.e) * par(FW_PAR_AR, P.ar));
+    if (P.par_slot1[FW_PAR_EXP_2MA0])
+      c.D(Ls.par_row + P.par_slot1[FW_PAR_EXP_2MA0] - 1) = exp(2.0 * par(FW_PAR_M, P.M) * par(FW_PAR_A_0, P.a_0));
+  }
   fw_sample_target<SH>(E, c, rng, flags, 0);
   if (init_target) {
     for (int k = 0; k < Es.n_targets; ++k) {

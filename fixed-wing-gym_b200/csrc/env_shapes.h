@@ -91,7 +91,7 @@ inline bool fw_env_same_shape(const fw_env_t& a, const fw_env_t& b) {
       a.has_bounds != b.has_bounds || a.n_targets != b.n_targets || a.resample_every != b.resample_every ||
       a.streak_req != b.streak_req || a.on_success != b.on_success || a.n_factors != b.n_factors ||
       a.potential != b.potential || a.step_fail_timesteps != b.step_fail_timesteps || a.n_terms != b.n_terms ||
-      a.metrics_enabled != b.metrics_enabled)
+      a.metrics_enabled != b.metrics_enabled || a.n_rand != b.n_rand || a.n_par_rows != b.n_par_rows)
     return false;
   for (int v = 0; v < a.obs_nvar; ++v) {
     const fw_obs_var_t &x = a.obs[v], &y = b.obs[v];

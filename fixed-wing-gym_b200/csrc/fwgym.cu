@@ -39,7 +39,7 @@ struct fw_handle_s {
   double* msum;              // FW_N_METRIC_SUMS
   cudaStream_t last_stream;
   int profiling;
-  int generic;                   // 1: the configuration needs FwSpecGeneric (see dynamics.cuh)
+  int generic;                   // dynamics instantiation: 0 FwSpecShipped, 1 FwSpecGeneric, 2 FwSpecRand (dynamics.cuh)
   int overlap;                   // launch the env kernel as a programmatic dependent of the attempt kernel
   int64_t q_len;                 // ints in `queue`: Q_N + chunks
   int shape;                     // env / reset kernel instantiation: index into FW_SHAPE_LIST, -1 generic (env_shapes.h)
@@ -111,6 +111,7 @@ struct FwDynArgs {
   int32_t* long_list;  // [stride] aircraft to start first
   int32_t* q;          // [Q_N + chunks] queue counters + per-chunk finished counters, zeroed at the start of every step
   double long_h;       // initial step sizes below this go on the priority list
+  int32_t par_row;     // first per-env model-parameter row of d (FwSpecRand)
 };
 
 // ---- action -> actuator commands (fixed_wing.py:349-354,439-459; Actuation.set_and_constrain_commands) ----
@@ -173,7 +174,8 @@ fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
     T y[FW_N_ODE], f0[FW_N_ODE], h_abs = 0;
 #pragma unroll
     for (int j = 0; j < FW_N_ODE; ++j) y[j] = (T)c.D(j);
-    const int failv = fw_ivp_init<T, Spec>(P, in, y, f0, h_abs);
+    const FwPar<T, Spec::rand> PP{P, a.d + (int64_t)a.par_row * a.stride + env, a.stride};
+    const int failv = fw_ivp_init<T, Spec>(P, PP, in, y, f0, h_abs);
     double* cd = a.cd + env;
     int32_t* ci = a.ci + env;
 #pragma unroll
@@ -218,6 +220,7 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   FwIvp<T> S;
   FwStepIn<T> in;
   int64_t env = -1;
+  const double* par_base = a.d;   // FwSpecRand: the adopted aircraft's element of parameter row 0
   S.status = FW_STATUS_FINISHED;
   S.fail = 0; S.rejected = 0; S.attempts = 0; S.accepted = 0; S.t = 0; S.h_abs = 0;
 #pragma unroll
@@ -262,6 +265,7 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
           const bool skip = failv != 0 || (!from_long && h0 < a.long_h);
           if (!skip) {
             env = e;
+            par_base = a.d + (int64_t)a.par_row * a.stride + e;
             FwEnvCtx c{a.d, a.i, a.stride, e};
 #pragma unroll
             for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = (T)c.D(j);
@@ -285,7 +289,8 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
     ++passes;
     if (S.status == FW_STATUS_RUNNING) {
       ++lane_attempts;
-      fw_ivp_attempt<T, Spec, FW_DYN_BLOCK>(P, in, S, K);
+      const FwPar<T, Spec::rand> PP{P, par_base, a.stride};
+      fw_ivp_attempt<T, Spec, FW_DYN_BLOCK>(P, PP, in, S, K);
       if (S.status != FW_STATUS_RUNNING) {   // env step finished (or raised): park the result for the env kernel
         double* cd = a.cd + env;
         int32_t* ci = a.ci + env;
@@ -768,6 +773,8 @@ static int needs_generic(const fw_sim_t& S) {
   static const int rank_sv[FW_R_BETA + 1] = {FW_SV_OMEGA_P, FW_SV_OMEGA_Q, FW_SV_OMEGA_R, FW_SV_VEL_U, FW_SV_VEL_V,
                                              FW_SV_VEL_W, FW_SV_ELEVON_L, FW_SV_ELEVON_R, FW_SV_THROTTLE,
                                              FW_SV_AILERON, FW_SV_ELEVATOR, FW_SV_VA, FW_SV_ALPHA, FW_SV_BETA};
+  for (int i = 0; i < FW_PAR_N; ++i)
+    if (S.par_slot1[i]) return 2;   // per-env model parameters: FwSpecRand
   const char* force = getenv("FWGYM_FORCE_GENERIC");
   if (force && force[0] == '1') return 1;
   uint32_t clip = 0, cons = 0;
@@ -807,6 +814,28 @@ static cudaError_t prepare_dyn(int sm_count, int* grid_out) {
   if (e != cudaSuccess) return e;
   if (grid_out) *grid_out = per_sm * sm_count;
   return cudaSuccess;
+}
+
+// dynamics instantiation by (precision, spec)
+static cudaError_t launch_dyn_any(int precision, int spec, const fw_sim_t& sim, const FwDynArgs& da, int grid, cudaStream_t s) {
+  if (precision == 0) {
+    if (spec == 0) return launch_dyn<double, FwSpecShipped>(sim, da, grid, s);
+    if (spec == 1) return launch_dyn<double, FwSpecGeneric>(sim, da, grid, s);
+    return launch_dyn<double, FwSpecRand>(sim, da, grid, s);
+  }
+  if (spec == 0) return launch_dyn<float, FwSpecShipped>(sim, da, grid, s);
+  if (spec == 1) return launch_dyn<float, FwSpecGeneric>(sim, da, grid, s);
+  return launch_dyn<float, FwSpecRand>(sim, da, grid, s);
+}
+static cudaError_t prepare_dyn_any(int precision, int spec, int sms, int* grid_out) {
+  if (precision == 0) {
+    if (spec == 0) return prepare_dyn<double, FwSpecShipped>(sms, grid_out);
+    if (spec == 1) return prepare_dyn<double, FwSpecGeneric>(sms, grid_out);
+    return prepare_dyn<double, FwSpecRand>(sms, grid_out);
+  }
+  if (spec == 0) return prepare_dyn<float, FwSpecShipped>(sms, grid_out);
+  if (spec == 1) return prepare_dyn<float, FwSpecGeneric>(sms, grid_out);
+  return prepare_dyn<float, FwSpecRand>(sms, grid_out);
 }
 
 extern "C" {
@@ -873,8 +902,7 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
     CK(cudaGetDeviceProperties(&prop, device));
     const int sms = prop.multiProcessorCount;
     int g = 0;
-    if (h->cfg.precision == 0) CK((h->generic ? prepare_dyn<double, FwSpecGeneric>(sms, &g) : prepare_dyn<double, FwSpecShipped>(sms, &g)));
-    else CK((h->generic ? prepare_dyn<float, FwSpecGeneric>(sms, &g) : prepare_dyn<float, FwSpecShipped>(sms, &g)));
+    CK(prepare_dyn_any(h->cfg.precision, h->generic, sms, &g));
     const char* e = getenv("FWGYM_ATTEMPT_WARPS_PER_SM");
     if (e && atoi(e) > 0) g = atoi(e) * sms;
     h->attempt_grid = g > 0 ? g : sms;
@@ -911,13 +939,12 @@ int fw_set_config(fw_handle h, const fw_config_t* cfg) {
   h->cfg = *cfg;
   h->shape = pick_shape(h->cfg);
   if (needs_generic(h->cfg.sim) != h->generic) {
-    h->generic = !h->generic;
+    h->generic = needs_generic(h->cfg.sim);
     cudaDeviceProp prop;
     CK(cudaSetDevice(h->device));
     CK(cudaGetDeviceProperties(&prop, h->device));
     int g = 0;
-    if (h->cfg.precision == 0) CK((h->generic ? prepare_dyn<double, FwSpecGeneric>(prop.multiProcessorCount, &g) : prepare_dyn<double, FwSpecShipped>(prop.multiProcessorCount, &g)));
-    else CK((h->generic ? prepare_dyn<float, FwSpecGeneric>(prop.multiProcessorCount, &g) : prepare_dyn<float, FwSpecShipped>(prop.multiProcessorCount, &g)));
+    CK(prepare_dyn_any(h->cfg.precision, h->generic, prop.multiProcessorCount, &g));
     if (g > 0) h->attempt_grid = g;
   }
   h->long_h = h->long_div > 0 ? h->cfg.sim.dt / h->long_div : 0.0;
@@ -957,7 +984,8 @@ int fw_launches_per_step(fw_handle h) { return h ? 3 : 0; }
 const char* fw_kernel_variant(fw_handle h) {
   static thread_local char buf[96];
   if (!h) return "";
-  snprintf(buf, sizeof(buf), "dyn=%s env=%s", h->generic ? "generic" : "shipped", shape_name(h->shape));
+  snprintf(buf, sizeof(buf), "dyn=%s env=%s", h->generic == 2 ? "rand" : (h->generic ? "generic" : "shipped"),
+           shape_name(h->shape));
   return buf;
 }
 int64_t fw_state_rows(fw_handle h) { return h ? h->L.d_rows + h->L.i_rows : 0; }
@@ -976,6 +1004,7 @@ const char* fw_state_row_name(fw_handle h, int64_t r) {
                                            "flags", "goal_count", "last_attempts", "sim_status", "goal_ring"};
   if (!h || r < 0) return nullptr;
   if (r < D_FIXED) return dn[r];
+  if (h->L.n_par_rows > 0 && r >= h->L.par_row && r < h->L.par_row + h->L.n_par_rows) return "param";
   if (r < h->L.d_rows) return "ring";
   r -= h->L.d_rows;
   if (r < I_GOALRING) return in[r];
@@ -1005,20 +1034,14 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
   FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, h->ctr, h->carry_d, h->carry_i, h->long_list,
-               h->queue, h->long_h};
+               h->queue, h->long_h, h->L.par_row};
   cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
   if (h->profiling) {
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
     CK(cudaEventRecord(pe[0], s));
   }
   CK(cudaMemsetAsync(h->queue, 0, (size_t)h->q_len * sizeof(int32_t), s));
-  if (h->cfg.precision == 0) {
-    CK((h->generic ? launch_dyn<double, FwSpecGeneric>(h->cfg.sim, da, h->attempt_grid, s)
-                   : launch_dyn<double, FwSpecShipped>(h->cfg.sim, da, h->attempt_grid, s)));
-  } else {
-    CK((h->generic ? launch_dyn<float, FwSpecGeneric>(h->cfg.sim, da, h->attempt_grid, s)
-                   : launch_dyn<float, FwSpecShipped>(h->cfg.sim, da, h->attempt_grid, s)));
-  }
+  CK(launch_dyn_any(h->cfg.precision, h->generic, h->cfg.sim, da, h->attempt_grid, s));
   if (h->profiling) CK(cudaEventRecord(pe[1], s));
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
                term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum, h->carry_d,

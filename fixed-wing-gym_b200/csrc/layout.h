@@ -62,6 +62,8 @@ struct FwLayout {
   int32_t sv_slot[FW_MAX_OBS_VARS];   // obs var index -> column in the sv ring (-1 if not a state var)
   // episode metrics (only when fw_env_t.metrics_enabled): accumulator rows + the 50-entry error ring of end_error
   int32_t met, m_drow, m_irow, end_row;
+  // per-env model parameters (simulator-parameter randomisation): n_par_rows rows starting at par_row
+  int32_t par_row, n_par_rows;
 };
 
 // metric accumulators, relative to FwLayout.m_drow (double) / m_irow (int32); k = target index
@@ -126,6 +128,10 @@ constexpr int fw_layout_build(const fw_env_t& E, int scale_actions, int64_t n, F
     L.end_row = row; row += FW_END_WINDOW * E.n_targets;
     L.m_irow = L.i_rows; L.i_rows += MI_GRING + 3 * L.goal_words;
   }
+  if (E.n_rand < 0 || E.n_rand > FW_MAX_RAND || E.n_par_rows < 0 || E.n_par_rows > FW_N_PAR) return 6;
+  L.par_row = row;
+  L.n_par_rows = E.n_par_rows;
+  row += E.n_par_rows;
   L.d_rows = row;
   return 0;
 }
@@ -136,6 +142,7 @@ inline const char* fw_layout_error(int code) {
     case 3: return "bad n_factors";
     case 4: return "success_streak_req > 256 unsupported";
     case 5: return "integrator observation / int_error reward need integration_window > 0";
+    case 6: return "bad simulator-parameter randomisation table";
   }
   return "";
 }

@@ -326,6 +326,39 @@ class FixedWingVecEnv:
     def reset_counters(self):
         _capi.check(self._lib.fw_reset_counters(self._h))
 
+    def get_simulator_parameters(self, normalize=True):
+        """FixedWingAircraft.get_simulator_parameters (fixed_wing.py:872-888) for every env: device tensor
+        [N, n_listed_parameters] of the current (per-episode randomised) model parameters, normalised as the reference
+        does ((value - original) / var).  Parameters the dynamics never read (inertia) report their nominal value:
+        their draw is consumed and discarded on the device."""
+        model = self.cc.cfg["simulator"].get("model", {})
+        plan, slot1, _ = self.cc._rand_slots()
+        st = self.get_state()
+        rows = self.state_rows()
+        first = rows.index("param") if "param" in rows else None
+        cols = []
+        for pa in model.get("parameters", []):
+            name = pa["name"]
+            orig = pa.get("original", None)
+            if orig is None:
+                orig = self.cc.params[name] if name != "ar" else self.cc.params["b"] ** 2 / self.cc.params["S_wing"]
+            pid = self.cc.par_id(name) if name in self.cc.LIVE_PARAMS else -1
+            if pid >= 0 and slot1[pid]:
+                val = st[first + slot1[pid] - 1]
+            else:
+                val = torch.full((self.num_envs,), float(orig), dtype=torch.float64, device=self.device)
+            if normalize:
+                var = pa.get("var", model["var"])
+                if model.get("var_type", "relative") == "relative":
+                    if orig == 0:
+                        continue
+                    var = var * orig
+                val = (val - orig) / var
+            cols.append(val)
+        if not cols:
+            return torch.empty((self.num_envs, 0), dtype=torch.float64, device=self.device)
+        return torch.stack(cols, dim=1)
+
     def kernel_variant(self):
         """Which kernel instantiations the configuration selected, e.g. "dyn=shipped env=default_turb"."""
         return self._lib.fw_kernel_variant(self._h).decode()

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 8
+#define FW_ABI_VERSION 9
 
 /* ---------------------------------------------------------------------------------------------- limits */
 #define FW_MAX_OBS_VARS 32
@@ -34,6 +34,8 @@ extern "C" {
 #define FW_N_ODE 19           /* quat4, omega3, pos3, vel3, actuator value3, actuator dot3 */
 #define FW_N_FILT 6           /* Dryden shaping filters u,v,w,p,q,r */
 #define FW_FILT_MAXN 3
+#define FW_N_PAR 53           /* == FW_PAR_N below (model parameters that can differ per env) */
+#define FW_MAX_RAND 64        /* entries of simulator-parameter randomisation per reset */
 
 /* PyFly state-variable ids (order of oracle/pyfly_restated.py REQUIRED_VARIABLES + elevons) */
 enum fw_sv {
@@ -41,6 +43,26 @@ enum fw_sv {
   FW_SV_POS_N, FW_SV_POS_E, FW_SV_POS_D, FW_SV_VEL_U, FW_SV_VEL_V, FW_SV_VEL_W,
   FW_SV_VA, FW_SV_ALPHA, FW_SV_BETA, FW_SV_ELEVATOR, FW_SV_AILERON, FW_SV_RUDDER, FW_SV_THROTTLE,
   FW_SV_ELEVON_L, FW_SV_ELEVON_R
+};
+
+/* Model parameters the right-hand side reads LIVE at every evaluation (PyFly.params[...] / PyFly.rho / PyFly.g), i.e.
+ * the ones whose per-episode randomisation (fixed_wing.py:523-570) changes the dynamics.  The inertia entries are not
+ * here: PyFly folds them into gammas at construction, so randomising them consumes a draw and changes nothing.  The
+ * last three are derived per env at reset (1/mass, 1/(pi e AR), exp(2 M a_0)). */
+enum fw_par {
+  FW_PAR_MASS = 0, FW_PAR_S_WING, FW_PAR_B, FW_PAR_C, FW_PAR_S_PROP, FW_PAR_K_MOTOR, FW_PAR_K_T_P, FW_PAR_K_OMEGA,
+  FW_PAR_C_PROP, FW_PAR_E, FW_PAR_M, FW_PAR_A_0, FW_PAR_AR,
+  FW_PAR_C_L_0, FW_PAR_C_L_ALPHA, FW_PAR_C_L_Q, FW_PAR_C_L_DELTA_E,
+  FW_PAR_C_D_P, FW_PAR_C_D_0, FW_PAR_C_D_ALPHA1, FW_PAR_C_D_ALPHA2, FW_PAR_C_D_BETA1, FW_PAR_C_D_BETA2, FW_PAR_C_D_Q,
+  FW_PAR_C_D_DELTA_E,
+  FW_PAR_C_M_0, FW_PAR_C_M_ALPHA, FW_PAR_C_M_Q, FW_PAR_C_M_DELTA_E, FW_PAR_C_M_FP,
+  FW_PAR_C_Y_0, FW_PAR_C_Y_BETA, FW_PAR_C_Y_P, FW_PAR_C_Y_R, FW_PAR_C_Y_DELTA_A, FW_PAR_C_Y_DELTA_R,
+  FW_PAR_C_L_ROLL_0, FW_PAR_C_L_ROLL_BETA, FW_PAR_C_L_ROLL_P, FW_PAR_C_L_ROLL_R, FW_PAR_C_L_ROLL_DELTA_A,
+  FW_PAR_C_L_ROLL_DELTA_R,
+  FW_PAR_C_N_0, FW_PAR_C_N_BETA, FW_PAR_C_N_P, FW_PAR_C_N_R, FW_PAR_C_N_DELTA_A, FW_PAR_C_N_DELTA_R,
+  FW_PAR_RHO, FW_PAR_G,
+  FW_PAR_INV_MASS, FW_PAR_INV_PI_E_AR, FW_PAR_EXP_2MA0,
+  FW_PAR_N
 };
 
 enum fw_status {
@@ -135,7 +157,22 @@ typedef struct {
   int32_t scale_actions, has_scale_low, has_scale_high, _pad2;
   double scale_low, scale_high;
   double act_to_low[FW_N_ACT], act_to_high[FW_N_ACT];
+  /* per-env model parameters (simulator-parameter randomisation): par_slot1[id] = 1 + row (relative to the handle's
+   * parameter rows) holding that parameter for every env, 0 = the same for all envs (the value above) */
+  int32_t par_slot1[FW_N_PAR];
 } fw_sim_t;
+
+/* One draw of FixedWingAircraft.sample_simulator_parameters (fixed_wing.py:523-570), in the reference's order.
+ * dist 0: gaussian  v = normal(orig, var), then np.clip(v, orig - clip, orig + clip) when has_clip
+ * dist 1: uniform   v = uniform(orig - var, orig + var)
+ * dist 2: uniform   v = uniform(orig, var)                     (simulator attributes given as low / high)
+ * var / clip are absolute (the host applies var_type "relative": var * |orig|, clip * orig - signed, as the reference).
+ * slot1: 1 + parameter row that receives v, 0 = drawn and discarded (a parameter the dynamics never read). */
+typedef struct {
+  int32_t par;         /* fw_par id, -1 when slot1 == 0 */
+  int32_t dist, has_clip, slot1;
+  double orig, var, clip;
+} fw_rand_t;
 
 /* env half: what FixedWingAircraft holds (passed to the env/reset kernels) */
 typedef struct {
@@ -156,6 +193,9 @@ typedef struct {
   /* episode metrics (FixedWingAircraft.get_metric, fixed_wing.py:1095-1162), streamed on the device when enabled */
   int32_t metrics_enabled, _pad4;
   double rise_low, rise_high;     /* rise_time thresholds (fractions of the initial error; config "metrics") */
+  /* simulator-parameter randomisation at every reset */
+  int32_t n_rand, n_par_rows;     /* draws per reset; per-env parameter rows (randomised + derived) */
+  fw_rand_t rand[FW_MAX_RAND];
 } fw_env_t;
 
 typedef struct {

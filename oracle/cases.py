@@ -48,4 +48,10 @@ CASES = {
                          "wind_magnitude_max": 6}, n=4, steps=30, amp=1.0),
     "poly_drag": dict(config="fixed_wing_config_constraints.json", config_kw=None,
                       sim_kw={"turbulence": False, "drag_model": "polynomial"}, n=6, steps=40, amp=1.2),
+    # per-episode simulator-parameter randomisation (gaussian with clips; several resets)
+    "param_rand": dict(config="fixed_wing_config_randomised.json", config_kw={"steps_max": 18},
+                       sim_kw={"turbulence": False}, n=6, steps=60, amp=1.0),
+    "param_rand_uniform": dict(config="fixed_wing_config_randomised.json",
+                               config_kw={"steps_max": 25, "simulator": {"model": {"distribution": "uniform"}}},
+                               sim_kw={"turbulence": True, "turbulence_intensity": "light"}, n=4, steps=40, amp=1.0),
 }

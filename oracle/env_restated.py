@@ -344,9 +344,49 @@ class RestatedEnv:
         return total
 
     # ------------------------------------------------------------------------------------------- reset and step
+    def sample_simulator_parameters(self):
+        """fixed_wing.py:523-570: per-episode randomisation of PyFly's model parameters and attributes."""
+        for key, value in self.cfg["simulator"].items():
+            if key == "states":
+                continue
+            elif key == "model":
+                dist_type = value.get("distribution", "gaussian")
+                for pa in value["parameters"]:
+                    orig = pa.get("original", None)
+                    if orig is None:
+                        orig = self.simulator.params[pa["name"]]
+                        pa["original"] = orig
+                    if orig == 0:
+                        continue
+                    var = pa.get("var", value["var"])
+                    if value["var_type"] == "relative":
+                        var *= np.abs(orig)
+                    if dist_type == "gaussian":
+                        val = self.np_random.normal(loc=orig, scale=var)
+                        clip = pa.get("clip", value.get("clip", None))
+                        if clip is not None:
+                            if value["var_type"] == "relative":
+                                clip *= orig
+                            val = np.clip(val, orig - clip, orig + clip)
+                    elif dist_type == "uniform":
+                        val = self.np_random.uniform(low=orig - var, high=orig + var)
+                    else:
+                        raise ValueError("Unexpected distribution type {}".format(dist_type))
+                    self.simulator.params[pa["name"]] = val
+            else:
+                if "values" in value:
+                    probs = value.get("probabilities", None)
+                    val = self.np_random.choice(value["values"], p=None if probs is None else np.array(probs))
+                else:
+                    val = self.np_random.uniform(value["low"], value["high"])
+                    if isinstance(value["low"], bool):
+                        val = bool(val)
+                setattr(self.simulator, key, val)
+
     def reset(self, state=None, target=None, **sim_reset_kw):
         self.steps_count = 0
         self.simulator.reset(state, **sim_reset_kw)
+        self.sample_simulator_parameters()
         self.sample_target()
         if target is not None:
             for k, v in target.items():

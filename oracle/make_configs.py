@@ -23,6 +23,29 @@ SOURCES = {
 }
 
 
+# simulator-parameter randomisation (fixed_wing.py:523-570): no shipped configuration carries a "model" block and
+# config_kw cannot add one (set_config_attrs only descends into existing keys), so the parity case has its own file:
+# the default configuration + a model block exercising every branch (per-parameter var / clip, a negative original
+# with a relative clip, an inertia entry the dynamics never read, a zero original that is skipped) + a simulator
+# attribute range.
+RANDOMISED_SIMULATOR = {
+    "model": {"var_type": "relative", "var": 0.1, "clip": 0.25, "distribution": "gaussian",
+              "parameters": [{"name": "mass"}, {"name": "C_L_alpha", "var": 0.2}, {"name": "C_m_q"},
+                             {"name": "Jx"}, {"name": "C_D_q"}, {"name": "M", "var": 0.05, "clip": 0.1},
+                             {"name": "e"}, {"name": "C_l_p", "clip": 0.05}, {"name": "k_motor"}, {"name": "b"}]},
+    "rho": {"low": 1.1, "high": 1.3},
+}
+
+
+def write_randomised():
+    with open(os.path.join(PARAMS, "fixed_wing_config.json")) as f:
+        cfg = json.load(f)
+    cfg["simulator"].update(RANDOMISED_SIMULATOR)
+    with open(os.path.join(PARAMS, "fixed_wing_config_randomised.json"), "w") as f:
+        json.dump(cfg, f, sort_keys=True, separators=(",", ":"))
+        f.write("\n")
+
+
 def main():
     for out, src in SOURCES.items():
         with open(os.path.join(REF, src)) as f:
@@ -31,6 +54,7 @@ def main():
         with open(os.path.join(PARAMS, out), "w") as f:
             json.dump(cfg, f, sort_keys=True, separators=(",", ":"))
             f.write("\n")
+    write_randomised()
     ex = os.path.join(REF, "gym_fixed_wing", "examples")
     scen = np.load(os.path.join(ex, "test_sets", "test_set_wind_none_step20-20-3.npy"), allow_pickle=True)
     skeys = sorted(scen[0]["state"].keys())

@@ -32,3 +32,15 @@ for depth in [int(x) for x in sys.argv[1:]] or [1, 2, 3, 4]:
     hs.wait(s)
     print("depth %d: %.4g env-steps/s, %.1f us/step; submit() host time %.1f us" % (depth, n * 100 / dt, dt / 100 * 1e6, (t2 - t1) * 1e6))
     hs.close()
+# device-resident loop without L2 flush (what a policy living on the GPU sees): 100 back-to-back steps
+dacts = acts.cuda()
+for _ in range(8):
+    vec.step_tensors(dacts[0])
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+e0.record()
+for i in range(100):
+    vec.step_tensors(dacts[i % 64])
+e1.record()
+torch.cuda.synchronize()
+print("device loop, no flush: %.1f us/step (%s, overlap env %s)" % (e0.elapsed_time(e1) * 10, vec.kernel_variant(), os.environ.get("FWGYM_OVERLAP", "1")))

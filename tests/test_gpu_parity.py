@@ -74,7 +74,8 @@ def test_kernel_variant_selection(built_lib):
     generated from; numbers (noise level, constraint values, curriculum level) do not change the choice."""
     want = {"default": "dyn=shipped env=default", "turb_noise": "dyn=shipped env=default_turb",
             "examples": "dyn=shipped env=examples_turb", "failure": "dyn=shipped env=default",
-            "dev_history": "generic", "success_new": "generic", "wind": "dyn=generic env=generic"}
+            "dev_history": "generic", "success_new": "generic", "wind": "dyn=generic env=generic",
+            "param_rand": "dyn=rand env=generic"}
     for name, v in want.items():
         vec = make_vec(CASES[name])
         assert vec.kernel_variant().endswith(v), (name, vec.kernel_variant())
@@ -189,6 +190,43 @@ def test_host_buffer_pipeline_matches_device_step(built_lib):
             assert np.array_equal(x.reshape(y.shape), y, equal_nan=True)
     hs.close()
     vec.close()
+
+
+def test_simulator_parameters_are_randomised_per_episode(built_lib):
+    """SURVEY §8f row 4 (fixed_wing.py:523-570, :872-888): every env draws its own model parameters at every reset;
+    the clipped gaussian keeps them inside the configured window, parameters change across episodes, and the derived
+    rows (1/mass ...) follow.  The step-level numbers are pinned by the param_rand golden fixtures."""
+    c = CASES["param_rand"]
+    vec = make_vec(c, n=512, seed=3)
+    vec.reset()
+    p0 = vec.get_simulator_parameters(normalize=False).cpu().numpy()
+    names = [pa["name"] for pa in vec.cc.cfg["simulator"]["model"]["parameters"]]
+    mass, clalpha = p0[:, names.index("mass")], p0[:, names.index("C_L_alpha")]
+    assert mass.std() > 0.05 and abs(mass.mean() - 3.364) < 0.1
+    assert mass.min() >= 3.364 * 0.75 - 1e-12 and mass.max() <= 3.364 * 1.25 + 1e-12          # clip 0.25 relative
+    assert clalpha.std() > 1.5 * mass.std()                                                    # var 0.2 vs 0.1
+    # negative original with a relative clip: np.clip(v, orig - clip*orig, orig + clip*orig) has min > max -> constant
+    cmq = p0[:, names.index("C_m_q")]
+    assert np.allclose(cmq, -1.3047 * 1.25, rtol=0, atol=1e-12)
+    assert np.all(p0[:, names.index("Jx")] == 1.229)                                           # never reaches the dynamics
+    st, rows = vec.get_state().cpu().numpy(), vec.state_rows()
+    prm = st[rows.index("param"):rows.index("param") + rows.count("param")]
+    _, slot1, _ = vec.cc._rand_slots()
+    inv_mass = prm[slot1[vec.cc.par_id("mass")] - 1] * prm[slot1[_enum("FW_PAR_INV_MASS")] - 1]
+    assert np.allclose(inv_mass, 1.0, atol=1e-15)
+    acts = torch.zeros((vec.num_envs, 3), dtype=torch.float64, device=vec.device)
+    for _ in range(c["config_kw"]["steps_max"]):
+        vec.step_tensors(acts)                      # every env ends its episode (steps_max) and is reset
+    p1 = vec.get_simulator_parameters(normalize=False).cpu().numpy()
+    assert (p1[:, names.index("mass")] != mass).mean() > 0.99
+    pn = vec.get_simulator_parameters(normalize=True).cpu().numpy()
+    assert pn.shape[1] == len(names) - 1            # C_D_q has a zero original: skipped, as in the reference
+    vec.close()
+
+
+def _enum(name):
+    from fwgym_b200 import _capi
+    return _capi.ENUMS[name]
 
 
 def test_sharding_invariance(built_lib):
