@@ -233,7 +233,7 @@ def run_gpu_arm(a):
     # are on the host.
     from fwgym_b200 import HostStepper
     stepper = HostStepper(vec, depth=2)
-    host_actions = (torch.rand((a.steps + 4, n, 3)) * 2 - 1).pin_memory()
+    host_actions = (torch.rand((a.steps + a.warmup, n, 3)) * 2 - 1).pin_memory()
     e2e_steps = a.steps
     checksum = 0.0
 
@@ -249,10 +249,14 @@ def run_gpu_arm(a):
             obs, rew, done = stepper.wait(pending.pop(0))
             checksum += float(rew[0])
 
-    e2e_run(0, 4)
+    # same position in the episodes as the device-timed region above: fresh reset, W warm-up steps, then K timed steps
+    # (the dopri5 work per step drifts as the aircraft of a batch age, so a region further into the episodes would not
+    # be comparable)
+    vec.reset()
+    e2e_run(0, a.warmup)
     barrier()
     t0 = time.perf_counter()
-    e2e_run(4, e2e_steps)
+    e2e_run(a.warmup, e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
 
