@@ -46,7 +46,7 @@ def _cpu_worker(args):
     """One host core: step one oracle env (restated reference path) with U(-1,1) actions for `n_steps` steps."""
     wid, n_steps, warm = args
     import numpy as np
-    from oracle import harness
+    from oracle import harness      # the cpu_baseline / reference arm is the one place bench.py may run the oracle
     env = harness.make_env("restated", harness.config_path(), CONFIG_KW, SIM_KW)
     run = harness.OracleRunner(env, seed=1234, env_id=wid)
     run.reset()
@@ -175,10 +175,10 @@ def run_gpu_arm(a):
     if world > 1:
         dist.barrier()
     from fwgym_b200 import FixedWingVecEnv, _capi
-    from oracle import harness   # only for the config path helper + cpu_baseline leg
+    from fwgym_b200.config import DEFAULT_ENV_CONFIG
 
     n = a.envs_per_gpu
-    vec = FixedWingVecEnv(harness.config_path(), n, device=dev, config_kw=CONFIG_KW, sim_config_kw=SIM_KW,
+    vec = FixedWingVecEnv(DEFAULT_ENV_CONFIG, n, device=dev, config_kw=CONFIG_KW, sim_config_kw=SIM_KW,
                           seed=20261017, env_offset=rank * n)
     vec.reset()
     gen = torch.Generator(device=dev)

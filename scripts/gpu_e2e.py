@@ -4,9 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from fwgym_b200 import FixedWingVecEnv, HostStepper
-from oracle import harness
+from fwgym_b200.config import DEFAULT_ENV_CONFIG
 n = 65536
-vec = FixedWingVecEnv(harness.config_path(), n, config_kw=bench.CONFIG_KW, sim_config_kw=bench.SIM_KW, seed=1)
+vec = FixedWingVecEnv(DEFAULT_ENV_CONFIG, n, config_kw=bench.CONFIG_KW, sim_config_kw=bench.SIM_KW, seed=1)
 vec.reset()
 acts = (torch.rand((64, n, 3)) * 2 - 1).pin_memory()
 for depth in [int(x) for x in sys.argv[1:]] or [1, 2, 3, 4]:

@@ -4,9 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from fwgym_b200 import FixedWingVecEnv, HostStepper
-from oracle import harness
+from fwgym_b200.config import DEFAULT_ENV_CONFIG
 n = 65536
-vec = FixedWingVecEnv(harness.config_path(), n, config_kw=bench.CONFIG_KW, sim_config_kw=bench.SIM_KW, seed=20261017)
+vec = FixedWingVecEnv(DEFAULT_ENV_CONFIG, n, config_kw=bench.CONFIG_KW, sim_config_kw=bench.SIM_KW, seed=20261017)
 acts = (torch.rand((64, n, 3)) * 2 - 1).pin_memory()
 dacts = acts.cuda()
 def e2e(depth, count=30, warm=5):

@@ -5,7 +5,7 @@ import torch
 import __graft_entry__ as ge
 ge.build()
 from fwgym_b200 import FixedWingVecEnv
-from oracle import harness
+from fwgym_b200.config import DEFAULT_ENV_CONFIG
 N = 65536
 variants = {
     "turb+noise": ({"observation": {"noise": {"mean": 0, "var": 0.1}}}, {"turbulence": True, "turbulence_intensity": "moderate"}),
@@ -14,7 +14,7 @@ variants = {
     "neither": (None, {"turbulence": False}),
 }
 for name, (ck, sk) in variants.items():
-    vec = FixedWingVecEnv(harness.config_path(), N, config_kw=ck, sim_config_kw=sk, seed=3)
+    vec = FixedWingVecEnv(DEFAULT_ENV_CONFIG, N, config_kw=ck, sim_config_kw=sk, seed=3)
     vec.reset()
     acts = torch.rand((40, N, 3), device="cuda") * 2 - 1
     for i in range(5):

@@ -1,5 +1,6 @@
+import os
 import sys, time, numpy as np, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+_R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, "tests"))
 import fwgym_b200
 from fwgym_b200 import FixedWingVecEnv
 from oracle import harness
