@@ -23,17 +23,18 @@ class RunningMeanStd:
     def __init__(self, shape, device):
         self.mean = torch.zeros(shape, dtype=torch.float64, device=device)
         self.var = torch.ones(shape, dtype=torch.float64, device=device)
-        self.count = 1e-4
+        self.count = torch.full((), 1e-4, dtype=torch.float64, device=device)   # a tensor: no host state, capturable
 
     def update(self, x):
+        """In place (static storage), so the same update can sit in a CUDA graph."""
         x = x.to(torch.float64)
-        bm, bv, bc = x.mean(0), x.var(0, unbiased=False), x.shape[0]
+        bm, bv, bc = x.mean(0), x.var(0, unbiased=False), float(x.shape[0])
         delta = bm - self.mean
         tot = self.count + bc
-        self.mean = self.mean + delta * bc / tot
         m2 = self.var * self.count + bv * bc + delta * delta * self.count * bc / tot
-        self.var = m2 / tot
-        self.count = tot
+        self.mean.add_(delta * bc / tot)
+        self.var.copy_(m2 / tot)
+        self.count.copy_(tot)
 
 
 class DeviceVecNormalize:
@@ -60,13 +61,13 @@ class DeviceVecNormalize:
 
     def step(self, actions):
         obs, rew, done, term = self.venv.step_tensors(actions)
-        self.ret = self.ret * self.gamma + rew.to(torch.float64)
+        self.ret.mul_(self.gamma).add_(rew.to(torch.float64))
         if self.training:
             self.ret_rms.update(self.ret)
         r = torch.clamp(rew.to(torch.float64) / torch.sqrt(self.ret_rms.var + self.eps), -self.clip_reward,
                         self.clip_reward).to(torch.float32)
         d = done.bool()
-        self.ret = torch.where(d, torch.zeros_like(self.ret), self.ret)
+        self.ret.masked_fill_(d, 0.0)
         return self._obs(obs), r, d, rew
 
 
@@ -86,7 +87,14 @@ class ActorCritic(nn.Module):
                     nn.init.zeros_(m.bias)
 
     def dist(self, obs):
-        return torch.distributions.Normal(self.pi(obs), self.log_std.exp())
+        return torch.distributions.Normal(self.pi(obs), self.log_std.exp(), validate_args=False)   # no host sync
+
+    def sample(self, obs):
+        """-> (action, log-probability).  mu + std * randn instead of Normal.sample(): torch.normal(tensor, tensor)
+        checks std >= 0 on the HOST (a device synchronisation, illegal while a CUDA graph is being captured)."""
+        mu, std = self.pi(obs), self.log_std.exp()
+        act = mu + std * torch.randn_like(mu)
+        return act, torch.distributions.Normal(mu, std, validate_args=False).log_prob(act).sum(-1)
 
     def value(self, obs):
         return self.vf(obs).squeeze(-1)
@@ -102,56 +110,80 @@ def _allreduce_grads(model):
 
 
 def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.5e-4, gamma=0.99, lam=0.95,
-          clip_range=0.2, ent_coef=0.01, vf_coef=0.5, max_grad_norm=0.5, seed=0, model=None, log=None):
+          clip_range=0.2, ent_coef=0.01, vf_coef=0.5, max_grad_norm=0.5, seed=0, model=None, log=None, cuda_graph=True):
     """PPO2-default training on a FixedWingVecEnv.  Returns (model, normalizer, stats); stats has env-steps/s inside
-    training and the env / policy / update split of the wall time (CUDA-event timed)."""
+    training and the split of the device time (CUDA events): eager mode env / policy_forward / ppo_update, graph mode
+    rollout / ppo_update (the rollout is one graph launch, so it has no inner split).
+    cuda_graph: capture the rollout + GAE of an iteration once (at the second iteration; the first runs eagerly and
+    warms every allocation up) and replay it afterwards."""
     dev = venv.device
     torch.manual_seed(seed)
     norm = DeviceVecNormalize(venv, gamma=gamma)
     n, od = venv.num_envs, venv.obs_dim
     model = model or ActorCritic(od, 3).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-5)
-    obs = norm.reset()
+    obs = norm.reset().clone()          # static: the rollout reads and overwrites it in place
     B = n_steps * n
     buf = dict(obs=torch.zeros((n_steps, n, od), device=dev), act=torch.zeros((n_steps, n, 3), device=dev),
                logp=torch.zeros((n_steps, n), device=dev), val=torch.zeros((n_steps, n), device=dev),
                rew=torch.zeros((n_steps, n), device=dev), done=torch.zeros((n_steps, n), device=dev))
+    adv = torch.zeros((n_steps, n), device=dev)
+    ret = torch.zeros((n_steps, n), device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    t_env = t_pol = t_upd = 0.0
-    iters = max(1, int(total_env_steps) // B)
-    stats = {"iterations": iters, "batch": B, "history": []}
-    torch.cuda.synchronize(dev)
-    wall0 = time.perf_counter()
-    for it in range(iters):
-        e = [ev() for _ in range(4)]
-        env_ms = pol_ms = 0.0
-        marks = []
-        for t in range(n_steps):
-            a0, a1, a2 = ev(), ev(), ev()
-            a0.record()
-            with torch.no_grad():
-                d = model.dist(obs)
-                act = d.sample()
-                buf["obs"][t], buf["act"][t] = obs, act
-                buf["logp"][t] = d.log_prob(act).sum(-1)
-                buf["val"][t] = model.value(obs)
-            a1.record()
-            obs, rew, done, raw = norm.step(act)
-            a2.record()
-            buf["rew"][t], buf["done"][t] = rew, done.float()
-            marks.append((a0, a1, a2))
-        e[0].record()
+
+    def rollout(marks=None):
+        """n_steps x (policy forward, sample, env step, normalise) + GAE into the static buffers."""
         with torch.no_grad():
+            for t in range(n_steps):
+                if marks is not None:
+                    a0, a1, a2 = ev(), ev(), ev()
+                    a0.record()
+                act, logp = model.sample(obs)
+                buf["obs"][t].copy_(obs)
+                buf["act"][t].copy_(act)
+                buf["logp"][t].copy_(logp)
+                buf["val"][t].copy_(model.value(obs))
+                if marks is not None:
+                    a1.record()
+                o, rew, done, _ = norm.step(act)
+                obs.copy_(o)
+                buf["rew"][t].copy_(rew)
+                buf["done"][t].copy_(done.float())
+                if marks is not None:
+                    a2.record()
+                    marks.append((a0, a1, a2))
             last_val = model.value(obs)
-            adv = torch.zeros_like(buf["rew"])
             gae = torch.zeros(n, device=dev)
             for t in reversed(range(n_steps)):
                 nv = last_val if t == n_steps - 1 else buf["val"][t + 1]
                 nonterm = 1.0 - buf["done"][t]
                 delta = buf["rew"][t] + gamma * nv * nonterm - buf["val"][t]
                 gae = delta + gamma * lam * nonterm * gae
-                adv[t] = gae
-            ret = adv + buf["val"]
+                adv[t].copy_(gae)
+            torch.add(adv, buf["val"], out=ret)
+
+    t_env = t_pol = t_upd = t_roll = 0.0
+    iters = max(1, int(total_env_steps) // B)
+    stats = {"iterations": iters, "batch": B, "history": [], "cuda_graph": bool(cuda_graph)}
+    graph = None
+    torch.cuda.synchronize(dev)
+    wall0 = time.perf_counter()
+    for it in range(iters):
+        e = [ev() for _ in range(3)]
+        marks = []
+        e[0].record()
+        if not cuda_graph:
+            rollout(marks)
+        elif it == 0:
+            rollout()                                   # eager: warms up allocations, cuBLAS handles, the env
+        else:
+            if graph is None:
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):           # capture only; nothing runs here
+                    rollout()
+            graph.replay()
+        e[1].record()
         flat = {k: v.reshape((B,) + v.shape[2:]) for k, v in buf.items()}
         f_adv, f_ret = adv.reshape(B), ret.reshape(B)
         mb = B // n_minibatches
@@ -169,26 +201,31 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
                 vclip = flat["val"][idx] + torch.clamp(v - flat["val"][idx], -clip_range, clip_range)
                 vl = 0.5 * torch.max((v - f_ret[idx]) ** 2, (vclip - f_ret[idx]) ** 2).mean()
                 loss = pg - ent_coef * d.entropy().sum(-1).mean() + vf_coef * vl
-                opt.zero_grad(set_to_none=True)
+                opt.zero_grad(set_to_none=False)        # gradients keep their storage
                 loss.backward()
                 _allreduce_grads(model)
                 nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
                 opt.step()
-        e[1].record()
+        e[2].record()
         torch.cuda.synchronize(dev)
+        roll_ms, upd_ms = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
         pol_ms = sum(a0.elapsed_time(a1) for a0, a1, _ in marks)
         env_ms = sum(a1.elapsed_time(a2) for _, a1, a2 in marks)
-        upd_ms = e[0].elapsed_time(e[1])
-        t_env, t_pol, t_upd = t_env + env_ms, t_pol + pol_ms, t_upd + upd_ms
+        t_env, t_pol, t_upd, t_roll = t_env + env_ms, t_pol + pol_ms, t_upd + upd_ms, t_roll + roll_ms
         rec = {"iter": it, "loss": float(loss.detach()), "mean_norm_reward": float(buf["rew"].mean()),
-               "value_loss": float(vl.detach()), "env_ms": env_ms, "policy_ms": pol_ms, "update_ms": upd_ms}
+               "value_loss": float(vl.detach()), "rollout_ms": roll_ms, "env_ms": env_ms, "policy_ms": pol_ms,
+               "update_ms": upd_ms}
         stats["history"].append(rec)
         if log:
             log(rec)
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - wall0
-    tot = t_env + t_pol + t_upd
-    stats.update(env_steps=iters * B, wall_s=wall, env_steps_per_s=iters * B / wall,
-                 time_fraction={"env": t_env / tot, "policy_forward": t_pol / tot, "ppo_update": t_upd / tot},
+    if cuda_graph:
+        tot = t_roll + t_upd
+        frac = {"rollout": t_roll / tot, "ppo_update": t_upd / tot}
+    else:
+        tot = t_env + t_pol + t_upd
+        frac = {"env": t_env / tot, "policy_forward": t_pol / tot, "ppo_update": t_upd / tot}
+    stats.update(env_steps=iters * B, wall_s=wall, env_steps_per_s=iters * B / wall, time_fraction=frac,
                  episode_metrics=venv.metric_sums().tolist())
     return model, norm, stats

@@ -78,18 +78,21 @@ def test_vecenv_surface(built_lib):
     assert v.get_attr("steps_count")[0] == 0
 
 
-def test_ppo_loop_runs(built_lib):
+@pytest.mark.parametrize("graph", [False, True])
+def test_ppo_loop_runs(built_lib, graph):
     """SURVEY §8f row 3 (BASELINE configs[3] at a small size): PPO2-default loop with the device VecNormalize and a
-    torch MLP policy steps the batched env, updates without NaNs and reports the env / policy / update split."""
+    torch MLP policy steps the batched env, updates without NaNs and reports the time split - eagerly and with the
+    rollout (policy + env kernels incl. the programmatic dependent launch + GAE) captured into a CUDA graph."""
     from fwgym_b200 import FixedWingVecEnv, ppo
     env = FixedWingVecEnv(harness.config_path("fixed_wing_config_examples.json"), 2048, seed=4)
     env.env_method("set_curriculum_level", 0.25)
-    model, norm, stats = ppo.train(env, total_env_steps=2048 * 32 * 2, n_steps=32)
-    assert stats["iterations"] == 2 and stats["env_steps"] == 2048 * 32 * 2
+    model, norm, stats = ppo.train(env, total_env_steps=2048 * 32 * 3, n_steps=32, cuda_graph=graph)
+    assert stats["iterations"] == 3 and stats["env_steps"] == 2048 * 32 * 3
+    assert env.counters()["env_steps"] == 2048 * 32 * 3 and env.counters()["watchdog"] == 0
     assert all(np.isfinite(h["loss"]) for h in stats["history"])
     assert abs(sum(stats["time_fraction"].values()) - 1.0) < 1e-9
     assert all(torch.isfinite(p).all() for p in model.parameters())
     assert float(norm.obs_rms.count) > 2048 * 32
-    print("PPO smoke: %.3g env-steps/s inside training; time split %s"
-          % (stats["env_steps_per_s"], {k: round(v, 3) for k, v in stats["time_fraction"].items()}))
+    print("PPO smoke (cuda_graph=%s): %.3g env-steps/s inside training; time split %s"
+          % (graph, stats["env_steps_per_s"], {k: round(v, 3) for k, v in stats["time_fraction"].items()}))
     env.close()
