@@ -134,15 +134,29 @@ struct FwSpecRand {
   X(RHO, rho) X(G, g) X(INV_MASS, inv_mass) X(INV_PI_E_AR, inv_pi_e_ar) X(EXP_2MA0, exp_2Ma0)
 static_assert(FW_PAR_N == FW_N_PAR, "FW_N_PAR in fwgym.h must equal the number of fw_par ids");
 
-template <typename T, bool RAND> struct FwPar {
+// Three sources, chosen per kernel:
+//   FW_PAR_CONST  the shared value: a constant-bank operand (every instantiation but FwSpecRand);
+//   FW_PAR_GLOBAL the per-env row in HBM for randomised parameters (init kernel: two evaluations per aircraft);
+//   FW_PAR_SMEM   the attempt kernel reads every parameter 6 times per pass inside a latency-bound dependency chain, so
+//                 it copies the adopted aircraft's parameter rows to shared memory ([row][lane]) at adoption and reads
+//                 them branch-free: 50 warp-uniform branches per RHS would cut it into basic blocks that cannot
+//                 overlap; an unconditional shared-memory read + select keeps it one block.
+enum { FW_PAR_CONST = 0, FW_PAR_GLOBAL = 1, FW_PAR_SMEM = 2 };
+template <typename T, int MODE> struct FwPar {
   const fw_sim_t& P;
-  const double* base;   // RAND: this aircraft's element of parameter row 0
+  const double* base;   // GLOBAL: this aircraft's element of parameter row 0
   int64_t stride;
+  const T* cache;       // SMEM: this lane's element of cached row 0 (32 lanes per row)
 #define FW_PAR_GETTER(ID, F)                                                      \
   __device__ __forceinline__ T F() const {                                        \
-    if constexpr (RAND) {                                                         \
+    if constexpr (MODE == FW_PAR_GLOBAL) {                                        \
       const int s1 = P.par_slot1[FW_PAR_##ID];                                    \
       if (s1) return (T)base[(int64_t)(s1 - 1) * stride];                         \
+    }                                                                             \
+    if constexpr (MODE == FW_PAR_SMEM) {                                          \
+      const int s1 = P.par_slot1[FW_PAR_##ID];                                    \
+      const T v = cache[(s1 > 0 ? s1 - 1 : 0) * 32];                              \
+      return s1 > 0 ? v : (T)P.F;                                                 \
     }                                                                             \
     return (T)P.F;                                                                \
   }
@@ -174,8 +188,8 @@ __device__ __forceinline__ T fw_cond_r(const fw_var_t& v, T x, uint32_t& failmas
 // conditioned after a step, but NOT after a reset (Variable.reset draws init values without clipping or checking), so
 // the first right-hand side of an episode must not clip / check the state variables.  Va, alpha, beta (and the
 // elevator / aileron mapping) are conditioned in _forces at every evaluation.
-template <typename T, class Spec, bool RAW = false>
-__device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const FwPar<T, Spec::rand>& PP, const FwStepIn<T>& in,
+template <typename T, class Spec, bool RAW = false, class PAR>
+__device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const PAR& PP, const FwStepIn<T>& in,
                                        const T (&y)[FW_N_ODE], T (&dy)[FW_N_ODE], uint32_t& failmask) {
   typedef FwMath<T> Mt;
   const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
@@ -375,8 +389,8 @@ __device__ __forceinline__ int fw_fail_code(uint32_t failmask) {
 // Two right-hand-side evaluations.  Returns the failure code (0 = ok); on success f0 holds f(t0, y0) and h_abs the
 // initial step size (clamped to the interval; the min_step clamp of the first _step_impl call is applied by
 // fw_ivp_attempt like for every other entry).
-template <typename T, class Spec>
-__device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const FwPar<T, Spec::rand>& PP, const FwStepIn<T>& in,
+template <typename T, class Spec, class PAR>
+__device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const PAR& PP, const FwStepIn<T>& in,
                                            const T (&y)[FW_N_ODE], T (&f0)[FW_N_ODE], T& h_abs) {
   typedef FwMath<T> Mt;
   const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
@@ -426,8 +440,8 @@ __device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const FwPar<T, Spe
 // lane whose S.status is RUNNING; six right-hand-side evaluations through one call site.  Updates S (and K slot 0 on
 // acceptance); sets S.status to FINISHED when t reaches t_bound or an RHS evaluation raises, TOO_SMALL when the step
 // size underflows.
-template <typename T, class Spec, int BLOCK>
-__device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const FwPar<T, Spec::rand>& PP,
+template <typename T, class Spec, int BLOCK, class PAR>
+__device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
                                                const FwStepIn<T>& in, FwIvp<T>& S, FwKStore<T, BLOCK> K) {
   typedef FwMath<T> Mt;
   const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;

@@ -112,6 +112,7 @@ struct FwDynArgs {
   int32_t* q;          // [Q_N + chunks] queue counters + per-chunk finished counters, zeroed at the start of every step
   double long_h;       // initial step sizes below this go on the priority list
   int32_t par_row;     // first per-env model-parameter row of d (FwSpecRand)
+  int32_t n_par_rows;
 };
 
 // ---- action -> actuator commands (fixed_wing.py:349-354,439-459; Actuation.set_and_constrain_commands) ----
@@ -174,7 +175,8 @@ fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
     T y[FW_N_ODE], f0[FW_N_ODE], h_abs = 0;
 #pragma unroll
     for (int j = 0; j < FW_N_ODE; ++j) y[j] = (T)c.D(j);
-    const FwPar<T, Spec::rand> PP{P, a.d + (int64_t)a.par_row * a.stride + env, a.stride};
+    const FwPar<T, Spec::rand ? FW_PAR_GLOBAL : FW_PAR_CONST> PP{P, a.d + (int64_t)a.par_row * a.stride + env, a.stride,
+                                                                   nullptr};
     const int failv = fw_ivp_init<T, Spec>(P, PP, in, y, f0, h_abs);
     double* cd = a.cd + env;
     int32_t* ci = a.ci + env;
@@ -221,6 +223,8 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   FwStepIn<T> in;
   int64_t env = -1;
   const double* par_base = a.d;   // FwSpecRand: the adopted aircraft's element of parameter row 0
+  // FwSpecRand: parameter cache behind the K stages, [n_par_rows][32]
+  T* par_cache = reinterpret_cast<T*>(smem_raw) + 6 * FW_N_KC * FW_DYN_BLOCK + threadIdx.x;
   S.status = FW_STATUS_FINISHED;
   S.fail = 0; S.rejected = 0; S.attempts = 0; S.accepted = 0; S.t = 0; S.h_abs = 0;
 #pragma unroll
@@ -266,6 +270,8 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
           if (!skip) {
             env = e;
             par_base = a.d + (int64_t)a.par_row * a.stride + e;
+            if constexpr (Spec::rand)
+              for (int r = 0; r < a.n_par_rows; ++r) par_cache[r * 32] = (T)par_base[(int64_t)r * a.stride];
             FwEnvCtx c{a.d, a.i, a.stride, e};
 #pragma unroll
             for (int j = 0; j < FW_N_ODE; ++j) S.y[j] = (T)c.D(j);
@@ -289,7 +295,7 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
     ++passes;
     if (S.status == FW_STATUS_RUNNING) {
       ++lane_attempts;
-      const FwPar<T, Spec::rand> PP{P, par_base, a.stride};
+      const FwPar<T, Spec::rand ? FW_PAR_SMEM : FW_PAR_CONST> PP{P, par_base, a.stride, par_cache};
       fw_ivp_attempt<T, Spec, FW_DYN_BLOCK>(P, PP, in, S, K);
       if (S.status != FW_STATUS_RUNNING) {   // env step finished (or raised): park the result for the env kernel
         double* cd = a.cd + env;
@@ -791,13 +797,19 @@ static int needs_generic(const fw_sim_t& S) {
   return 0;
 }
 
+// dynamic shared memory of one attempt warp: 6 K stages x 16 components (+ the parameter cache of FwSpecRand)
+template <typename T, class Spec>
+static int fw_attempt_smem(int n_par_rows) {
+  return (6 * FW_N_KC + (Spec::rand ? n_par_rows : 0)) * FW_DYN_BLOCK * (int)sizeof(T);
+}
+
 template <typename T, class Spec>
 static cudaError_t launch_dyn(const fw_sim_t& sim, const FwDynArgs& da, int attempt_grid, cudaStream_t s) {
   const int igrid = (int)((da.n + FW_INIT_BLOCK - 1) / FW_INIT_BLOCK);
   fw_init_kernel<T, Spec><<<igrid, FW_INIT_BLOCK, 0, s>>>(sim, da);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(T);
+  const int smem = fw_attempt_smem<T, Spec>(da.n_par_rows);
   const int64_t warps = (da.n + FW_DYN_BLOCK - 1) / FW_DYN_BLOCK;
   const int grid = (int)(warps < attempt_grid ? warps : attempt_grid);
   fw_attempt_kernel<T, Spec><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
@@ -805,8 +817,8 @@ static cudaError_t launch_dyn(const fw_sim_t& sim, const FwDynArgs& da, int atte
 }
 // per device (called from fw_create): opt in to the K-stage shared memory and size the persistent grid
 template <typename T, class Spec>
-static cudaError_t prepare_dyn(int sm_count, int* grid_out) {
-  const int smem = 6 * FW_N_KC * FW_DYN_BLOCK * (int)sizeof(T);
+static cudaError_t prepare_dyn(int sm_count, int n_par_rows, int* grid_out) {
+  const int smem = fw_attempt_smem<T, Spec>(n_par_rows);
   cudaError_t e = cudaFuncSetAttribute(fw_attempt_kernel<T, Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -827,15 +839,15 @@ static cudaError_t launch_dyn_any(int precision, int spec, const fw_sim_t& sim, 
   if (spec == 1) return launch_dyn<float, FwSpecGeneric>(sim, da, grid, s);
   return launch_dyn<float, FwSpecRand>(sim, da, grid, s);
 }
-static cudaError_t prepare_dyn_any(int precision, int spec, int sms, int* grid_out) {
+static cudaError_t prepare_dyn_any(int precision, int spec, int sms, int n_par_rows, int* grid_out) {
   if (precision == 0) {
-    if (spec == 0) return prepare_dyn<double, FwSpecShipped>(sms, grid_out);
-    if (spec == 1) return prepare_dyn<double, FwSpecGeneric>(sms, grid_out);
-    return prepare_dyn<double, FwSpecRand>(sms, grid_out);
+    if (spec == 0) return prepare_dyn<double, FwSpecShipped>(sms, n_par_rows, grid_out);
+    if (spec == 1) return prepare_dyn<double, FwSpecGeneric>(sms, n_par_rows, grid_out);
+    return prepare_dyn<double, FwSpecRand>(sms, n_par_rows, grid_out);
   }
-  if (spec == 0) return prepare_dyn<float, FwSpecShipped>(sms, grid_out);
-  if (spec == 1) return prepare_dyn<float, FwSpecGeneric>(sms, grid_out);
-  return prepare_dyn<float, FwSpecRand>(sms, grid_out);
+  if (spec == 0) return prepare_dyn<float, FwSpecShipped>(sms, n_par_rows, grid_out);
+  if (spec == 1) return prepare_dyn<float, FwSpecGeneric>(sms, n_par_rows, grid_out);
+  return prepare_dyn<float, FwSpecRand>(sms, n_par_rows, grid_out);
 }
 
 extern "C" {
@@ -902,7 +914,7 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
     CK(cudaGetDeviceProperties(&prop, device));
     const int sms = prop.multiProcessorCount;
     int g = 0;
-    CK(prepare_dyn_any(h->cfg.precision, h->generic, sms, &g));
+    CK(prepare_dyn_any(h->cfg.precision, h->generic, sms, h->L.n_par_rows, &g));
     const char* e = getenv("FWGYM_ATTEMPT_WARPS_PER_SM");
     if (e && atoi(e) > 0) g = atoi(e) * sms;
     h->attempt_grid = g > 0 ? g : sms;
@@ -944,7 +956,7 @@ int fw_set_config(fw_handle h, const fw_config_t* cfg) {
     CK(cudaSetDevice(h->device));
     CK(cudaGetDeviceProperties(&prop, h->device));
     int g = 0;
-    CK(prepare_dyn_any(h->cfg.precision, h->generic, prop.multiProcessorCount, &g));
+    CK(prepare_dyn_any(h->cfg.precision, h->generic, prop.multiProcessorCount, h->L.n_par_rows, &g));
     if (g > 0) h->attempt_grid = g;
   }
   h->long_h = h->long_div > 0 ? h->cfg.sim.dt / h->long_div : 0.0;
@@ -1034,7 +1046,7 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
   FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, h->ctr, h->carry_d, h->carry_i, h->long_list,
-               h->queue, h->long_h, h->L.par_row};
+               h->queue, h->long_h, h->L.par_row, h->L.n_par_rows};
   cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
   if (h->profiling) {
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
