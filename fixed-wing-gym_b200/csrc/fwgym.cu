@@ -157,7 +157,7 @@ __device__ __forceinline__ void fw_load_gusts(const fw_sim_t& P, const FwEnvCtx&
 #define FW_INIT_BLOCK 64
 template <typename T, class Spec>
 #ifndef FW_INIT_MIN_BLOCKS
-#define FW_INIT_MIN_BLOCKS 4
+#define FW_INIT_MIN_BLOCKS 8   // 128 registers: one wave at 65536 envs (1024 blocks on 148 x 8 slots); 4 -> 8: init 18 -> 13 us
 #endif
 __global__ void __launch_bounds__(FW_INIT_BLOCK, FW_INIT_MIN_BLOCKS)
 fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
