@@ -19,7 +19,9 @@
 #include "env.cuh"
 
 #define FW_DYN_BLOCK 32
+#ifndef FW_DYN_MIN_BLOCKS
 #define FW_DYN_MIN_BLOCKS 8
+#endif
 #ifndef FW_ENV_BLOCK
 #define FW_ENV_BLOCK 128
 #endif
