@@ -281,11 +281,12 @@ def run_gpu_arm(a):
         _capi.check(_capi.lib().fw_dfma_peak(local, ctypes.byref(fl), ctypes.byref(pk_ms)))
         flops_rank = (F_FIXED * p_env_steps + F_ATTEMPT * p_attempts) / world   # of the profiled pass
         achieved = flops_rank / (dyn_ms * 1e-3) / 1e12
-        traffic = None
+        traffic, ncu_notes = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("dyn_kernel_dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic, ncu_notes = tj.get("dyn_kernel_dram_bytes_per_launch"), tj.get("ncu")
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -308,6 +309,7 @@ def run_gpu_arm(a):
                          "how": "%d extra steps with an event between the dynamics and env kernels (serialised); the "
                                 "timed region runs them overlapped" % prof_steps,
                          "flops_per_env_step": "1080 + 3660*k, k = dopri5 attempts counted on device",
+                         "ncu_capture": ncu_notes,   # from the committed ncu --set full capture (profiles/), not live
                          "mean_attempts_per_env_step": k_mean,
                          "warp_divergence": {"warp_passes": wmax / world, "lane_attempts": wsteps / world,
                                              "lane_efficiency": wsteps / max(1.0, 32.0 * wmax)}},
