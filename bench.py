@@ -166,6 +166,16 @@ def run_gpu_arm(a):
     os.dup2(2, 1)
     if world != a.gpus and world > 1:
         a.gpus = world
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # one block of host cores per rank: the e2e loop is a tight submit / wait cycle, and 8 such loops plus the
+        # driver's helper threads migrating over the same cores cost the slowest rank (= the reported time) up to 1.6x
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+        except OSError:
+            pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -232,21 +242,29 @@ def run_gpu_arm(a):
     # so the PCIe traffic of step t overlaps the kernels of step t+1.  The loop ends when the LAST step's results
     # are on the host.
     from fwgym_b200 import HostStepper
-    stepper = HostStepper(vec, depth=2)
+    stepper = HostStepper(vec, depth=int(os.environ.get("FWGYM_HOST_DEPTH", "2")))
     host_actions = (torch.rand((a.steps + a.warmup, n, 3)) * 2 - 1).pin_memory()
     e2e_steps = a.steps
     checksum = 0.0
+
+    host_split = [0.0, 0.0]     # seconds inside submit() / wait() (diagnostics)
 
     def e2e_run(first, count):
         nonlocal checksum
         pending = []
         for i in range(count):
+            ta = time.perf_counter()
             pending.append(stepper.submit(host_actions[first + i]))
+            tb = time.perf_counter()
+            host_split[0] += tb - ta
             if len(pending) == stepper.depth:
                 obs, rew, done = stepper.wait(pending.pop(0))
+                host_split[1] += time.perf_counter() - tb
                 checksum += float(rew[0])          # touch the host result of every step
         while pending:
+            tb = time.perf_counter()
             obs, rew, done = stepper.wait(pending.pop(0))
+            host_split[1] += time.perf_counter() - tb
             checksum += float(rew[0])
 
     # same position in the episodes as the device-timed region above: fresh reset, W warm-up steps, then K timed steps
@@ -256,7 +274,10 @@ def run_gpu_arm(a):
     e2e_run(0, a.warmup)
     barrier()
     t0 = time.perf_counter()
+    host_split[0] = host_split[1] = 0.0
     e2e_run(a.warmup, e2e_steps)
+    torch.cuda.synchronize(dev)
+    e2e_local = time.perf_counter() - t0       # this rank's own time (the reported one is the max over ranks)
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -265,7 +286,11 @@ def run_gpu_arm(a):
                         ctr["failures"], ctr["resets"], prof_env_steps, prof_attempts, ctr_prof["watchdog"]],
                        dtype=torch.float64, device=dev)
     msum = torch.tensor(vec.metric_sums(), dtype=torch.float64, device=dev)
+    e2e_each = [e2e_local * 1e6 / e2e_steps]
     if world > 1:
+        g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([e2e_each[0]], dtype=torch.float64, device=dev))
+        e2e_each = [float(x.item()) for x in g]
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)     # time = max over ranks
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         dist.all_reduce(msum, op=dist.ReduceOp.SUM)   # the only data-path collective: episode metric sums
@@ -297,6 +322,9 @@ def run_gpu_arm(a):
             "clocks": clocks,
             "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes,
+                    "us_per_step_by_rank": [round(x, 1) for x in e2e_each],
+                    "rank0_host_us_per_step": {"submit": round(host_split[0] * 1e6 / e2e_steps, 1),
+                                               "wait": round(host_split[1] * 1e6 / e2e_steps, 1)},
                     "how": "C-ABI fw_host_submit / fw_host_wait (HostStepper, depth 2): actions from pinned host memory, observations / rewards / dones / termination codes to pinned host memory every step, copies on their own streams, wall clock"},
             "gpu_launches": int(vec.launches_per_step * a.steps),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fl.value / 1e12, "unit": "TFLOP/s",

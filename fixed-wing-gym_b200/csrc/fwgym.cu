@@ -1102,7 +1102,7 @@ int fw_host_open(fw_handle h, int depth) {
         cudaMallocHost(&r.h_term, n * sizeof(int32_t)) != cudaSuccess ||
         cudaEventCreateWithFlags(&r.e_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&r.e_step, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&r.e_out, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&r.e_out, cudaEventDisableTiming | (getenv("FWGYM_HOST_BLOCKING") ? cudaEventBlockingSync : 0)) != cudaSuccess) {
       const char* msg = cudaGetErrorString(cudaGetLastError());
       host_free(h);
       return fail(FW_ERR_ALLOC, "fw_host_open: allocation failed: %s", msg);
