@@ -1,11 +1,16 @@
 // libfwgym.so — kernels + C-ABI (include/fwgym.h).  sm_100a only.
 //
-//   fw_dyn_kernel  : one thread per aircraft; action scaling + command constraining, adaptive dopri5 integration of
-//                    the 6-DOF model over one env step (register-resident state, K stages in shared memory), state
-//                    commit, Dryden filter advance.  FP64-pipe bound.
-//   fw_env_kernel  : one thread per env; goal bits / streak, reward, target resample + advance, history rings,
-//                    observation (+noise), done, metric sums, auto-reset.  HBM bound.
-//   fw_reset_kernel: explicit (masked) reset with optional injected initial states / targets.
+//   fw_init_kernel    : one thread per aircraft, natural order: action scaling + command constraining, f(t0, y0) and
+//                       scipy's initial step size (2 RHS evaluations), parked in carry rows.
+//   fw_attempt_kernel : persistent warps, one aircraft per lane; every pass is one dopri5 step attempt (6 RHS
+//                       evaluations, K stages in shared memory); lanes adopt the next waiting aircraft at attempt
+//                       boundaries.  FP64-pipe / dependent-issue bound.
+//   fw_env_kernel     : one thread per env, specialised on the configuration's shape (env_shapes.h): PyFly's state
+//                       commit, Dryden filter advance, goal bits / streak, reward, target resample + advance, history
+//                       rings, observation (+noise), done, metric sums, auto-reset.  Launched as a programmatic
+//                       dependent of the attempt kernel; waits per chunk of 128 aircraft.
+//   fw_reset_kernel   : explicit (masked) reset with optional injected initial states / targets.
+//   host side         : handle, launches, host-buffer pipeline (fw_host_*), counters, profiling events.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -47,7 +47,7 @@ enum {
 #define FWF_TCLS_SHIFT 8          // 2 bits per target: current class (reset(target=) may force constant)
 #define FWF_EP_SUCCESS (1u << 16) // streak achieved in this episode (metric "success"["all"])
 
-// variable part, computed on the host from the config (api.cu: make_layout)
+// variable part, computed from the config by fw_layout_build below (host: make_layout in fwgym.cu; device: folded)
 struct FwLayout {
   int64_t n;            // number of envs
   int64_t stride;       // padded row length (multiple of 32)

@@ -317,7 +317,7 @@ int fw_pid_step(fw_handle h, const fw_pid_gains_t* gains, double* integ, const u
 /* Introspection */
 int64_t fw_num_envs(fw_handle h);
 int fw_obs_dim(fw_handle h);
-/* Kernel launches one fw_step issues: the dynamics stages (staged re-grouping, FWGYM_STAGES) + the env kernel. */
+/* Kernel launches one fw_step issues: init, attempt and env kernel. */
 int fw_launches_per_step(fw_handle h);
 /* Which kernel instantiations this handle's configuration selected: "dyn=<shipped|generic> env=<shape name|generic>"
  * (dynamics.cuh "kernel specialisation", env_shapes.h).  Valid until the next call on the calling thread. */

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU round trip: parity tests, a short bench, an ncu --set full capture of the dynamics kernel.
+# One GPU round trip: parity tests, a short bench, an ncu --set full capture of the attempt kernel.
 # usage: scripts/gpu_cycle.sh TAG [notest] [noncu]
 TAG=${1:-x}
 mkdir -p gpurun_out
@@ -15,7 +15,7 @@ r=d["roofline"]
 print("value %.4g ms_step %.4f e2e %.4g dyn_ms %.4f env_ms %.4f frac %.4f k %.3f lane_eff %.3f" % (d["value"], d["ms_per_step"], d["e2e"]["value"], r["kernel_ms_per_launch"], d["env_kernel"]["ms_per_launch"], r["frac"], r["mean_attempts_per_env_step"], r["warp_divergence"]["lane_efficiency"]))
 P
 if [[ "$*" != *noncu* ]]; then
-  timeout 600 ncu --set full --import-source on --clock-control none -k regex:fw_dyn_kernel -s 12 -c 1 -o gpurun_out/prof_dyn_$TAG -f \
+  timeout 600 ncu --set full --import-source on --clock-control none -k regex:fw_attempt_kernel -s 12 -c 1 -o gpurun_out/prof_att_$TAG -f \
      python bench.py --steps 10 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_$TAG.log
 fi

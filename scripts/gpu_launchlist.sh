@@ -1,6 +1,6 @@
 #!/bin/bash
-# ncu launch list (gpu__time_duration + a few counters) for a short bench run; usage: gpu_launchlist.sh TAG [STAGES]
-TAG=$1; export FWGYM_STAGES="${2-24,16}"
+# ncu launch list (gpu__time_duration + a few counters) for a short bench run; usage: gpu_launchlist.sh TAG
+TAG=$1
 timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__cycles_active.avg,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,sm__warps_active.avg.pct_of_peak_sustained_active \
   --clock-control none -k regex:fw_ -s 40 -c 16 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 6 --warmup 5 --no-cpu-baseline > gpurun_out/launches_$TAG.log 2>&1
 python - <<P
