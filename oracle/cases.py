@@ -54,4 +54,8 @@ CASES = {
     "param_rand_uniform": dict(config="fixed_wing_config_randomised.json",
                                config_kw={"steps_max": 25, "simulator": {"model": {"distribution": "uniform"}}},
                                sim_kw={"turbulence": True, "turbulence_intensity": "light"}, n=4, steps=40, amp=1.0),
+    # the CNN controller's configuration (examples/models/cnn_controller): 5-row matrix observation of 12 variables,
+    # action space bounded by the actuator limits (low / high null), bounds_outside_cost
+    "cnn": dict(config="fixed_wing_config_cnn.json", config_kw={"steps_max": 40},
+                sim_kw={"turbulence": True, "turbulence_intensity": "moderate"}, n=4, steps=60, amp=1.3),
 }
