@@ -55,12 +55,12 @@ def test_golden_fixture(built_lib, name):
     vec.close()
 
 
-@pytest.mark.parametrize("name", ["default", "turb_noise", "examples", "failure"])
+@pytest.mark.parametrize("name", ["default", "turb_noise", "examples", "failure", "cnn"])
 def test_generic_kernel_instantiation(built_lib, name, monkeypatch):
     """The dynamics kernel has two instantiations (dynamics.cuh): FwSpecShipped covers the shipped configurations and
     FwSpecGeneric everything else (any variable clipped / constrained, steady wind, polynomial drag).  The env / reset
     kernels have one instantiation per shipped configuration SHAPE plus the table-walking generic one
-    (env_shapes.h).  These four cases normally run on the specialised kernels; force the generic ones and hold them
+    (env_shapes.h).  These cases normally run on the specialised kernels; force the generic ones and hold them
     to the same fixtures."""
     monkeypatch.setenv("FWGYM_FORCE_GENERIC", "1")
     vec = make_vec(CASES[name])
@@ -75,7 +75,7 @@ def test_kernel_variant_selection(built_lib):
     want = {"default": "dyn=shipped env=default", "turb_noise": "dyn=shipped env=default_turb",
             "examples": "dyn=shipped env=examples_turb", "failure": "dyn=shipped env=default",
             "dev_history": "generic", "success_new": "generic", "wind": "dyn=generic env=generic",
-            "param_rand": "dyn=rand env=generic"}
+            "param_rand": "dyn=rand env=generic", "cnn": "env=cnn_turb"}
     for name, v in want.items():
         vec = make_vec(CASES[name])
         assert vec.kernel_variant().endswith(v), (name, vec.kernel_variant())
