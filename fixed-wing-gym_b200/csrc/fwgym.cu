@@ -49,6 +49,7 @@ struct fw_handle_s {
   int generic;                   // dynamics instantiation: 0 FwSpecShipped, 1 FwSpecGeneric, 2 FwSpecRand (dynamics.cuh)
   int overlap;                   // launch the env kernel as a programmatic dependent of the attempt kernel
   int64_t q_len;                 // ints in `queue`: Q_N + chunks
+  const int32_t* order;          // fw_debug_set_order
   int shape;                     // env / reset kernel instantiation: index into FW_SHAPE_LIST, -1 generic (env_shapes.h)
   double* ep_out;                // caller's episode-metric buffer (fw_set_episode_out)
   // init -> attempt -> env pipeline (see "dynamics kernels")
@@ -120,6 +121,7 @@ struct FwDynArgs {
   double long_h;       // initial step sizes below this go on the priority list
   int32_t par_row;     // first per-env model-parameter row of d (FwSpecRand)
   int32_t n_par_rows;
+  const int32_t* order;   // experiment hook (fw_debug_set_order): adoption order of the natural queue, NULL = identity
 };
 
 // ---- action -> actuator commands (fixed_wing.py:349-354,439-459; Actuation.set_and_constrain_commands) ----
@@ -214,6 +216,11 @@ fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   }
 }
 
+#ifdef FW_PARK_MERGED
+#define FW_CLAIMED_EARLY claim_early
+#else
+#define FW_CLAIMED_EARLY false
+#endif
 template <typename T, class Spec>
 __global__ void __launch_bounds__(FW_DYN_BLOCK, FW_DYN_MIN_BLOCKS)
 fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
@@ -239,21 +246,46 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
 #pragma unroll
   for (int j = 0; j < 3; ++j) { S.k0pos[j] = 0; in.cmd[j] = 0; in.gl[j] = 0; in.ga[j] = 0; in.wind[j] = 0; }
   bool long_left = n_long > 0, nat_left = true;
+#ifdef FW_PARK_MERGED
+  int32_t pub_env = -1;   // parked at the end of the previous pass, completion count not yet published
+#endif
   unsigned long long passes = 0, lane_attempts = 0;
+#ifdef FW_TIME_SEGMENTS
+  long long tseg_refill = 0, tseg_park = 0;
+  const long long tseg_start = clock64();
+#endif
   for (;;) {
+#ifdef FW_TIME_SEGMENTS
+    const long long tseg0 = clock64();
+#endif
     // ---- lanes without an aircraft adopt the next waiting ones (priority list first) ----
     const unsigned idle = __ballot_sync(full, S.status != FW_STATUS_RUNNING);
+#ifdef FW_PARK_MERGED
+    // The release fence of the lanes that parked a result and the claim of their next aircraft are one round trip to
+    // L2 each (~1000 cycles, measured: scripts/gpu_segments.sh).  Issue the claim first, so the two overlap.
+    const bool claim_early = idle && !long_left && nat_left;
+    int base_early = 0;
+    if (claim_early && lane == 0) base_early = atomicAdd(a.q + Q_NAT_CURSOR, __popc(idle));
+    if (pub_env >= 0) { __threadfence(); atomicAdd(FW_CHUNK_DONE(a.q, pub_env), 1); pub_env = -1; }
+#endif
     if (idle && (long_left || nat_left)) {
       const int want = __popc(idle);
       const int rank = __popc(idle & ((1u << lane) - 1u));
       int got_long = 0, got_nat = 0, base_long = 0, base_nat = 0;
+#ifdef FW_PARK_MERGED
+      if (claim_early) {
+        base_nat = __shfl_sync(full, base_early, 0);
+        got_nat = min(want, max(0, n_nat - base_nat));
+        if (base_nat + want >= n_nat) nat_left = false;
+      } else
+#endif
       if (long_left) {
         if (lane == 0) base_long = atomicAdd(a.q + Q_LONG_CURSOR, want);
         base_long = __shfl_sync(full, base_long, 0);
         got_long = min(want, max(0, n_long - base_long));
         if (base_long + want >= n_long) long_left = false;
       }
-      if (got_long < want && nat_left) {
+      if (!FW_CLAIMED_EARLY && got_long < want && nat_left) {
         const int need = want - got_long;
         if (lane == 0) base_nat = atomicAdd(a.q + Q_NAT_CURSOR, need);
         base_nat = __shfl_sync(full, base_nat, 0);
@@ -264,7 +296,10 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
         const bool from_long = rank < got_long;
         int64_t e = -1;
         if (from_long) e = a.long_list[base_long + rank];
-        else if (rank - got_long < got_nat) e = (int64_t)base_nat + (rank - got_long);
+        else if (rank - got_long < got_nat) {
+          e = (int64_t)base_nat + (rank - got_long);
+          if (a.order) e = a.order[e];
+        }
         env = -1;
         if (e >= 0) {
           const double* cd = a.cd + e;
@@ -294,16 +329,25 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
       }
     }
     const unsigned running = __ballot_sync(full, S.status == FW_STATUS_RUNNING);
+#ifdef FW_TIME_SEGMENTS
+    tseg_refill += clock64() - tseg0;
+#endif
     if (!running) {
       if (!long_left && !nat_left) break;
       continue;   // everything adopted in this round was a skip; draw again
     }
     // ---- one dopri5 step attempt for every lane that holds an aircraft ----
     ++passes;
+#ifdef FW_TIME_SEGMENTS
+    long long tseg1 = 0;
+#endif
     if (S.status == FW_STATUS_RUNNING) {
       ++lane_attempts;
       const FwPar<T, Spec::rand ? FW_PAR_SMEM : FW_PAR_CONST> PP{P, par_base, a.stride, par_cache};
       fw_ivp_attempt<T, Spec, FW_DYN_BLOCK>(P, PP, in, S, K);
+#ifdef FW_TIME_SEGMENTS
+      tseg1 = clock64();
+#endif
       if (S.status != FW_STATUS_RUNNING) {   // env step finished (or raised): park the result for the env kernel
         double* cd = a.cd + env;
         int32_t* ci = a.ci + env;
@@ -312,11 +356,27 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
         ci[CI_FAIL * a.stride] = S.fail;
         ci[CI_ATTEMPTS * a.stride] = S.attempts;
         ci[CI_ACCEPTED * a.stride] = S.accepted;
+#ifdef FW_PARK_MERGED
+        pub_env = (int32_t)env;   // published at the top of the loop, behind the claim of the next aircraft
+#else
+#ifndef FW_PARK_NO_FENCE   // experiment build (valid with FWGYM_OVERLAP=0 only): what the release fence costs
         __threadfence();                               // results before the count (release)
+#endif
         atomicAdd(FW_CHUNK_DONE(a.q, env), 1);
+#endif
       }
     }
+#ifdef FW_TIME_SEGMENTS
+    __syncwarp();
+    tseg1 = __shfl_sync(full, tseg1, __ffs(running) - 1);
+    tseg_park += clock64() - tseg1;
+#endif
   }
+#ifdef FW_TIME_SEGMENTS   // experiment build: the divergence counters carry cycle sums instead (scripts/gpu_segments.sh)
+  passes = (unsigned long long)tseg_refill;
+  lane_attempts = lane == 0 ? (unsigned long long)(clock64() - tseg_start) : 0ull;
+  if (lane == 0) atomicAdd(a.ctr + CTR_WATCHDOG, (unsigned long long)tseg_park);
+#endif
   // ---- counters: warp passes (cost) and lane attempts (useful work) ----
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lane_attempts += __shfl_xor_sync(full, lane_attempts, o);
@@ -912,6 +972,7 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   CK(cudaMemset(h->msum, 0, FW_N_METRIC_SUMS * sizeof(double)));
   h->generic = needs_generic(h->cfg.sim);
   h->shape = pick_shape(h->cfg);
+  h->order = nullptr;
   {
     const char* e = getenv("FWGYM_OVERLAP");
     h->overlap = e ? atoi(e) : 1;
@@ -1053,7 +1114,7 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
   FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, h->ctr, h->carry_d, h->carry_i, h->long_list,
-               h->queue, h->long_h, h->L.par_row, h->L.n_par_rows};
+               h->queue, h->long_h, h->L.par_row, h->L.n_par_rows, h->order};
   cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
   if (h->profiling) {
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
@@ -1161,6 +1222,12 @@ int fw_host_wait(fw_handle h, int slot, const float** obs, const float** rew, co
   if (rew) *rew = sl.h_rew;
   if (done) *done = sl.h_done;
   if (term) *term = sl.h_term;
+  return FW_OK;
+}
+
+int fw_debug_set_order(fw_handle h, const int32_t* order) {
+  if (!h) return fail(FW_ERR_ARG, "null handle");
+  h->order = order;
   return FW_OK;
 }
 

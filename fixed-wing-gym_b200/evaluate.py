@@ -57,6 +57,39 @@ class DevicePID:
         return self.actions
 
 
+class MlpController:
+    """A trained stable-baselines PPO2 MlpPolicy as the reference evaluates it (evaluate_controller.py:92-99,153):
+    `model.predict(obs, deterministic=True)` = the mean of the Gaussian head, clipped to the action space, on
+    observations normalised by the saved VecNormalize statistics ((obs - mean) / sqrt(var + 1e-8), clip 10) — EXCEPT
+    the first observation of every scenario, which the reference takes from `env_method("reset")` and therefore feeds
+    to the policy raw (evaluate_controller.py:115).  The policy math runs in float64 on the device (a 12-64-64-3 MLP:
+    torch matmuls; the controller is not the hot path) so that the CPU twin in the tests reproduces it to rounding.
+    `params`: the arrays of tests/golden/mlp_controller.npz (oracle/make_golden_policy.py)."""
+
+    def __init__(self, vec, params, clip_obs=10.0, eps=1e-8):
+        from .ppo import ActorCritic, load_sb2_parameters
+        self.vec = vec
+        d = vec.device
+        net = load_sb2_parameters(ActorCritic(int(np.asarray(params["pi_fc0_w"]).shape[0]), 3), params)
+        self.pi = net.pi.to(device=d, dtype=torch.float64)
+        self.mean = torch.as_tensor(np.asarray(params["obs_mean"], dtype=np.float64), device=d)
+        self.std = torch.sqrt(torch.as_tensor(np.asarray(params["obs_var"], dtype=np.float64), device=d) + eps)
+        self.ret_std = float(np.sqrt(float(params["ret_var"]) + eps))
+        self.clip = clip_obs
+        self.low = torch.as_tensor(np.asarray(vec.action_space.low, dtype=np.float64), device=d)
+        self.high = torch.as_tensor(np.asarray(vec.action_space.high, dtype=np.float64), device=d)
+
+    @torch.no_grad()
+    def __call__(self, obs, raw_mask=None):
+        """obs: [N, obs_dim] device tensor (any float type); raw_mask: bool [N], envs whose observation comes straight
+        from reset (fed unnormalised).  -> actions [N, 3] float64."""
+        o = obs.reshape(obs.shape[0], -1).to(torch.float64)
+        on = torch.clamp((o - self.mean) / self.std, -self.clip, self.clip)
+        if raw_mask is not None:
+            on = torch.where(raw_mask.reshape(-1, 1), o, on)
+        return torch.minimum(torch.maximum(self.pi(on), self.low), self.high)
+
+
 def load_test_set(path):
     """The reference's test sets are pickled lists of {"state": {...}, "target": {...}} (evaluate_controller.py:62);
     the committed fixture stores the same content as plain arrays (tests/golden/test_set_wind_none.npz)."""
@@ -71,7 +104,8 @@ def load_test_set(path):
 
 def evaluate_on_set(scenarios, config_path, controller="pid", config_kw=None, metrics=DEFAULT_METRICS,
                     turbulence_intensity="none", device="cuda:0", seed=0, max_steps=None):
-    """Run every scenario once (in parallel) under `controller` ("pid" or a callable(vec) -> actions tensor).
+    """Run every scenario once (in parallel) under `controller`: "pid", a dict of saved MlpPolicy arrays
+    (MlpController), or a callable(vec) -> actions tensor.
     Returns (res, vec_env): res[metric][state] lists in scenario order, res["rewards"], res["lengths"]."""
     n = len(scenarios)
     kw = dict(config_kw or {})
@@ -91,16 +125,24 @@ def evaluate_on_set(scenarios, config_path, controller="pid", config_kw=None, me
         else:
             state[k] = np.array([s["state"][k] for s in scenarios], dtype=np.float64)
     target = {k: np.array([s["target"][k] for s in scenarios], dtype=np.float64) for k in scenarios[0]["target"]}
+    vec.enable_f64_outputs(True)
     vec.reset(state=state, target=target)
     pid = DevicePID(vec) if controller == "pid" else None
+    if isinstance(controller, dict):                     # a saved MlpPolicy: the arrays of mlp_controller.npz
+        controller = MlpController(vec, controller)
+    first = torch.ones(n, dtype=torch.bool, device=vec.device)
     steps_cap = max_steps or vec.cc.steps_max
     alive = torch.ones(n, dtype=torch.bool, device=vec.device)
     rew_trace = torch.full((steps_cap, n), float("nan"), dtype=torch.float64, device=vec.device)
     lengths = torch.zeros(n, dtype=torch.long, device=vec.device)
     ep_rows = torch.full((n, vec.ep_dim), float("nan"), dtype=torch.float64, device=vec.device)
-    vec.enable_f64_outputs(True)
     for t in range(steps_cap):
-        actions = pid() if pid is not None else controller(vec)
+        if pid is not None:
+            actions = pid()
+        elif isinstance(controller, MlpController):
+            actions = controller(vec._obs64, first if t == 0 else None)
+        else:
+            actions = controller(vec)
         _, _, done, _ = vec.step_tensors(actions)
         rew_trace[t] = torch.where(alive, vec._rew64, rew_trace[t])
         fin = alive & done.bool()

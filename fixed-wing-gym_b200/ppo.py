@@ -100,6 +100,22 @@ class ActorCritic(nn.Module):
         return self.vf(obs).squeeze(-1)
 
 
+def load_sb2_parameters(model, params):
+    """Fill an ActorCritic from a stable-baselines 2 PPO2 parameter set (`parameters` inside the saved model zip,
+    e.g. examples/models/mlp_controller/model.pkl; keys model/pi_fc0/w:0 ...).  `params`: mapping with the keys
+    pi_fc0_w, pi_fc0_b, pi_fc1_*, pi_*, vf_fc0_*, vf_fc1_*, vf_*, pi_logstd (tf layout [in, out]), e.g. the committed
+    tests/golden/mlp_controller.npz (oracle/make_golden_policy.py)."""
+    def fill(lin, name):
+        with torch.no_grad():
+            lin.weight.copy_(torch.as_tensor(np.asarray(params[name + "_w"])).t())
+            lin.bias.copy_(torch.as_tensor(np.asarray(params[name + "_b"])))
+    fill(model.pi[0], "pi_fc0"); fill(model.pi[2], "pi_fc1"); fill(model.pi[4], "pi")
+    fill(model.vf[0], "vf_fc0"); fill(model.vf[2], "vf_fc1"); fill(model.vf[4], "vf")
+    with torch.no_grad():
+        model.log_std.copy_(torch.as_tensor(np.asarray(params["pi_logstd"])).reshape(-1))
+    return model
+
+
 def _allreduce_grads(model):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         w = dist.get_world_size()

@@ -323,6 +323,11 @@ int fw_launches_per_step(fw_handle h);
  * (dynamics.cuh "kernel specialisation", env_shapes.h).  Valid until the next call on the calling thread. */
 const char* fw_kernel_variant(fw_handle h);
 
+/* Experiment hook (scheduling studies): `order` is a device int32 [N] permutation of the env ids, the
+ * order in which the attempt kernel's warps adopt aircraft (NULL restores the natural order).  Results do not depend
+ * on it; the time does.  The buffer must stay valid while it is set. */
+int fw_debug_set_order(fw_handle h, const int32_t* order);
+
 /* Micro-benchmark: sustained DFMA throughput of this GPU in FLOP/s (roofline denominator, bench.py). */
 int fw_dfma_peak(int device, double* flops_out, double* ms_out);
 

@@ -378,3 +378,62 @@ def test_pid_evaluation_harness(built_lib):
              np.max(gaps), same_len))
     assert np.isfinite(gaps).all()
     vec.close()
+
+
+def test_pretrained_mlp_controller_evaluation(built_lib):
+    """SURVEY §8f row 3 (policy-in-the-loop sanity run): the reference's shipped PPO2 MlpPolicy
+    (examples/models/mlp_controller, weights + VecNormalize statistics extracted into tests/golden/mlp_controller.npz)
+    flies the 100 scenarios of test_set_wind_none on the device.  (a) Parity: the CPU oracle under a numpy twin of the
+    policy gives the same rewards (<= 1e-7: the policy's float64 matmuls sum in a different order on the two sides)
+    and episode lengths.  (b) The published evaluation of this controller (eval_res_RL_MLP_none.npy: 100 % success,
+    mean episode 270 steps) is compared and REPORTED — like the PID trace it measures the recalled aircraft
+    constants, not the kernels; only "the trained policy still controls this aircraft" is asserted."""
+    from fwgym_b200 import evaluate
+    par = dict(np.load(os.path.join(GOLDEN, "mlp_controller.npz")))
+    scen = evaluate.load_test_set(os.path.join(GOLDEN, "test_set_wind_none.npz"))
+    cfg = harness.config_path("fixed_wing_config_examples.json")
+    res, vec = evaluate.evaluate_on_set(scen, cfg, controller=par, seed=1)
+    W = [(par["pi_fc0_w"].astype(np.float64), par["pi_fc0_b"].astype(np.float64)),
+         (par["pi_fc1_w"].astype(np.float64), par["pi_fc1_b"].astype(np.float64)),
+         (par["pi_w"].astype(np.float64), par["pi_b"].astype(np.float64))]
+    std = np.sqrt(par["obs_var"] + 1e-8)
+
+    def policy(obs, raw):
+        o = np.asarray(obs, dtype=np.float64).reshape(-1)
+        x = o if raw else np.clip((o - par["obs_mean"]) / std, -10, 10)
+        x = np.tanh(x @ W[0][0] + W[0][1])
+        x = np.tanh(x @ W[1][0] + W[1][1])
+        return np.clip(x @ W[2][0] + W[2][1], vec.action_space.low.astype(np.float64),
+                       vec.action_space.high.astype(np.float64))
+
+    for i in range(2):
+        env = harness.make_env("restated", cfg, dict(evaluate.EVAL_CONFIG_KW),
+                               {"turbulence": False, "turbulence_intensity": "none"})
+        obs = env.reset(state=dict(scen[i]["state"]), target=dict(scen[i]["target"]))
+        rews, done, raw = [], False, True
+        while not done:
+            obs, r, done, info = env.step(policy(obs, raw))
+            raw = False
+            rews.append(r)
+        assert len(rews) == res["lengths"][i]
+        assert pu.rel_err(res["rewards"][i], np.array(rews), 1e-3).max() <= 1e-7
+    s = evaluate.summarise(res)
+    ret_std = float(np.sqrt(par["ret_var"] + 1e-8))
+    off = np.concatenate([[0], np.cumsum(par["pub_lengths"])])
+    gaps = []
+    for i in range(len(scen)):
+        m = int(min(len(res["rewards"][i]), par["pub_lengths"][i]))
+        ours = np.clip(res["rewards"][i][:m] / ret_std, -10, 10)       # VecNormalize(training=False) reward scaling
+        gaps.append(np.abs(ours - par["pub_rewards"][off[i]:off[i] + m]).max())
+    print("shipped MLP controller on test_set_wind_none (100 scenarios): success roll/pitch/Va/all %.2f/%.2f/%.2f/%.2f "
+          "(published %.2f/%.2f/%.2f/%.2f), mean length %.1f (published %.1f), settling_time_all %.1f (published %.1f), "
+          "control_variation %.3f (published %.3f); max |normalised reward gap|: median %.3g, worst %.3g"
+          % (s.get("success_roll", np.nan), s.get("success_pitch", np.nan), s.get("success_Va", np.nan),
+             s.get("success_all", np.nan), par["pub_success_roll"].mean(), par["pub_success_pitch"].mean(),
+             par["pub_success_Va"].mean(), par["pub_success_all"].mean(), res["lengths"].mean(),
+             par["pub_lengths"].mean(), s.get("settling_time_all", np.nan), np.nanmean(par["pub_settling_time_all"]),
+             s.get("control_variation_all", np.nan), np.nanmean(par["pub_control_variation_all"]),
+             np.median(gaps), np.max(gaps)))
+    assert np.isfinite(gaps).all()
+    assert s.get("success_all", 0.0) >= 0.9     # a policy trained on true PyFly still flies the restated aircraft
+    vec.close()
