@@ -216,11 +216,6 @@ fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
   }
 }
 
-#ifdef FW_PARK_MERGED
-#define FW_CLAIMED_EARLY claim_early
-#else
-#define FW_CLAIMED_EARLY false
-#endif
 template <typename T, class Spec>
 __global__ void __launch_bounds__(FW_DYN_BLOCK, FW_DYN_MIN_BLOCKS)
 fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
@@ -246,9 +241,6 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
 #pragma unroll
   for (int j = 0; j < 3; ++j) { S.k0pos[j] = 0; in.cmd[j] = 0; in.gl[j] = 0; in.ga[j] = 0; in.wind[j] = 0; }
   bool long_left = n_long > 0, nat_left = true;
-#ifdef FW_PARK_MERGED
-  int32_t pub_env = -1;   // parked at the end of the previous pass, completion count not yet published
-#endif
   unsigned long long passes = 0, lane_attempts = 0;
 #ifdef FW_TIME_SEGMENTS
   long long tseg_refill = 0, tseg_park = 0;
@@ -260,32 +252,17 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
 #endif
     // ---- lanes without an aircraft adopt the next waiting ones (priority list first) ----
     const unsigned idle = __ballot_sync(full, S.status != FW_STATUS_RUNNING);
-#ifdef FW_PARK_MERGED
-    // The release fence of the lanes that parked a result and the claim of their next aircraft are one round trip to
-    // L2 each (~1000 cycles, measured: scripts/gpu_segments.sh).  Issue the claim first, so the two overlap.
-    const bool claim_early = idle && !long_left && nat_left;
-    int base_early = 0;
-    if (claim_early && lane == 0) base_early = atomicAdd(a.q + Q_NAT_CURSOR, __popc(idle));
-    if (pub_env >= 0) { __threadfence(); atomicAdd(FW_CHUNK_DONE(a.q, pub_env), 1); pub_env = -1; }
-#endif
     if (idle && (long_left || nat_left)) {
       const int want = __popc(idle);
       const int rank = __popc(idle & ((1u << lane) - 1u));
       int got_long = 0, got_nat = 0, base_long = 0, base_nat = 0;
-#ifdef FW_PARK_MERGED
-      if (claim_early) {
-        base_nat = __shfl_sync(full, base_early, 0);
-        got_nat = min(want, max(0, n_nat - base_nat));
-        if (base_nat + want >= n_nat) nat_left = false;
-      } else
-#endif
       if (long_left) {
         if (lane == 0) base_long = atomicAdd(a.q + Q_LONG_CURSOR, want);
         base_long = __shfl_sync(full, base_long, 0);
         got_long = min(want, max(0, n_long - base_long));
         if (base_long + want >= n_long) long_left = false;
       }
-      if (!FW_CLAIMED_EARLY && got_long < want && nat_left) {
+      if (got_long < want && nat_left) {
         const int need = want - got_long;
         if (lane == 0) base_nat = atomicAdd(a.q + Q_NAT_CURSOR, need);
         base_nat = __shfl_sync(full, base_nat, 0);
@@ -356,14 +333,10 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
         ci[CI_FAIL * a.stride] = S.fail;
         ci[CI_ATTEMPTS * a.stride] = S.attempts;
         ci[CI_ACCEPTED * a.stride] = S.accepted;
-#ifdef FW_PARK_MERGED
-        pub_env = (int32_t)env;   // published at the top of the loop, behind the claim of the next aircraft
-#else
 #ifndef FW_PARK_NO_FENCE   // experiment build (valid with FWGYM_OVERLAP=0 only): what the release fence costs
         __threadfence();                               // results before the count (release)
 #endif
         atomicAdd(FW_CHUNK_DONE(a.q, env), 1);
-#endif
       }
     }
 #ifdef FW_TIME_SEGMENTS
