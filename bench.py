@@ -198,6 +198,15 @@ def run_gpu_arm(a):
     # synthetic policy output: i.i.d. U(-1,1) actions, a fresh batch per step, resident in HBM before timing
     actions = torch.rand((total, n, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    flush_mode = os.environ.get("FWGYM_BENCH_FLUSH", "write")
+    flush_rd = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device=dev) if flush_mode == "write+read" else None
+
+    def flush_l2():
+        # write a buffer larger than L2.  "write+read" (diagnostic): a 256 MiB read pass behind it, so that the lines the
+        # memset leaves DIRTY in L2 are written back before the timed step starts instead of on its misses
+        flush.zero_()
+        if flush_rd is not None:
+            flush_rd.sum()
 
     def barrier():
         if world > 1:
@@ -215,7 +224,7 @@ def run_gpu_arm(a):
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(a.steps):
-        flush.zero_()                       # L2 flush between timed iterations (not inside the timed interval)
+        flush_l2()                          # L2 flush between timed iterations (not inside the timed interval)
         ev[k][0].record()
         vec.step_tensors(actions[a.warmup + k])
         ev[k][1].record()
@@ -229,7 +238,7 @@ def run_gpu_arm(a):
     # of the attempt kernel and overlaps its tail)
     vec.set_profiling(True)
     for k in range(prof_steps_n):
-        flush.zero_()
+        flush_l2()
         vec.step_tensors(actions[a.warmup + a.steps + k])
     dyn_ms, env_ms, prof_steps = vec.profile()
     vec.set_profiling(False)
@@ -317,7 +326,9 @@ def run_gpu_arm(a):
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": n, "actions": "i.i.d. U(-1,1)^3 per step",
-                       "l2": "256 MiB memset between timed steps; per-step CUDA events summed",
+                       "l2": "256 MiB memset between timed steps; per-step CUDA events summed"
+                             + ("; + 256 MiB read pass (memset's dirty lines written back before the step)"
+                                if flush_mode == "write+read" else ""),
                        "parallelism": "env-sharded x%d, no step-path collective" % world},
             "clocks": clocks,
             "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": "env-steps/s",

@@ -29,17 +29,58 @@ template <> struct FwMath<double> {
   // nextafter(x, +inf) for finite x >= 0 (the integrator's t)
   static __device__ __forceinline__ double next_up(double x) { return __longlong_as_double(__double_as_longlong(x) + 1); }
 };
+// fp32 (opt-in mode, reported separately from the fp64 parity claim): hardware approximations (MUFU.RCP / RSQ / EX2 /
+// LG2, ~1-2 ulp) and a straight-line atan2 — no libdevice slow paths, so the right-hand side stays one basic block
+// like the fp64 one.  Inputs are finite physical numbers; zero arguments of sqrt / atan2 are handled.
 template <> struct FwMath<float> {
-  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
-  static __device__ __forceinline__ void sqrt_rsqrt(float x, float* s, float* rs) { *s = sqrtf(x); *rs = 1.0f / *s; }
-  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
-  static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
-  static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
-  static __device__ __forceinline__ float div_(float a, float b) { return a / b; }
-  static __device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
+  static __device__ __forceinline__ float rcp_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+  static __device__ __forceinline__ float sqrt_(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+  static __device__ __forceinline__ void sqrt_rsqrt(float x, float* s, float* rs) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    *rs = r;
+    *s = x > 0.0f ? x * r : 0.0f;
+  }
+  static __device__ __forceinline__ float exp_(float x) { return __expf(x); }
+  static __device__ __forceinline__ float div_(float a, float b) { return a * rcp_(b); }
+  static __device__ __forceinline__ float pow_(float x, float y) { return __powf(x, y); }
+  // atan(t) = t * R(t^2) on [0, 1] (degree 8, max abs error 1.1e-7), octant / quadrant fix-ups by selects
+  static __device__ __forceinline__ float atan2_(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = mx > 0.0f ? mn * rcp_(mx) : 0.0f;
+    const float z = t * t, z2 = z * z, z4 = z2 * z2;
+    const float p01 = fmaf(-0.3333306610584259f, z, 1.0f), p23 = fmaf(-0.14202570915222168f, z, 0.19992484152317047f);
+    const float p45 = fmaf(-0.07495445758104324f, z, 0.10636754333972931f);
+    const float p67 = fmaf(-0.016005029901862144f, z, 0.042587608098983765f);
+    const float lo = fmaf(p23, z2, p01), hi = fmaf(p67, z2, p45);
+    float r = t * fmaf(fmaf(0.0028340641874819994f, z4, hi), z4, lo);
+    r = ay > ax ? 1.5707963267948966f - r : r;
+    r = x < 0.0f ? 3.141592653589793f - r : r;
+    return copysignf(r, y);
+  }
   static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
   static __device__ __forceinline__ float next_up(float x) { return __int_as_float(__float_as_int(x) + 1); }
 };
+
+// ---- fp32 kernels read the model's numbers as FLOATS ----
+// fw_sim_t holds doubles; converting one at its point of use is an F2F.F32.F64 (FP64 pipe) per read, ~190 per attempt
+// body.  An fp32 dynamics kernel therefore receives FwSimX = the configuration + a float image of it: element k of the
+// image is the float value of the k-th 8-byte slot of fw_sim_t (slots that are not doubles hold garbage and are never
+// read).  fw_rd<T>(P, P.field) returns the field itself for double and the image element for float; after inlining
+// both are constant-bank operands at fixed offsets of the kernel parameter.  P must be the FwSimX's own member.
+struct FwSimF { float v[sizeof(fw_sim_t) / 8]; };
+struct FwSimX { fw_sim_t P; FwSimF F; };
+static_assert(sizeof(fw_sim_t) % 8 == 0, "fw_sim_t must be a whole number of 8-byte slots");
+template <typename T> struct FwSimArg { typedef fw_sim_t type; };
+template <> struct FwSimArg<float> { typedef FwSimX type; };
+__device__ __forceinline__ const fw_sim_t& fw_sim_of(const fw_sim_t& p) { return p; }
+__device__ __forceinline__ const fw_sim_t& fw_sim_of(const FwSimX& p) { return p.P; }
+template <typename T>
+__device__ __forceinline__ T fw_rd(const fw_sim_t& P, const double& field) {
+  if constexpr (sizeof(T) == 8) return field;
+  else return reinterpret_cast<const FwSimX*>(&P)->F.v[&field - reinterpret_cast<const double*>(&P)];
+}
 
 // PyFly Variable.apply_conditions: constraint check -> clip -> (wrap).  `fail` keeps the FIRST violated variable.
 // The host stores every missing bound as +-inf (lo/hi for the clip, clo/chi for the constraint), so the body is
@@ -156,9 +197,9 @@ template <typename T, int MODE> struct FwPar {
     if constexpr (MODE == FW_PAR_SMEM) {                                          \
       const int s1 = P.par_slot1[FW_PAR_##ID];                                    \
       const T v = cache[(s1 > 0 ? s1 - 1 : 0) * 32];                              \
-      return s1 > 0 ? v : (T)P.F;                                                 \
+      return s1 > 0 ? v : fw_rd<T>(P, P.F);                                       \
     }                                                                             \
-    return (T)P.F;                                                                \
+    return fw_rd<T>(P, P.F);                                                      \
   }
   FW_LIVE_PARAMS(FW_PAR_GETTER)
 #undef FW_PAR_GETTER
@@ -167,15 +208,16 @@ template <typename T, int MODE> struct FwPar {
 // branch-free condition of the variable of rank R: violated constraints set bit R of failmask.  RAW: no condition
 // at all (see fw_rhs).
 template <typename T, class Spec, int R, bool RAW = false>
-__device__ __forceinline__ T fw_cond_r(const fw_var_t& v, T x, uint32_t& failmask) {
+__device__ __forceinline__ T fw_cond_r(const fw_sim_t& P, const fw_var_t& v, T x, uint32_t& failmask) {
   if constexpr (RAW) return x;
   if constexpr ((Spec::cons >> R) & 1u) {
-    const bool bad = (x < (T)v.clo) | (x > (T)v.chi);
+    const bool bad = (x < fw_rd<T>(P, v.clo)) | (x > fw_rd<T>(P, v.chi));
     failmask |= bad ? FW_RB(R) : 0u;
   }
   if constexpr ((Spec::clip >> R) & 1u) {
-    x = x < (T)v.lo ? (T)v.lo : x;     // compares keep NaN, like np.clip
-    x = x > (T)v.hi ? (T)v.hi : x;
+    const T lo = fw_rd<T>(P, v.lo), hi = fw_rd<T>(P, v.hi);
+    x = x < lo ? lo : x;     // compares keep NaN, like np.clip
+    x = x > hi ? hi : x;
   }
   return x;
 }
@@ -193,26 +235,26 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const PAR& PP, const F
                                        const T (&y)[FW_N_ODE], T (&dy)[FW_N_ODE], uint32_t& failmask) {
   typedef FwMath<T> Mt;
   const T e0 = y[0], e1 = y[1], e2 = y[2], e3 = y[3];
-  const T p = fw_cond_r<T, Spec, FW_R_P, RAW>(P.var[FW_SV_OMEGA_P], y[4], failmask);
-  const T q = fw_cond_r<T, Spec, FW_R_Q, RAW>(P.var[FW_SV_OMEGA_Q], y[5], failmask);
-  const T r = fw_cond_r<T, Spec, FW_R_R, RAW>(P.var[FW_SV_OMEGA_R], y[6], failmask);
+  const T p = fw_cond_r<T, Spec, FW_R_P, RAW>(P, P.var[FW_SV_OMEGA_P], y[4], failmask);
+  const T q = fw_cond_r<T, Spec, FW_R_Q, RAW>(P, P.var[FW_SV_OMEGA_Q], y[5], failmask);
+  const T r = fw_cond_r<T, Spec, FW_R_R, RAW>(P, P.var[FW_SV_OMEGA_R], y[6], failmask);
   // position variables carry no limits (config.py rejects them): their stage states are never formed
-  const T u = fw_cond_r<T, Spec, FW_R_U, RAW>(P.var[FW_SV_VEL_U], y[10], failmask);
-  const T v = fw_cond_r<T, Spec, FW_R_V, RAW>(P.var[FW_SV_VEL_V], y[11], failmask);
-  const T w = fw_cond_r<T, Spec, FW_R_W, RAW>(P.var[FW_SV_VEL_W], y[12], failmask);
+  const T u = fw_cond_r<T, Spec, FW_R_U, RAW>(P, P.var[FW_SV_VEL_U], y[10], failmask);
+  const T v = fw_cond_r<T, Spec, FW_R_V, RAW>(P, P.var[FW_SV_VEL_V], y[11], failmask);
+  const T w = fw_cond_r<T, Spec, FW_R_W, RAW>(P, P.var[FW_SV_VEL_W], y[12], failmask);
   // actuators: value conditions + rate clip (ControlVariable.apply_conditions)
-  const T el = fw_cond_r<T, Spec, FW_R_EL, RAW>(P.var[FW_SV_ELEVON_L], y[13], failmask);
-  const T er = fw_cond_r<T, Spec, FW_R_ER, RAW>(P.var[FW_SV_ELEVON_R], y[14], failmask);
-  const T th = fw_cond_r<T, Spec, FW_R_TH, RAW>(P.var[FW_SV_THROTTLE], y[15], failmask);
+  const T el = fw_cond_r<T, Spec, FW_R_EL, RAW>(P, P.var[FW_SV_ELEVON_L], y[13], failmask);
+  const T er = fw_cond_r<T, Spec, FW_R_ER, RAW>(P, P.var[FW_SV_ELEVON_R], y[14], failmask);
+  const T th = fw_cond_r<T, Spec, FW_R_TH, RAW>(P, P.var[FW_SV_THROTTLE], y[15], failmask);
   T ad[3] = {y[16], y[17], y[18]};
 #pragma unroll
   for (int i = 0; i < 3; ++i)
     if (!RAW && ((Spec::clip >> (FW_R_AD0 + i)) & 1u)) {
-      const T m = P.act_has_dot_max[i] ? (T)P.act_dot_max[i] : (T)CUDART_INF;
+      const T m = P.act_has_dot_max[i] ? fw_rd<T>(P, P.act_dot_max[i]) : (T)CUDART_INF;
       ad[i] = ad[i] < -m ? -m : (ad[i] > m ? m : ad[i]);
     }
-  const T ail = fw_cond_r<T, Spec, FW_R_AIL>(P.var[FW_SV_AILERON], (-er + el) * (T)0.5, failmask);
-  const T elev = fw_cond_r<T, Spec, FW_R_ELEV>(P.var[FW_SV_ELEVATOR], (er + el) * (T)0.5, failmask);
+  const T ail = fw_cond_r<T, Spec, FW_R_AIL>(P, P.var[FW_SV_AILERON], (-er + el) * (T)0.5, failmask);
+  const T elev = fw_cond_r<T, Spec, FW_R_ELEV>(P, P.var[FW_SV_ELEVATOR], (er + el) * (T)0.5, failmask);
   const T rud = (T)0;
 
   // ---- airspeed factors (PyFly._calculate_airspeed_factors with the quaternion rotation) ----
@@ -234,11 +276,11 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const PAR& PP, const F
   Mt::sqrt_rsqrt(hxz2, &hxz, &ih);
   T alpha = Mt::atan2_(wr, ur);
   T beta = Mt::atan2_(vr, hxz);
-  const T Va = fw_cond_r<T, Spec, FW_R_VA>(P.var[FW_SV_VA], Va_raw, failmask);
+  const T Va = fw_cond_r<T, Spec, FW_R_VA>(P, P.var[FW_SV_VA], Va_raw, failmask);
   T invVa = invVa_raw;
   if (Va != Va_raw) invVa = Mt::rcp_(Va);   // value_min clip engaged (rare)
-  alpha = fw_cond_r<T, Spec, FW_R_ALPHA>(P.var[FW_SV_ALPHA], alpha, failmask);
-  beta = fw_cond_r<T, Spec, FW_R_BETA>(P.var[FW_SV_BETA], beta, failmask);
+  alpha = fw_cond_r<T, Spec, FW_R_ALPHA>(P, P.var[FW_SV_ALPHA], alpha, failmask);
+  beta = fw_cond_r<T, Spec, FW_R_BETA>(P, P.var[FW_SV_BETA], beta, failmask);
 
   // ---- forces and moments (PyFly._forces) ----
   const T pre = (T)0.5 * PP.rho() * Va * Va * PP.S_wing();
@@ -260,7 +302,7 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const PAR& PP, const F
     // fp32: (1+e1)(1+e2) must stay below FLT_MAX, so both exponents are clamped (e1 * e2 is constant)
     const T ex1 = Mt::exp_(fminf(-PP.M() * (alpha - PP.a_0()), 80.0f));
     const T ex2 = Mt::exp_(fminf(PP.M() * (alpha + PP.a_0()), 80.0f));
-    sigma = (1 + ex1 + ex2) / ((1 + ex1) * (1 + ex2));
+    sigma = Mt::div_(1 + ex1 + ex2, (1 + ex1) * (1 + ex2));
   }
   // sin/cos of alpha and beta follow algebraically from the airspeed components (beta = asin(v_r / |v_r|) uses the
   // UNclipped airspeed) when neither angle was altered by a clip (the usual configuration); otherwise sincos.
@@ -311,10 +353,11 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const PAR& PP, const F
   dy[1] = (T)0.5 * (p * e0 + r * e2 - q * e3);
   dy[2] = (T)0.5 * (q * e0 - r * e1 + p * e3);
   dy[3] = (T)0.5 * (r * e0 + q * e1 - p * e2);
-  const double* G = P.gammas;
-  dy[4] = (T)G[1] * p * q - (T)G[2] * q * r + (T)G[3] * tl + (T)G[4] * tn;
-  dy[5] = (T)G[5] * p * r - (T)G[6] * (p * p - r * r) + tm * (T)P.inv_Jy;
-  dy[6] = (T)G[7] * p * q - (T)G[1] * q * r + (T)G[4] * tl + (T)G[8] * tn;
+#define FW_G(k) fw_rd<T>(P, P.gammas[k])
+  dy[4] = FW_G(1) * p * q - FW_G(2) * q * r + FW_G(3) * tl + FW_G(4) * tn;
+  dy[5] = FW_G(5) * p * r - FW_G(6) * (p * p - r * r) + tm * fw_rd<T>(P, P.inv_Jy);
+  dy[6] = FW_G(7) * p * q - FW_G(1) * q * r + FW_G(4) * tl + FW_G(8) * tn;
+#undef FW_G
   dy[7] = (e1 * e1 + e0 * e0 - e2 * e2 - e3 * e3) * u + 2 * (e1 * e2 - e3 * e0) * v + 2 * (e1 * e3 + e2 * e0) * w;
   dy[8] = 2 * (e1 * e2 + e3 * e0) * u + (e2 * e2 + e0 * e0 - e1 * e1 - e3 * e3) * v + 2 * (e2 * e3 - e1 * e0) * w;
   dy[9] = 2 * (e1 * e3 - e2 * e0) * u + 2 * (e2 * e3 + e1 * e0) * v + (e3 * e3 + e0 * e0 - e1 * e1 - e2 * e2) * w;
@@ -325,9 +368,10 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const PAR& PP, const F
   const T av[3] = {el, er, th};
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const double* c = P.act_coef[i];
-    dy[13 + i] = av[i] * (T)c[0] + in.cmd[i] * (T)c[2] + ad[i] * (T)c[1];
-    dy[16 + i] = av[i] * (T)c[3] + in.cmd[i] * (T)c[5] + ad[i] * (T)c[4];
+#define FW_AC(k) fw_rd<T>(P, P.act_coef[i][k])
+    dy[13 + i] = av[i] * FW_AC(0) + in.cmd[i] * FW_AC(2) + ad[i] * FW_AC(1);
+    dy[16 + i] = av[i] * FW_AC(3) + in.cmd[i] * FW_AC(5) + ad[i] * FW_AC(4);
+#undef FW_AC
   }
 }
 
@@ -341,6 +385,22 @@ __constant__ double c_dpA[7][6] = {
     {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
     {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
 __constant__ double c_dpE[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+__constant__ float c_dpAf[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {(float)(1.0 / 5), 0, 0, 0, 0, 0},
+    {(float)(3.0 / 40), (float)(9.0 / 40), 0, 0, 0, 0},
+    {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), 0, 0, 0},
+    {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0, 0},
+    {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176), (float)(-5103.0 / 18656), 0},
+    {(float)(35.0 / 384), 0, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784), (float)(11.0 / 84)}};
+__constant__ float c_dpEf[7] = {(float)(-71.0 / 57600), 0, (float)(71.0 / 16695), (float)(-71.0 / 1920),
+                                (float)(17253.0 / 339200), (float)(-22.0 / 525), (float)(1.0 / 40)};
+template <typename T> __device__ __forceinline__ T fw_dpA(int s, int j) {
+  if constexpr (sizeof(T) == 8) return c_dpA[s][j]; else return c_dpAf[s][j];
+}
+template <typename T> __device__ __forceinline__ T fw_dpE(int s) {
+  if constexpr (sizeof(T) == 8) return c_dpE[s]; else return c_dpEf[s];
+}
 
 // The position states (y[7..9]) never feed back into the right-hand side, so their K stages are not stored: their
 // contributions to y_new (B row) and to the error estimate (E row) are accumulated in registers as each stage is
@@ -363,7 +423,7 @@ __device__ __forceinline__ double fw_rcp(double x) {
   r = fma(fma(-x, r, 1.0), r, r);
   return r;
 }
-__device__ __forceinline__ float fw_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float fw_rcp(float x) { return FwMath<float>::rcp_(x); }
 
 // ---- resumable scipy-RK45 state of ONE solve_ivp(fun, (0, dt), y0) call ---------------------------------------------
 // Everything an aircraft carries from one dopri5 step attempt to the next.  K0 = f(t, y) (FSAL) lives in slot 0 of the
@@ -393,7 +453,7 @@ template <typename T, class Spec, class PAR>
 __device__ __forceinline__ int fw_ivp_init(const fw_sim_t& P, const PAR& PP, const FwStepIn<T>& in,
                                            const T (&y)[FW_N_ODE], T (&f0)[FW_N_ODE], T& h_abs) {
   typedef FwMath<T> Mt;
-  const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
+  const T rtol = fw_rd<T>(P, P.rtol), atol = fw_rd<T>(P, P.atol), tb = fw_rd<T>(P, P.dt);
   const T inv_sqrtn = (T)(1.0 / 4.358898943540674);   // 1 / 19 ** 0.5
   uint32_t failmask = 0u;
   fw_rhs<T, Spec, true>(P, PP, in, y, f0, failmask);   // t == 0: stored state values, unconditioned
@@ -444,7 +504,7 @@ template <typename T, class Spec, int BLOCK, class PAR>
 __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
                                                const FwStepIn<T>& in, FwIvp<T>& S, FwKStore<T, BLOCK> K) {
   typedef FwMath<T> Mt;
-  const T rtol = (T)P.rtol, atol = (T)P.atol, tb = (T)P.dt;
+  const T rtol = fw_rd<T>(P, P.rtol), atol = fw_rd<T>(P, P.atol), tb = fw_rd<T>(P, P.dt);
   const T inv_sqrtn = (T)(1.0 / 4.358898943540674);
   // ---- start a step attempt (rk.py:111-147); min_step = 10 * |nextafter(t, inf) - t|
   const T min_step = 10 * fabs(Mt::next_up(S.t) - S.t);
@@ -460,7 +520,7 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
   ++S.attempts;
   T accB[3], accE[3];    // running B-row / E-row sums of the position components (never stored as K stages)
 #pragma unroll
-  for (int j = 0; j < 3; ++j) { accB[j] = (T)c_dpA[6][0] * S.k0pos[j]; accE[j] = (T)c_dpE[0] * S.k0pos[j]; }
+  for (int j = 0; j < 3; ++j) { accB[j] = fw_dpA<T>(6, 0) * S.k0pos[j]; accE[j] = fw_dpE<T>(0) * S.k0pos[j]; }
 #pragma unroll 1
   for (int s = 1; s <= 6; ++s) {
     T ys[FW_N_ODE], f[FW_N_ODE];
@@ -469,7 +529,7 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
 #pragma unroll
       for (int kc = 0; kc < FW_N_KC; ++kc) ys[fw_kc_to_ode(kc)] = S.y[fw_kc_to_ode(kc)];
       for (int j = 0; j < s; ++j) {
-        const T ha = h * (T)c_dpA[s][j];
+        const T ha = h * fw_dpA<T>(s, j);
 #pragma unroll
         for (int kc = 0; kc < FW_N_KC; ++kc) ys[fw_kc_to_ode(kc)] = fma(ha, K.at(j, kc), ys[fw_kc_to_ode(kc)]);
       }
@@ -487,7 +547,7 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
     if (s < 6) {
 #pragma unroll
       for (int kc = 0; kc < FW_N_KC; ++kc) K.at(s, kc) = f[fw_kc_to_ode(kc)];
-      const T b = (T)c_dpA[6][s], e = (T)c_dpE[s];
+      const T b = fw_dpA<T>(6, s), e = fw_dpE<T>(s);
 #pragma unroll
       for (int j = 0; j < 3; ++j) { accB[j] += b * f[7 + j]; accE[j] += e * f[7 + j]; }
       continue;
@@ -497,10 +557,10 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
 #pragma unroll
     for (int kc = 0; kc < FW_N_KC; ++kc) {
       const int c = fw_kc_to_ode(kc);
-      T e = (T)c_dpE[6] * f[c];
+      T e = fw_dpE<T>(6) * f[c];
 #pragma unroll
       for (int j = 0; j < 6; ++j)
-        if (j != 1) e += (T)c_dpE[j] * K.at(j, kc);
+        if (j != 1) e += fw_dpE<T>(j) * K.at(j, kc);
       e *= h;
       const T ay = fabs(S.y[c]), an = fabs(ys[c]);
       const T q = e * fw_rcp(atol + (ay > an ? ay : an) * rtol);
@@ -508,7 +568,7 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const T e = (accE[j] + (T)c_dpE[6] * f[7 + j]) * h;
+      const T e = (accE[j] + fw_dpE<T>(6) * f[7 + j]) * h;
       const T ay = fabs(S.y[7 + j]), an = fabs(ys[7 + j]);
       const T q = e * fw_rcp(atol + (ay > an ? ay : an) * rtol);
       se += q * q;

@@ -24,6 +24,9 @@
 #include "env.cuh"
 
 #define FW_DYN_BLOCK 32
+#ifndef FW_DYN_MIN_BLOCKS_F32
+#define FW_DYN_MIN_BLOCKS_F32 16
+#endif
 #ifndef FW_DYN_MIN_BLOCKS
 #define FW_DYN_MIN_BLOCKS 8
 #endif
@@ -107,6 +110,22 @@ enum { Q_LONG_COUNT = 0, Q_LONG_CURSOR, Q_NAT_CURSOR, Q_N };
 // only, so the env-side work of the early chunks runs in the shadow of the attempt kernel's tail.
 #define FW_CHUNK_DONE(q, env) ((q) + Q_N + (int)((env) / FW_ENV_BLOCK))
 
+// Experiment build (-DFW_TIMELINE, scripts/gpu_timeline.py): first block start / last block end of the three kernels of a
+// step on the GPU's global timer (ns), read back with fw_debug_timeline.
+__device__ unsigned long long fw_timeline_buf[8];   // [6] first env block past its wait, [7] sum of env block run times
+#ifdef FW_TIMELINE
+__device__ __forceinline__ unsigned long long fw_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FW_TL_BEGIN(k) do { if (threadIdx.x == 0) atomicMin(&fw_timeline_buf[2 * (k)], fw_gtime()); } while (0)
+#define FW_TL_END(k) do { if (threadIdx.x == 0) atomicMax(&fw_timeline_buf[2 * (k) + 1], fw_gtime()); } while (0)
+#else
+#define FW_TL_BEGIN(k) do { } while (0)
+#define FW_TL_END(k) do { } while (0)
+#endif
+
 struct FwDynArgs {
   double* d;
   int32_t* i;
@@ -169,7 +188,9 @@ template <typename T, class Spec>
 #define FW_INIT_MIN_BLOCKS 8   // 128 registers: one wave at 65536 envs (1024 blocks on 148 x 8 slots); 4 -> 8: init 18 -> 13 us
 #endif
 __global__ void __launch_bounds__(FW_INIT_BLOCK, FW_INIT_MIN_BLOCKS)
-fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
+fw_init_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDynArgs a) {
+  const fw_sim_t& P = fw_sim_of(Px);
+  FW_TL_BEGIN(0);
   const int64_t env = (int64_t)blockIdx.x * FW_INIT_BLOCK + threadIdx.x;
   const bool valid = env < a.n;
   bool is_long = false, init_failed = false;
@@ -214,11 +235,15 @@ fw_init_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
     base = __shfl_sync(full, base, 0);
     if (is_long) a.long_list[base + __popc(lm & ((1u << lane) - 1u))] = (int32_t)env;
   }
+  FW_TL_END(0);
 }
 
+// fp32 aircraft need half the registers and half the K-stage shared memory: twice the resident warps
 template <typename T, class Spec>
-__global__ void __launch_bounds__(FW_DYN_BLOCK, FW_DYN_MIN_BLOCKS)
-fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
+__global__ void __launch_bounds__(FW_DYN_BLOCK, sizeof(T) == 4 ? FW_DYN_MIN_BLOCKS_F32 : FW_DYN_MIN_BLOCKS)
+fw_attempt_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDynArgs a) {
+  const fw_sim_t& P = fw_sim_of(Px);
+  FW_TL_BEGIN(1);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwKStore<T, FW_DYN_BLOCK> K{reinterpret_cast<T*>(smem_raw)};
   // Every warp of this (fully resident) grid is on an SM by now: let the env kernel's blocks queue up behind us.  They
@@ -357,6 +382,7 @@ fw_attempt_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
     atomicAdd(a.ctr + CTR_WARP_MAX, passes);
     atomicAdd(a.ctr + CTR_WARP_STEPS, lane_attempts);
   }
+  FW_TL_END(1);
 }
 
 // ---- PyFly._set_states_from_ode_solution(save=True) + airspeed factors + next gust column (env kernel prologue) ----
@@ -629,6 +655,7 @@ __global__ void __launch_bounds__(FW_ENV_BLOCK, FW_ENV_MIN_BLOCKS)
 fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
               const FwEnvArgs a) {
   const int64_t env = (int64_t)blockIdx.x * FW_ENV_BLOCK + threadIdx.x;
+  FW_TL_BEGIN(2);
   // Wait until every aircraft of this block's chunk has been parked by the dynamics kernels (acquire side of the
   // release in fw_attempt_kernel).  One polling thread per block; the others sleep on the barrier.  The attempt kernel
   // never waits for anything, so this cannot deadlock; the watchdog turns a lost update into an error flag
@@ -645,6 +672,10 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
     __threadfence();
   }
   __syncthreads();
+#ifdef FW_TIMELINE
+  const unsigned long long tl_go = fw_gtime();
+  if (threadIdx.x == 0) atomicMin(&fw_timeline_buf[6], tl_go);
+#endif
   double m[FW_N_METRIC_SUMS];
 #pragma unroll
   for (int k = 0; k < FW_N_METRIC_SUMS; ++k) m[k] = 0.0;
@@ -666,6 +697,11 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
     atomicAdd(a.ctr + CTR_ACCEPTED, (unsigned long long)accepted);
     if (failed) atomicAdd(a.ctr + CTR_FAILURES, (unsigned long long)failed);
   }
+#ifdef FW_TIMELINE
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(&fw_timeline_buf[7], fw_gtime() - tl_go);
+#endif
+  FW_TL_END(2);
 }
 
 
@@ -844,7 +880,14 @@ static int fw_attempt_smem(int n_par_rows) {
 }
 
 template <typename T, class Spec>
-static cudaError_t launch_dyn(const fw_sim_t& sim, const FwDynArgs& da, int attempt_grid, cudaStream_t s) {
+static cudaError_t launch_dyn(const fw_sim_t& sim_in, const FwDynArgs& da, int attempt_grid, cudaStream_t s) {
+  typename FwSimArg<T>::type sim;
+  if constexpr (sizeof(T) == 8) sim = sim_in;
+  else {   // fp32 kernels: the configuration + its float image (dynamics.cuh, FwSimX)
+    sim.P = sim_in;
+    const double* src = reinterpret_cast<const double*>(&sim_in);
+    for (size_t k = 0; k < sizeof(fw_sim_t) / 8; ++k) sim.F.v[k] = (float)src[k];
+  }
   const int igrid = (int)((da.n + FW_INIT_BLOCK - 1) / FW_INIT_BLOCK);
   fw_init_kernel<T, Spec><<<igrid, FW_INIT_BLOCK, 0, s>>>(sim, da);
   cudaError_t e = cudaGetLastError();
@@ -1201,6 +1244,16 @@ int fw_host_wait(fw_handle h, int slot, const float** obs, const float** rew, co
 int fw_debug_set_order(fw_handle h, const int32_t* order) {
   if (!h) return fail(FW_ERR_ARG, "null handle");
   h->order = order;
+  return FW_OK;
+}
+
+int fw_debug_timeline(unsigned long long* out8, int reset) {
+  if (out8 && cudaMemcpyFromSymbol(out8, fw_timeline_buf, sizeof(unsigned long long) * 8) != cudaSuccess)
+    return fail(FW_ERR_CUDA, "timeline read");
+  if (reset) {
+    const unsigned long long z[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+    if (cudaMemcpyToSymbol(fw_timeline_buf, z, sizeof(z)) != cudaSuccess) return fail(FW_ERR_CUDA, "timeline reset");
+  }
   return FW_OK;
 }
 

@@ -328,6 +328,11 @@ const char* fw_kernel_variant(fw_handle h);
  * on it; the time does.  The buffer must stay valid while it is set. */
 int fw_debug_set_order(fw_handle h, const int32_t* order);
 
+/* Experiment hook (library built with -DFW_TIMELINE only; otherwise the values never change): out8 = GPU global-timer
+ * stamps in ns {init first start, init last end, attempt first start, attempt last end, env first start, env last end,
+ * first env block past its chunk wait, sum of env block run times}; reset != 0 re-arms the buffer afterwards. */
+int fw_debug_timeline(unsigned long long* out8, int reset);
+
 /* Micro-benchmark: sustained DFMA throughput of this GPU in FLOP/s (roofline denominator, bench.py). */
 int fw_dfma_peak(int device, double* flops_out, double* ms_out);
 
