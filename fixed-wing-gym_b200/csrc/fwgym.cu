@@ -136,7 +136,7 @@ struct FwDynArgs {
   double* cd;          // carry rows [CY_ROWS][stride]
   int32_t* ci;         // carry int rows [CI_ROWS][stride]
   int32_t* long_list;  // [stride] aircraft to start first
-  int32_t* q;          // [Q_N + chunks] queue counters + per-chunk finished counters, zeroed at the start of every step
+  int32_t* q;          // [Q_N + chunks] queue counters + per-chunk finished counters; all zero between steps (fw_init_kernel)
   double long_h;       // initial step sizes below this go on the priority list
   int32_t par_row;     // first per-env model-parameter row of d (FwSpecRand)
   int32_t n_par_rows;
@@ -194,6 +194,10 @@ fw_init_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDy
   const int64_t env = (int64_t)blockIdx.x * FW_INIT_BLOCK + threadIdx.x;
   const bool valid = env < a.n;
   bool is_long = false, init_failed = false;
+  // Queue words are zeroed by the kernels instead of a memset node per step (one launch gap less): the two cursors,
+  // which only the attempt kernel uses, here; the priority-list length and the chunk counters by the env kernel of the
+  // previous step once it has consumed them (fw_create / fw_seed / fw_set_state zero everything).
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.q[Q_LONG_CURSOR] = 0; a.q[Q_NAT_CURSOR] = 0; }
   if (valid) {
     FwEnvCtx c{a.d, a.i, a.stride, env};
     double cmd[3];
@@ -248,10 +252,11 @@ fw_attempt_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const F
   FwKStore<T, FW_DYN_BLOCK> K{reinterpret_cast<T*>(smem_raw)};
   // Every warp of this (fully resident) grid is on an SM by now: let the env kernel's blocks queue up behind us.  They
   // synchronise on the per-chunk counters below, not on this kernel's completion.
-  asm volatile("griddepcontrol.launch_dependents;");
+  // (The priority-list length is read first and the release depends on it: env block 0 zeroes it for the next step.)
+  const int n_long = a.q[Q_LONG_COUNT];     // final: the init kernel has completed
+  asm volatile("griddepcontrol.launch_dependents;" :: "r"(n_long) : "memory");
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int n_long = a.q[Q_LONG_COUNT];     // final: the init kernel has completed
   const int n_nat = (int)a.n;
   FwIvp<T> S;
   FwStepIn<T> in;
@@ -670,6 +675,10 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
       if (++spins > (1u << 22)) { atomicAdd(a.ctr + CTR_WATCHDOG, 1ull); break; }   // ~1 s
     }
     __threadfence();
+    // consumed: zero it for the next step (nothing adds to a complete chunk); block 0 also zeroes the priority-list
+    // length, which every attempt warp read before this kernel could start
+    *FW_CHUNK_DONE(a.q, first) = 0;
+    if (blockIdx.x == 0) a.q[Q_LONG_COUNT] = 0;
   }
   __syncthreads();
 #ifdef FW_TIMELINE
@@ -973,6 +982,7 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
     delete h;
     return fail(FW_ERR_ALLOC, "cudaMalloc (carry) failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  CK(cudaMemset(h->queue, 0, (size_t)h->q_len * sizeof(int32_t)));   // from here on the kernels keep it zeroed (fw_init_kernel)
   CK(cudaMemset(h->carry_d, 0, (size_t)CY_ROWS * h->L.stride * sizeof(double)));
   CK(cudaMemset(h->carry_i, 0, (size_t)CI_ROWS * h->L.stride * sizeof(int32_t)));
   {
@@ -1136,7 +1146,6 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
     CK(cudaEventRecord(pe[0], s));
   }
-  CK(cudaMemsetAsync(h->queue, 0, (size_t)h->q_len * sizeof(int32_t), s));
   CK(launch_dyn_any(h->cfg.precision, h->generic, h->cfg.sim, da, h->attempt_grid, s));
   if (h->profiling) CK(cudaEventRecord(pe[1], s));
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
