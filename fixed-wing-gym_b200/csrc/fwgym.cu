@@ -53,6 +53,7 @@ struct fw_handle_s {
   int overlap;                   // launch the env kernel as a programmatic dependent of the attempt kernel
   int64_t q_len;                 // ints in `queue`: Q_N + chunks
   const int32_t* order;          // fw_debug_set_order
+  int pdl_dyn;                   // attempt kernel launched as a programmatic dependent of the init kernel (FWGYM_PDL_DYN)
   int shape;                     // env / reset kernel instantiation: index into FW_SHAPE_LIST, -1 generic (env_shapes.h)
   double* ep_out;                // caller's episode-metric buffer (fw_set_episode_out)
   // init -> attempt -> env pipeline (see "dynamics kernels")
@@ -141,6 +142,7 @@ struct FwDynArgs {
   int32_t par_row;     // first per-env model-parameter row of d (FwSpecRand)
   int32_t n_par_rows;
   const int32_t* order;   // experiment hook (fw_debug_set_order): adoption order of the natural queue, NULL = identity
+  int32_t pdl;            // the attempt kernel was launched as a programmatic dependent of the init kernel
 };
 
 // ---- action -> actuator commands (fixed_wing.py:349-354,439-459; Actuation.set_and_constrain_commands) ----
@@ -197,6 +199,9 @@ fw_init_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDy
   // Queue words are zeroed by the kernels instead of a memset node per step (one launch gap less): the two cursors,
   // which only the attempt kernel uses, here; the priority-list length and the chunk counters by the env kernel of the
   // previous step once it has consumed them (fw_create / fw_seed / fw_set_state zero everything).
+  // (a.pdl) let the attempt kernel's warps take their places on the SMs as this kernel's blocks retire; they wait for
+  // this grid's completion (griddepcontrol.wait) before they read anything
+  if (a.pdl) asm volatile("griddepcontrol.launch_dependents;");
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.q[Q_LONG_CURSOR] = 0; a.q[Q_NAT_CURSOR] = 0; }
   if (valid) {
     FwEnvCtx c{a.d, a.i, a.stride, env};
@@ -252,6 +257,7 @@ fw_attempt_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const F
   FwKStore<T, FW_DYN_BLOCK> K{reinterpret_cast<T*>(smem_raw)};
   // Every warp of this (fully resident) grid is on an SM by now: let the env kernel's blocks queue up behind us.  They
   // synchronise on the per-chunk counters below, not on this kernel's completion.
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");   // the init kernel has completed and its writes are visible
   // (The priority-list length is read first and the release depends on it: env block 0 zeroes it for the next step.)
   const int n_long = a.q[Q_LONG_COUNT];     // final: the init kernel has completed
   asm volatile("griddepcontrol.launch_dependents;" :: "r"(n_long) : "memory");
@@ -904,8 +910,21 @@ static cudaError_t launch_dyn(const fw_sim_t& sim_in, const FwDynArgs& da, int a
   const int smem = fw_attempt_smem<T, Spec>(da.n_par_rows);
   const int64_t warps = (da.n + FW_DYN_BLOCK - 1) / FW_DYN_BLOCK;
   const int grid = (int)(warps < attempt_grid ? warps : attempt_grid);
-  fw_attempt_kernel<T, Spec><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
-  return cudaGetLastError();
+  if (!da.pdl) {
+    fw_attempt_kernel<T, Spec><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(FW_DYN_BLOCK);
+  lc.dynamicSmemBytes = (size_t)smem;
+  lc.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, fw_attempt_kernel<T, Spec>, sim, da);
 }
 // per device (called from fw_create): opt in to the K-stage shared memory and size the persistent grid
 template <typename T, class Spec>
@@ -999,6 +1018,10 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   h->generic = needs_generic(h->cfg.sim);
   h->shape = pick_shape(h->cfg);
   h->order = nullptr;
+  {
+    const char* e = getenv("FWGYM_PDL_DYN");
+    h->pdl_dyn = e ? atoi(e) : 1;
+  }
   {
     const char* e = getenv("FWGYM_OVERLAP");
     h->overlap = e ? atoi(e) : 1;
@@ -1140,7 +1163,7 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
   FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, h->ctr, h->carry_d, h->carry_i, h->long_list,
-               h->queue, h->long_h, h->L.par_row, h->L.n_par_rows, h->order};
+               h->queue, h->long_h, h->L.par_row, h->L.n_par_rows, h->order, h->pdl_dyn};
   cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
   if (h->profiling) {
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
