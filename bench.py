@@ -36,6 +36,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="fwgym", choices=["fwgym", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--burn-in", type=int, default=200,
+                    help="untimed env steps after the reset, before the warm-up: every env starts its first episode at the "
+                         "same moment, and with random actions the whole batch reaches stall / failure together around "
+                         "step 50-65 (a burst of dopri5 stragglers with 15-35 attempts); after ~200 steps the episode ages "
+                         "are mixed and the step time is the stationary one")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -198,6 +203,12 @@ def run_gpu_arm(a):
     # synthetic policy output: i.i.d. U(-1,1) actions, a fresh batch per step, resident in HBM before timing
     actions = torch.rand((total, n, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    burn_actions = torch.rand((16, n, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+
+    def burn_in():
+        for i in range(a.burn_in):
+            vec.step_tensors(burn_actions[i % 16])
+        torch.cuda.synchronize(dev)
     flush_mode = os.environ.get("FWGYM_BENCH_FLUSH", "write")
     flush_rd = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device=dev) if flush_mode == "write+read" else None
 
@@ -213,6 +224,7 @@ def run_gpu_arm(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    burn_in()
     for i in range(a.warmup):
         vec.step_tensors(actions[i])
     vec.reset_counters()
@@ -276,10 +288,11 @@ def run_gpu_arm(a):
             host_split[1] += time.perf_counter() - tb
             checksum += float(rew[0])
 
-    # same position in the episodes as the device-timed region above: fresh reset, W warm-up steps, then K timed steps
+    # same position in the episodes as the device-timed region above: fresh reset, burn-in, W warm-up steps, K timed steps
     # (the dopri5 work per step drifts as the aircraft of a batch age, so a region further into the episodes would not
     # be comparable)
     vec.reset()
+    burn_in()
     e2e_run(0, a.warmup)
     barrier()
     t0 = time.perf_counter()
@@ -325,7 +338,7 @@ def run_gpu_arm(a):
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "actions": "i.i.d. U(-1,1)^3 per step",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "actions": "i.i.d. U(-1,1)^3 per step", "burn_in_steps": a.burn_in,
                        "l2": "256 MiB memset between timed steps; per-step CUDA events summed"
                              + ("; + 256 MiB read pass (memset's dirty lines written back before the step)"
                                 if flush_mode == "write+read" else ""),

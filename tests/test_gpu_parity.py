@@ -387,9 +387,9 @@ def test_pretrained_mlp_controller_evaluation(built_lib):
     policy gives the same rewards (<= 1e-7: the policy's float64 matmuls sum in a different order on the two sides)
     and episode lengths.  (b) The published evaluation of this controller (eval_res_RL_MLP_none.npy: 100 % success,
     mean episode 270 steps) is compared and REPORTED — like the PID trace it measures the recalled aircraft
-    constants, not the kernels.  Measured: roll 100 %, pitch 37 %, Va 42 %, all 36 % success: a policy
-    trained on true PyFly does NOT transfer to the restated aircraft's longitudinal dynamics (the PID loop does, 100 %),
-    which bounds how far the recalled thrust / pitch-moment constants are from PyFly's."""
+    constants, not the kernels.  Measured: 95 / 100 scenarios succeed (99 / 95 / 98 % roll / pitch / Va)
+    with the calibrated thrust constant; with the recalled one it was 36 / 100, which is how the error was found
+    (oracle/calibrate_thrust.py)."""
     from fwgym_b200 import evaluate
     par = dict(np.load(os.path.join(GOLDEN, "mlp_controller.npz")))
     scen = evaluate.load_test_set(os.path.join(GOLDEN, "test_set_wind_none.npz"))
@@ -437,5 +437,5 @@ def test_pretrained_mlp_controller_evaluation(built_lib):
              s.get("control_variation_all", np.nan), np.nanmean(par["pub_control_variation_all"]),
              np.median(gaps), np.max(gaps)))
     assert np.isfinite(gaps).all()
-    assert s.get("success_roll", 0.0) >= 0.9    # the lateral loop survives the recalled constants; the rest is reported
+    assert s.get("success_all", 0.0) >= 0.85    # a policy trained on true PyFly flies the restated aircraft
     vec.close()
