@@ -63,6 +63,7 @@ struct fw_handle_s {
   int32_t* queue;                // [Q_N]
   int attempt_grid;              // persistent warps of the attempt kernel (resident capacity of the device)
   double long_div, long_h;       // priority threshold on the initial step size: long_h = dt / long_div
+  double long_omega;             // priority threshold on max |omega| in rad/s (FWGYM_LONG_OMEGA, 0 = off)
   std::vector<cudaEvent_t> ev;   // 3 events per profiled step: before dyn, between, after env
   // host-buffer pipeline (fw_host_*): `depth` slots of device staging + pinned host result buffers, copy streams
   struct HostSlot {
@@ -139,6 +140,7 @@ struct FwDynArgs {
   int32_t* long_list;  // [stride] aircraft to start first
   int32_t* q;          // [Q_N + chunks] queue counters + per-chunk finished counters; all zero between steps (fw_init_kernel)
   double long_h;       // initial step sizes below this go on the priority list
+  double long_omega;   // ... and aircraft whose largest body rate (rad/s) exceeds this
   int32_t par_row;     // first per-env model-parameter row of d (FwSpecRand)
   int32_t n_par_rows;
   const int32_t* order;   // experiment hook (fw_debug_set_order): adoption order of the natural queue, NULL = identity
@@ -223,11 +225,16 @@ fw_init_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDy
     for (int kc = 0; kc < FW_N_KC; ++kc) cd[(CY_K0 + kc) * a.stride] = (double)f0[fw_kc_to_ode(kc)];
 #pragma unroll
     for (int j = 0; j < 3; ++j) { cd[(CY_KP + j) * a.stride] = (double)f0[7 + j]; cd[(CY_CMD + j) * a.stride] = cmd[j]; }
-    cd[CY_H * a.stride] = (double)h_abs;
+    // Priority start: a tiny first step (the 1e-6 start after a reset) or, when FWGYM_LONG_OMEGA is
+    // set, fast body rates (85 % of the aircraft that go on to need >= 12 attempts rotate faster than 3 rad/s about some
+    // axis at the start of the step, 17 % of all do; measured: no gain, off by default).  Membership is carried by the
+    // SIGN of the parked step size, so the attempt kernel's natural-order visit can skip list members without a load.
+    const double wmax = fmax(fabs((double)y[4]), fmax(fabs((double)y[5]), fabs((double)y[6])));
+    is_long = !failv && (double)h_abs > 0.0 && ((double)h_abs < a.long_h || wmax > a.long_omega);
+    cd[CY_H * a.stride] = is_long ? -(double)h_abs : (double)h_abs;
     ci[CI_FAIL * a.stride] = failv;     // != 0: ConstraintException inside RK45.__init__; nothing left to integrate
     ci[CI_ATTEMPTS * a.stride] = 0;
     ci[CI_ACCEPTED * a.stride] = 0;
-    is_long = !failv && (double)h_abs < a.long_h;
     init_failed = failv != 0;
   }
   const unsigned full = 0xffffffffu;
@@ -317,11 +324,12 @@ fw_attempt_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const F
         if (e >= 0) {
           const double* cd = a.cd + e;
           const int32_t* ci = a.ci + e;
-          const double h0 = cd[CY_H * a.stride];
+          const double h0s = cd[CY_H * a.stride];   // negative: on the priority list
+          const double h0 = fabs(h0s);
           const int failv = ci[CI_FAIL * a.stride];
           // skipped: aircraft that raised inside RK45.__init__ (the init kernel parked that result), and the
           // natural-order visit of an aircraft that is on the priority list
-          const bool skip = failv != 0 || (!from_long && h0 < a.long_h);
+          const bool skip = failv != 0 || (!from_long && h0s < 0.0);
           if (!skip) {
             env = e;
             par_base = a.d + (int64_t)a.par_row * a.stride + e;
@@ -1010,6 +1018,9 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
     const char* e = getenv("FWGYM_LONG_DIV");
     h->long_div = e ? atof(e) : 32.0;
     h->long_h = h->long_div > 0 ? h->cfg.sim.dt / h->long_div : 0.0;
+    const char* w = getenv("FWGYM_LONG_OMEGA");
+    h->long_omega = w ? atof(w) : 0.0;      // off by default: measured 207.1 (3 rad/s) / 208.0 (5) vs 208.5 us per step
+    if (!(h->long_omega > 0)) h->long_omega = 1e300;
   }
   CK(cudaMemset(h->d, 0, db));
   CK(cudaMemset(h->i, 0, ib));
@@ -1163,7 +1174,7 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
   FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, h->ctr, h->carry_d, h->carry_i, h->long_list,
-               h->queue, h->long_h, h->L.par_row, h->L.n_par_rows, h->order, h->pdl_dyn};
+               h->queue, h->long_h, h->long_omega, h->L.par_row, h->L.n_par_rows, h->order, h->pdl_dyn};
   cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
   if (h->profiling) {
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
