@@ -200,7 +200,7 @@ fw_init_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDy
   bool is_long = false, init_failed = false;
   // Queue words are zeroed by the kernels instead of a memset node per step (one launch gap less): the two cursors,
   // which only the attempt kernel uses, here; the priority-list length and the chunk counters by the env kernel of the
-  // previous step once it has consumed them (fw_create / fw_seed / fw_set_state zero everything).
+  // previous step once it has consumed them (fw_create, a full fw_reset and fw_set_state zero everything).
   // (a.pdl) let the attempt kernel's warps take their places on the SMs as this kernel's blocks retire; they wait for
   // this grid's completion (griddepcontrol.wait) before they read anything
   if (a.pdl) asm volatile("griddepcontrol.launch_dependents;");
@@ -1161,6 +1161,9 @@ int fw_reset(fw_handle h, const uint8_t* mask, const double* init_state, const d
                 (uint32_t)h->offset, obs_out, obs64_out, fw_obs_dim(h), h->ctr};
   const int grid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
   CK(launch_reset(h->shape, grid, s, h->cfg.env, h->cfg.sim, h->L, a));
+  // a full reset also re-arms the step queue (the kernels keep it zeroed between steps; this covers a step that was
+  // abandoned half-way, e.g. after an error)
+  if (!mask) CK(cudaMemsetAsync(h->queue, 0, (size_t)h->q_len * sizeof(int32_t), s));
   h->last_stream = s;
   return FW_OK;
 }
@@ -1338,6 +1341,7 @@ int fw_set_state(fw_handle h, const double* in, void* stream) {
   CK(cudaSetDevice(h->device));
   const int grid = (int)((h->n + 255) / 256);
   fw_import_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, h->i, h->L.stride, h->n, h->L.d_rows, h->L.i_rows, in);
+  CK(cudaMemsetAsync(h->queue, 0, (size_t)h->q_len * sizeof(int32_t), (cudaStream_t)stream));   // re-arm the step queue
   CK(cudaGetLastError());
   return FW_OK;
 }
