@@ -58,4 +58,40 @@ CASES = {
     # action space bounded by the actuator limits (low / high null), bounds_outside_cost
     "cnn": dict(config="fixed_wing_config_cnn.json", config_kw={"steps_max": 40},
                 sim_kw={"turbulence": True, "turbulence_intensity": "moderate"}, n=4, steps=60, amp=1.3),
+    # ---- reward / target branches no shipped configuration reaches (fixed_wing_config_zoo.json, oracle/make_configs.py) ----
+    # every reward class (action value / delta / bound, state value / error / int_error, success timesteps / constant,
+    # step, goal per_state / all), three function classes, potential form with shaping memory, success "new"
+    "reward_zoo": dict(config="fixed_wing_config_zoo.json",
+                       config_kw={"reward": {"form": "potential"},
+                                  "target": {"success_streak_req": 5, "success_streak_fraction": 0.6, "on_success": "new",
+                                             "states": {0: {"bound": 120}, 1: {"bound": 60}, 2: {"bound": 20}}}},
+                       sim_kw={"turbulence": False}, n=6, steps=50, amp=1.2),
+    # absolute form; a tight pitch bound makes goal per_state differ from goal all
+    "reward_zoo_abs": dict(config="fixed_wing_config_zoo.json",
+                           config_kw={"steps_max": 25,
+                                      "target": {"success_streak_req": 6, "success_streak_fraction": 0.5,
+                                                 "states": {0: {"bound": 100}, 1: {"bound": 4}, 2: {"bound": 20}}}},
+                           sim_kw={"turbulence": True, "turbulence_intensity": "light"}, n=4, steps=40, amp=1.0),
+    # linear targets (fixed_wing.py:495-500,977-978): fast roll slopes cross +-pi (wrap, :988-989); pitch linear under
+    # the Va compensate class (:944-946); resampled mid-episode and at resets
+    "target_linear": dict(config="fixed_wing_config_zoo.json",
+                          config_kw={"steps_max": 70,
+                                     "target": {"resample_every": 45,
+                                                "states": {0: {"class": "linear", "slope_low": 500, "slope_high": 800},
+                                                           1: {"class": "linear"}}}},
+                          sim_kw={"turbulence": False}, n=6, steps=90, amp=0.8),
+    # sinusoidal targets (:501-507,979-980) incl. sinusoidal pitch under Va compensate (bias branch, :947-948);
+    # resampling at steps_count > 0 exercises the bias formula
+    "target_sinusoidal": dict(config="fixed_wing_config_zoo.json",
+                              config_kw={"steps_max": 60,
+                                         "target": {"resample_every": 25,
+                                                    "states": {0: {"class": "sinusoidal"}, 1: {"class": "sinusoidal"}}}},
+                              sim_kw={"turbulence": False}, n=6, steps=80, amp=0.8),
+    # sinusoidal Va, linear pitch, constant roll, 3-row observation (target / error rings carry the moving targets)
+    "target_mixed": dict(config="fixed_wing_config_zoo.json",
+                         config_kw={"steps_max": 35, "observation": {"length": 3, "step": 1},
+                                    "target": {"states": {1: {"class": "linear"},
+                                                          2: {"class": "sinusoidal", "amplitude_low": 1.0,
+                                                              "amplitude_high": 3.0}}}},
+                         sim_kw={"turbulence": True, "turbulence_intensity": "moderate"}, n=4, steps=50, amp=0.8),
 }

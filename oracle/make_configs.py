@@ -46,6 +46,59 @@ def write_randomised():
         f.write("\n")
 
 
+# Reward / target "zoo" (fixed_wing.py:495-507, :684-746, :948, :977-985): no shipped configuration uses the reward
+# classes action.value / state.value / success / step / goal, the quadratic function class, or linear / sinusoidal
+# targets, and config_kw cannot ADD keys, so the parity cases get their own file: the default configuration with one
+# reward factor per branch (three terms), and the slope / amplitude / period keys present on every target state so that
+# a case can switch a state's class with config_kw.
+ZOO_FACTORS = [
+    {"class": "state", "type": "error", "name": "roll", "function_class": "linear", "scaling": 3.2, "max": 0.3,
+     "shaping": True, "sign": -1},
+    {"class": "state", "type": "error", "name": "pitch", "function_class": "quadratic", "scaling": 2.0,
+     "shaping": True, "sign": -1},
+    {"class": "state", "type": "error", "name": "Va", "function_class": "exponential", "scaling": 400.0,
+     "shaping": True, "sign": -1},
+    {"class": "action", "type": "delta", "name": "action", "function_class": "linear", "scaling": 60, "window_size": 5,
+     "shaping": False, "sign": -1},
+    {"class": "action", "type": "bound", "name": "action_bound", "function_class": "linear", "scaling": 1,
+     "shaping": False, "sign": -1},
+    {"class": "action", "type": "value", "name": "action_value", "function_class": "linear", "scaling": 30,
+     "max": 0.08, "shaping": False, "sign": -1},
+    {"class": "state", "type": "value", "name": "omega_q", "function_class": "quadratic", "scaling": 10.0,
+     "shaping": False, "sign": -1},
+    {"class": "state", "type": "value", "name": "Va", "function_class": "exponential", "scaling": 9000.0,
+     "shaping": False, "sign": -1},
+    {"class": "success", "name": "success_time", "value": "timesteps", "function_class": "linear", "scaling": 2000,
+     "shaping": False, "sign": 1},
+    {"class": "success", "name": "success_bonus", "value": 5.0, "function_class": "quadratic", "scaling": 50,
+     "shaping": False, "sign": 1},
+    {"class": "step", "name": "step", "value": 1, "function_class": "linear", "scaling": 100, "shaping": False,
+     "sign": -1},
+    {"class": "goal", "type": "per_state", "name": "goal_state", "value": 0.3, "function_class": "linear",
+     "scaling": 1, "shaping": False, "sign": 1},
+    {"class": "goal", "type": "all", "name": "goal_all", "value": 1.0, "function_class": "linear", "scaling": 2,
+     "shaping": True, "sign": 1},
+    {"class": "state", "type": "int_error", "name": "roll", "function_class": "linear", "scaling": 300.0, "max": 0.2,
+     "shaping": False, "sign": -1},
+]
+ZOO_TARGET_KEYS = {"slope_low": 1.0, "slope_high": 5.0, "amplitude_low": 2.0, "amplitude_high": 8.0,
+                   "period_low": 40, "period_high": 90}
+
+
+def write_zoo():
+    with open(os.path.join(PARAMS, "fixed_wing_config.json")) as f:
+        cfg = json.load(f)
+    cfg["integration_window"] = 10
+    cfg["reward"]["factors"] = ZOO_FACTORS
+    cfg["reward"]["terms"] = [{"function_class": "linear", "weight": 1}, {"function_class": "exponential", "weight": 0.5},
+                              {"function_class": "quadratic", "weight": 0.25}]
+    for st in cfg["target"]["states"]:
+        st.update(ZOO_TARGET_KEYS)
+    with open(os.path.join(PARAMS, "fixed_wing_config_zoo.json"), "w") as f:
+        json.dump(cfg, f, sort_keys=True, separators=(",", ":"))
+        f.write("\n")
+
+
 def main():
     for out, src in SOURCES.items():
         with open(os.path.join(REF, src)) as f:
@@ -55,6 +108,7 @@ def main():
             json.dump(cfg, f, sort_keys=True, separators=(",", ":"))
             f.write("\n")
     write_randomised()
+    write_zoo()
     ex = os.path.join(REF, "gym_fixed_wing", "examples")
     scen = np.load(os.path.join(ex, "test_sets", "test_set_wind_none_step20-20-3.npy"), allow_pickle=True)
     skeys = sorted(scen[0]["state"].keys())
