@@ -62,6 +62,8 @@ struct fw_handle_s {
   int32_t* long_list;            // [stride]
   int32_t* queue;                // [Q_N]
   int attempt_grid;              // persistent warps of the attempt kernel (resident capacity of the device)
+  int pair;                      // fp64 attempt kernel with two warps per 32 aircraft (attempt_pair.cuh; FWGYM_PAIR=1, off by default: measured slower)
+  int pair_grid;                 // its persistent blocks
   double long_div, long_h;       // priority threshold on the initial step size: long_h = dt / long_div
   double long_omega;             // priority threshold on max |omega| in rad/s (FWGYM_LONG_OMEGA, 0 = off)
   std::vector<cudaEvent_t> ev;   // 3 events per profiled step: before dyn, between, after env
@@ -145,6 +147,9 @@ struct FwDynArgs {
   int32_t n_par_rows;
   const int32_t* order;   // experiment hook (fw_debug_set_order): adoption order of the natural queue, NULL = identity
   int32_t pdl;            // the attempt kernel was launched as a programmatic dependent of the init kernel
+  int32_t pair;           // host only: launch fw_attempt_pair_kernel with pair_grid blocks
+  int32_t pair_grid;
+  int32_t pair_mix;       // alternate which warp of a block plays role T (FWGYM_PAIR_MIX, default on)
 };
 
 // ---- action -> actuator commands (fixed_wing.py:349-354,439-459; Actuation.set_and_constrain_commands) ----
@@ -403,6 +408,8 @@ fw_attempt_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const F
   }
   FW_TL_END(1);
 }
+
+#include "attempt_pair.cuh"   // fw_attempt_pair_kernel: two warps per 32 aircraft (fp64, FwSpecShipped / FwSpecGeneric)
 
 // ---- PyFly._set_states_from_ode_solution(save=True) + airspeed factors + next gust column (env kernel prologue) ----
 // PyFly Variable.apply_conditions with the variable's condition FLAGS taken from the shape (a literal in a fixed
@@ -915,8 +922,23 @@ static cudaError_t launch_dyn(const fw_sim_t& sim_in, const FwDynArgs& da, int a
   fw_init_kernel<T, Spec><<<igrid, FW_INIT_BLOCK, 0, s>>>(sim, da);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int smem = fw_attempt_smem<T, Spec>(da.n_par_rows);
   const int64_t warps = (da.n + FW_DYN_BLOCK - 1) / FW_DYN_BLOCK;
+  if constexpr (sizeof(T) == 8 && !Spec::rand) {
+    if (da.pair) {
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3((unsigned)(warps < da.pair_grid ? warps : da.pair_grid));
+      lc.blockDim = dim3(FW_PAIR_THREADS);
+      lc.dynamicSmemBytes = (size_t)FW_PAIR_SMEM_BYTES;
+      lc.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = at;
+      lc.numAttrs = da.pdl ? 1 : 0;
+      return cudaLaunchKernelEx(&lc, fw_attempt_pair_kernel<Spec>, sim, da);
+    }
+  }
+  const int smem = fw_attempt_smem<T, Spec>(da.n_par_rows);
   const int grid = (int)(warps < attempt_grid ? warps : attempt_grid);
   if (!da.pdl) {
     fw_attempt_kernel<T, Spec><<<grid, FW_DYN_BLOCK, smem, s>>>(sim, da);
@@ -936,7 +958,7 @@ static cudaError_t launch_dyn(const fw_sim_t& sim_in, const FwDynArgs& da, int a
 }
 // per device (called from fw_create): opt in to the K-stage shared memory and size the persistent grid
 template <typename T, class Spec>
-static cudaError_t prepare_dyn(int sm_count, int n_par_rows, int* grid_out) {
+static cudaError_t prepare_dyn(int sm_count, int n_par_rows, int* grid_out, int* pair_grid_out) {
   const int smem = fw_attempt_smem<T, Spec>(n_par_rows);
   cudaError_t e = cudaFuncSetAttribute(fw_attempt_kernel<T, Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -944,6 +966,18 @@ static cudaError_t prepare_dyn(int sm_count, int n_par_rows, int* grid_out) {
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fw_attempt_kernel<T, Spec>, FW_DYN_BLOCK, smem);
   if (e != cudaSuccess) return e;
   if (grid_out) *grid_out = per_sm * sm_count;
+  if constexpr (sizeof(T) == 8 && !Spec::rand) {
+    if (pair_grid_out) {
+      e = cudaFuncSetAttribute(fw_attempt_pair_kernel<Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_PAIR_SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(fw_attempt_pair_kernel<Spec>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (e != cudaSuccess) return e;
+      int pb = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, fw_attempt_pair_kernel<Spec>, FW_PAIR_THREADS, FW_PAIR_SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+      *pair_grid_out = pb * sm_count;
+    }
+  } else if (pair_grid_out) *pair_grid_out = 0;
   return cudaSuccess;
 }
 
@@ -958,15 +992,15 @@ static cudaError_t launch_dyn_any(int precision, int spec, const fw_sim_t& sim, 
   if (spec == 1) return launch_dyn<float, FwSpecGeneric>(sim, da, grid, s);
   return launch_dyn<float, FwSpecRand>(sim, da, grid, s);
 }
-static cudaError_t prepare_dyn_any(int precision, int spec, int sms, int n_par_rows, int* grid_out) {
+static cudaError_t prepare_dyn_any(int precision, int spec, int sms, int n_par_rows, int* grid_out, int* pair_grid_out) {
   if (precision == 0) {
-    if (spec == 0) return prepare_dyn<double, FwSpecShipped>(sms, n_par_rows, grid_out);
-    if (spec == 1) return prepare_dyn<double, FwSpecGeneric>(sms, n_par_rows, grid_out);
-    return prepare_dyn<double, FwSpecRand>(sms, n_par_rows, grid_out);
+    if (spec == 0) return prepare_dyn<double, FwSpecShipped>(sms, n_par_rows, grid_out, pair_grid_out);
+    if (spec == 1) return prepare_dyn<double, FwSpecGeneric>(sms, n_par_rows, grid_out, pair_grid_out);
+    return prepare_dyn<double, FwSpecRand>(sms, n_par_rows, grid_out, pair_grid_out);
   }
-  if (spec == 0) return prepare_dyn<float, FwSpecShipped>(sms, n_par_rows, grid_out);
-  if (spec == 1) return prepare_dyn<float, FwSpecGeneric>(sms, n_par_rows, grid_out);
-  return prepare_dyn<float, FwSpecRand>(sms, n_par_rows, grid_out);
+  if (spec == 0) return prepare_dyn<float, FwSpecShipped>(sms, n_par_rows, grid_out, pair_grid_out);
+  if (spec == 1) return prepare_dyn<float, FwSpecGeneric>(sms, n_par_rows, grid_out, pair_grid_out);
+  return prepare_dyn<float, FwSpecRand>(sms, n_par_rows, grid_out, pair_grid_out);
 }
 
 extern "C" {
@@ -1042,10 +1076,14 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
     CK(cudaGetDeviceProperties(&prop, device));
     const int sms = prop.multiProcessorCount;
     int g = 0;
-    CK(prepare_dyn_any(h->cfg.precision, h->generic, sms, h->L.n_par_rows, &g));
+    int pg = 0;
+    CK(prepare_dyn_any(h->cfg.precision, h->generic, sms, h->L.n_par_rows, &g, &pg));
     const char* e = getenv("FWGYM_ATTEMPT_WARPS_PER_SM");
-    if (e && atoi(e) > 0) g = atoi(e) * sms;
+    if (e && atoi(e) > 0) { g = atoi(e) * sms; if (pg > 0) pg = atoi(e) * sms; }
     h->attempt_grid = g > 0 ? g : sms;
+    h->pair_grid = pg;
+    const char* pe = getenv("FWGYM_PAIR");
+    h->pair = (pg > 0 && pe && atoi(pe) != 0) ? 1 : 0;   // opt-in: measured slower than one thread per aircraft
   }
   *out = h;
   return FW_OK;
@@ -1083,9 +1121,12 @@ int fw_set_config(fw_handle h, const fw_config_t* cfg) {
     cudaDeviceProp prop;
     CK(cudaSetDevice(h->device));
     CK(cudaGetDeviceProperties(&prop, h->device));
-    int g = 0;
-    CK(prepare_dyn_any(h->cfg.precision, h->generic, prop.multiProcessorCount, h->L.n_par_rows, &g));
+    int g = 0, pg = 0;
+    CK(prepare_dyn_any(h->cfg.precision, h->generic, prop.multiProcessorCount, h->L.n_par_rows, &g, &pg));
     if (g > 0) h->attempt_grid = g;
+    h->pair_grid = pg;
+    const char* pe = getenv("FWGYM_PAIR");
+    h->pair = (pg > 0 && pe && atoi(pe) != 0) ? 1 : 0;   // opt-in: measured slower than one thread per aircraft
   }
   h->long_h = h->long_div > 0 ? h->cfg.sim.dt / h->long_div : 0.0;
   return FW_OK;
@@ -1128,6 +1169,7 @@ const char* fw_kernel_variant(fw_handle h) {
            shape_name(h->shape));
   return buf;
 }
+int fw_attempt_warps_per_group(fw_handle h) { return h ? (h->pair ? 2 : 1) : 0; }
 int64_t fw_state_rows(fw_handle h) { return h ? h->L.d_rows + h->L.i_rows : 0; }
 
 const char* fw_state_row_name(fw_handle h, int64_t r) {
@@ -1177,7 +1219,8 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
   FwDynArgs da{h->d, h->i, h->L.stride, h->n, actions, actions_f64, h->ctr, h->carry_d, h->carry_i, h->long_list,
-               h->queue, h->long_h, h->long_omega, h->L.par_row, h->L.n_par_rows, h->order, h->pdl_dyn};
+               h->queue, h->long_h, h->long_omega, h->L.par_row, h->L.n_par_rows, h->order, h->pdl_dyn, h->pair,
+               h->pair_grid, getenv("FWGYM_PAIR_MIX") ? atoi(getenv("FWGYM_PAIR_MIX")) : 1};
   cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
   if (h->profiling) {
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->ev.push_back(pe[k]); }
