@@ -1393,7 +1393,9 @@ int fw_last_attempts(fw_handle h, int32_t* out, void* stream) {
   if (!h || !out) return fail(FW_ERR_ARG, "null argument");
   CK(cudaSetDevice(h->device));
   const int grid = (int)((h->n + 255) / 256);
-  fw_gather_i32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->i, h->L.stride, h->n, I_LASTK, out);
+  // the carry row, not I_LASTK: an env that finished in the step was reset on the spot (I_LASTK = 0), the carry row still
+  // holds the attempts of the step that ended its episode (incl. the attempt a ConstraintException cut short)
+  fw_gather_i32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->carry_i, h->L.stride, h->n, CI_ATTEMPTS, out);
   CK(cudaGetLastError());
   return FW_OK;
 }

@@ -273,7 +273,7 @@ int fw_set_state(fw_handle h, const double* in, void* stream);
 /* name of row r of the state matrix ("q0", "omega_p", "steps_count", ...), NULL when out of range */
 const char* fw_state_row_name(fw_handle h, int64_t r);
 
-/* Per-env dopri5 attempt count of the last step: device int32 [N]. */
+/* Per-env dopri5 attempt count of the last step (also for envs whose episode ended in it): device int32 [N]. */
 int fw_last_attempts(fw_handle h, int32_t* out, void* stream);
 
 /* Counters (synchronises the stream it was last used on). */
@@ -324,8 +324,8 @@ int fw_launches_per_step(fw_handle h);
 const char* fw_kernel_variant(fw_handle h);
 
 /* Warps that share one group of 32 aircraft in the dopri5 attempt kernel: 1 = one thread per aircraft (default),
- * 2 = fw_attempt_pair_kernel (csrc/attempt_pair.cuh; fp64 without per-env model parameters, opt-in with FWGYM_PAIR=1:
- * parity-tested, measured slower). */
+ * 2 = the two-warp kernel of csrc/attempt_pair.cuh; fp64 without per-env model parameters, opt-in with FWGYM_PAIR=1:
+ * parity-tested, measured slower, DESIGN.md 4.4. */
 int fw_attempt_warps_per_group(fw_handle h);
 
 /* Experiment hook (scheduling studies): `order` is a device int32 [N] permutation of the env ids, the

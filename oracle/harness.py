@@ -72,8 +72,11 @@ class OracleRunner:
         """-> (obs, reward, done, info); on done with auto_reset the returned obs is the post-reset one and
         info["terminal_observation"] the terminal one (SubprocVecEnv semantics, train_rl_controller.py:223)."""
         self._begin()
+        evals0 = self.env.simulator.n_rhs_evals
         obs, rew, done, info = self.env.step(np.asarray(action, dtype=np.float64))
-        self.nfev.append(self.env.simulator.last_step_nfev)
+        # right-hand-side evaluations of THIS step, counted at the call (sol.nfev is lost when a ConstraintException
+        # leaves solve_ivp)
+        self.nfev.append(self.env.simulator.n_rhs_evals - evals0)
         self.ep_return += float(rew)         # what a Monitor wrapper would report as episode "r"
         if done and self.on_done is not None:
             self.on_done(self.env, info)     # before the auto-reset wipes the episode's histories
@@ -84,7 +87,10 @@ class OracleRunner:
         return obs, rew, done, info
 
     def attempts_last(self):
-        return (self.nfev[-1] - 2) // 6
+        """dopri5 step attempts of the last env step.  RK45.__init__ takes 2 evaluations and every attempt 6; an
+        attempt cut short by a ConstraintException (raised inside the RHS, counted by scipy before the call) still
+        counts, so a failing step reports the attempt it failed in."""
+        return -((2 - self.nfev[-1]) // 6)
 
     def ode_state(self):
         """The 19-vector PyFly would start the next step from + derived values, for state parity checks."""
