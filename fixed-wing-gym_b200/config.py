@@ -35,13 +35,19 @@ class ConfigError(ValueError):
     pass
 
 
-def set_config_attrs(parent, kws):
-    """fixed_wing.py:24-29: dict values recurse; so do values addressed into a list (int keys)."""
-    for attr, val in kws.items():
-        if isinstance(val, dict) or isinstance(parent[attr], list):
-            set_config_attrs(parent[attr], val)
-        else:
-            parent[attr] = val
+def apply_overrides(tree, overrides):
+    """`config_kw` semantics of FixedWingAircraft.__init__ (fixed_wing.py:24-35): an override tree is merged into the
+    parsed JSON; a dict value descends into the existing node, and so does ANY value addressed into a list (integer
+    keys pick list elements, e.g. {"states": {6: {"value": "integrator"}}}); everything else replaces the leaf.  Keys
+    must already exist (KeyError otherwise, like the reference: overrides cannot add entries)."""
+    pending = [(tree, overrides)]
+    while pending:
+        node, patch = pending.pop()
+        for key, val in patch.items():
+            if isinstance(val, dict) or isinstance(node[key], list):
+                pending.append((node[key], val))
+            else:
+                node[key] = val
 
 
 def _set_sim_config_attrs(parent, kws):
@@ -154,7 +160,7 @@ class CompiledConfig:
         with open(config_path) as f:
             self.cfg = json.load(f)
         if config_kw is not None:
-            set_config_attrs(self.cfg, copy.deepcopy(config_kw))
+            apply_overrides(self.cfg, copy.deepcopy(config_kw))
         sim_config_kw = dict(sim_config_kw or {})
         sim_config_kw.update({"actuation": {"inputs": [a["name"] for a in self.cfg["action"]["states"]]}})
         sim_config_kw["turbulence_sim_length"] = self.cfg["steps_max"]
@@ -192,8 +198,6 @@ class CompiledConfig:
             if any(getattr(v, a) is not None for a in ("value_min", "value_max", "constraint_min", "constraint_max")) or v.wrap:
                 raise ConfigError("value limits / constraints on %s are not supported (position stage states are "
                                   "never formed in the integrator)" % n)
-        if self.cfg["reward"].get("randomize_scaling", False):
-            raise ConfigError("reward.randomize_scaling is not supported yet (SURVEY §8f)")
         self._rand_plan()   # raises on simulator-parameter randomisation entries the device path cannot honour
         if self.sim_cfg["turbulence"] and not self.cfg["steps_max"] > 0:
             raise ConfigError("turbulence needs steps_max > 0 (turbulence_sim_length = steps_max, fixed_wing.py:40)")
@@ -277,72 +281,67 @@ class CompiledConfig:
         return plan, slot1, n
 
     # ------------------------------------------------------------------------- fixed_wing.py:57-191 (spaces etc.)
-    def _build_spaces(self):
-        cfg = self.cfg
-        self.obs_norm = cfg["observation"].get("normalize", False)
-        obs_low, obs_high = [], []
-        for obs_var in cfg["observation"]["states"]:
-            high = obs_var.get("high", None)
-            if high is None:
-                st = self.state[obs_var["name"]]
-                high = st.value_max if st.value_max is not None else (
-                    st.constraint_max if st.constraint_max is not None else F32_MAX)
-            elif obs_var.get("convert_to_radians", False):
-                high = np.radians(high)
-            low = obs_var.get("low", None)
-            if low is None:
-                st = self.state[obs_var["name"]]
-                low = st.value_min if st.value_min is not None else (
-                    st.constraint_min if st.constraint_min is not None else -F32_MAX)
-            elif obs_var.get("convert_to_radians", False):
-                low = np.radians(low)
-            bounded = high != F32_MAX and low != -F32_MAX
-            if obs_var["type"] == "target" and obs_var["value"] == "relative":
-                obs_high.append(high - low if bounded else F32_MAX)
-                obs_low.append(low - high if bounded else -F32_MAX)
-            else:
-                obs_high.append(high)
-                obs_low.append(low)
-            if self.obs_norm:
-                if obs_var.get("mean", None) is None:
-                    obs_var["mean"] = high - low if bounded else 0
-                if obs_var.get("var", None) is None:
-                    obs_var["var"] = (high - low) / (4 ** 2) if bounded else 1
-        length, shape = cfg["observation"]["length"], cfg["observation"]["shape"]
-        if length > 1:
-            if shape == "vector":
-                obs_low, obs_high = obs_low * length, obs_high * length
-            elif shape == "matrix":
-                obs_low, obs_high = [obs_low] * length, [obs_high] * length
-            else:
-                raise ConfigError("observation.shape must be vector or matrix")
-        self.observation_low = np.array(obs_low, dtype=np.float64)
-        self.observation_high = np.array(obs_high, dtype=np.float64)
+    def _limit(self, state_name, side):
+        """Bound of a simulator state for the spaces: its value limit, else its constraint, else +-float32 max."""
+        st = self.state[state_name]
+        for attr in ("value_" + side, "constraint_" + side):
+            if getattr(st, attr) is not None:
+                return getattr(st, attr)
+        return F32_MAX if side == "max" else -F32_MAX
 
-        a_low, a_high, s_low, s_high = [], [], [], []
-        for av in cfg["action"]["states"]:
-            st = self.state[av["name"]]
-            state_high = st.value_max if st.value_max is not None else (
-                st.constraint_max if st.constraint_max is not None else F32_MAX)
-            state_low = st.value_min if st.value_min is not None else (
-                st.constraint_min if st.constraint_min is not None else -F32_MAX)
-            sh, sl = av.get("high", None), av.get("low", None)
-            s_high.append(F32_MAX if sh == "max" else (state_high if sh is None else sh))
-            s_low.append(-F32_MAX if sl == "max" else (state_low if sl is None else sl))
-            a_high.append(state_high)
-            a_low.append(state_low)
-        self.action_scale_to_low = np.array(a_low, dtype=np.float64)
-        self.action_scale_to_high = np.array(a_high, dtype=np.float64)
-        self.action_space_low = np.array(s_low, dtype=np.float64)
-        self.action_space_high = np.array(s_high, dtype=np.float64)
-        self.scale_actions = cfg["action"].get("scale_space", False)
+    def _observation_bounds(self, var):
+        """(low, high) of one observation variable: the configured numbers (degrees converted when asked) or the state's
+        limits; a relative target value spans the difference of the two."""
+        rad = var.get("convert_to_radians", False)
+        ends = {}
+        for key, side in (("high", "max"), ("low", "min")):
+            given = var.get(key, None)
+            ends[key] = self._limit(var["name"], side) if given is None else (np.radians(given) if rad else given)
+        low, high = ends["low"], ends["high"]
+        bounded = high != F32_MAX and low != -F32_MAX
+        if self.obs_norm:       # defaults of the normalisation constants are written back into the config (:101-105)
+            if var.get("mean", None) is None:
+                var["mean"] = high - low if bounded else 0
+            if var.get("var", None) is None:
+                var["var"] = (high - low) / (4 ** 2) if bounded else 1
+        if var["type"] == "target" and var["value"] == "relative":
+            return (low - high, high - low) if bounded else (-F32_MAX, F32_MAX)
+        return low, high
+
+    def _build_spaces(self):
+        ocfg, acfg = self.cfg["observation"], self.cfg["action"]
+        self.obs_norm = ocfg.get("normalize", False)
+        bounds = [self._observation_bounds(var) for var in ocfg["states"]]
+        row_low, row_high = [b[0] for b in bounds], [b[1] for b in bounds]
+        if ocfg["length"] > 1:
+            if ocfg["shape"] not in ("vector", "matrix"):
+                raise ConfigError("observation.shape must be vector or matrix")
+            tile = (lambda r: r * ocfg["length"]) if ocfg["shape"] == "vector" else (lambda r: [r] * ocfg["length"])
+            row_low, row_high = tile(row_low), tile(row_high)
+        self.observation_low = np.array(row_low, dtype=np.float64)
+        self.observation_high = np.array(row_high, dtype=np.float64)
+
+        names = [av["name"] for av in acfg["states"]]
+        to_low = [self._limit(n, "min") for n in names]
+        to_high = [self._limit(n, "max") for n in names]
+
+        def space_end(av, key, fallback, unbounded):     # "max": no bound; null: the actuator's own limit; else the number
+            v = av.get(key, None)
+            return unbounded if v == "max" else (fallback if v is None else v)
+        self.action_scale_to_low = np.array(to_low, dtype=np.float64)
+        self.action_scale_to_high = np.array(to_high, dtype=np.float64)
+        self.action_space_low = np.array([space_end(av, "low", lo, -F32_MAX) for av, lo in zip(acfg["states"], to_low)],
+                                         dtype=np.float64)
+        self.action_space_high = np.array([space_end(av, "high", hi, F32_MAX) for av, hi in zip(acfg["states"], to_high)],
+                                          dtype=np.float64)
+        self.scale_actions = acfg.get("scale_space", False)
         self.action_bounds_max = self.action_bounds_min = None
-        if cfg["action"].get("bounds_multiplier", None) is not None:
-            m = cfg["action"]["bounds_multiplier"]
-            self.action_bounds_max = np.full(3, cfg["action"].get("scale_high", 1)) * m
-            self.action_bounds_min = np.full(3, cfg["action"].get("scale_low", -1)) * m
-        self.goal_enabled = cfg["target"]["success_streak_req"] > 0
-        self._bounded_targets = {t["name"] for t in cfg["target"]["states"] if t.get("bound", None) is not None}
+        mult = acfg.get("bounds_multiplier", None)
+        if mult is not None:
+            self.action_bounds_max = np.full(3, acfg.get("scale_high", 1)) * mult
+            self.action_bounds_min = np.full(3, acfg.get("scale_low", -1)) * mult
+        self.goal_enabled = self.cfg["target"]["success_streak_req"] > 0
+        self._bounded_targets = {t["name"] for t in self.cfg["target"]["states"] if t.get("bound", None) is not None}
 
     # ------------------------------------------------------------------------------------ fixed_wing.py:224-285
     def goal_has_bound(self, target_name):
@@ -350,44 +349,56 @@ class CompiledConfig:
         return target_name in self._bounded_targets
 
     def set_curriculum_level(self, level):
+        """fixed_wing.py:224-285: `level` in [0, 1] shrinks every configured RANGE towards its midpoint - the init / value
+        ranges of the simulator states listed under simulator.states and the target sampling ranges - and picks
+        list-valued target settings by level."""
         assert 0 <= level <= 1
         self._curriculum_level = level
-        if "states" in self.cfg["simulator"]:
-            for state in self.cfg["simulator"]["states"]:
-                state = copy.copy(state)
-                state_name = state.pop("name")
-                to_rad = state.pop("convert_to_radians", False)
-                for prop, val in state.items():
-                    if val is not None:
-                        if "constraint" not in prop and any(m in prop for m in ["min", "max"]):
-                            midpoint = (state[prop[:-3] + "max"] + state[prop[:-3] + "min"]) / 2
-                            val = midpoint - level * (midpoint - val)
-                        if to_rad:
-                            val = np.radians(val)
-                    setattr(self.state[state_name], prop, val)
-        tp = {"states": {}}
-        for attr, val in self.cfg["target"].items():
-            if attr == "states":
-                for state in val:
-                    name = state.get("name")
-                    tp["states"][name] = {}
-                    for k, v in state.items():
-                        if k == "name":
-                            continue
-                        if k not in ["bound", "class"] and v is not None and not isinstance(v, bool):
-                            if k == "low":
-                                midpoint = (state["high"] + v) / 2
-                            elif k == "high":
-                                midpoint = (v + state["low"]) / 2
-                            else:
-                                midpoint = 0
-                            v = midpoint - level * (midpoint - v)
-                        tp["states"][name][k] = v
-            elif isinstance(val, list):
-                tp[attr] = val[round(len(val) * level)]
-            else:
-                tp[attr] = val
-        self._target_props_init = tp
+        for name, prop, value in self._curriculum_state_limits(level):
+            setattr(self.state[name], prop, value)
+        self._target_props_init = self._curriculum_targets(level)
+
+    @staticmethod
+    def _towards(mid, end, level):
+        return mid - level * (mid - end)
+
+    def _curriculum_state_limits(self, level):
+        """-> [(state name, property, value)]: every property of every simulator.states entry, as the reference assigns
+        them (:233-245).  A property whose name contains min / max and not "constraint" is the end of a range whose other
+        end is the sibling property with the same stem; nulls pass through; degrees are converted after scaling."""
+        out = []
+        for entry in self.cfg["simulator"].get("states", ()):
+            spec = {k: v for k, v in entry.items() if k not in ("name", "convert_to_radians")}
+            to_rad = entry.get("convert_to_radians", False)
+            for prop, val in spec.items():
+                if val is not None:
+                    if "constraint" not in prop and ("min" in prop or "max" in prop):
+                        stem = prop[:-3]
+                        val = self._towards((spec[stem + "max"] + spec[stem + "min"]) / 2, val, level)
+                    if to_rad:
+                        val = np.radians(val)
+                out.append((entry["name"], prop, val))
+        return out
+
+    def _curriculum_targets(self, level):
+        """-> the target properties sample_target reads (:247-265).  Per target state: low / high move towards the
+        midpoint of the configured range, every other number (delta, slopes, amplitudes, periods) towards zero; bound,
+        class, booleans and nulls are kept.  Other target settings: a list is indexed by round(len * level)."""
+        props = {"states": {}}
+        for key, val in self.cfg["target"].items():
+            if key != "states":
+                props[key] = val[round(len(val) * level)] if isinstance(val, list) else val
+        for st in self.cfg["target"]["states"]:
+            scaled = {}
+            for key, val in st.items():
+                if key == "name":
+                    continue
+                if key not in ("bound", "class") and val is not None and not isinstance(val, bool):
+                    mid = (st["high"] + val) / 2 if key == "low" else ((val + st["low"]) / 2 if key == "high" else 0)
+                    val = self._towards(mid, val, level)
+                scaled[key] = val
+            props["states"][st["name"]] = scaled
+        return props
 
     # -------------------------------------------------------------------------------------------------- to POD
     @property
@@ -594,6 +605,7 @@ class CompiledConfig:
         e.n_factors = len(r["factors"])
         if e.n_factors > _capi.DEFINES["FW_MAX_FACTORS"]:
             raise ConfigError("too many reward factors")
+        n_scale = 0
         for i, comp in enumerate(r["factors"]):
             F = e.fac[i]
             F.cls = {"action": 0, "state": 1, "success": 2, "step": 3, "goal": 4}[comp["class"]]
@@ -621,8 +633,18 @@ class CompiledConfig:
             elif comp["class"] == "goal":
                 F.type = {"per_state": 0, "all": 1}[comp["type"]]
                 F.value = float(comp["value"])
-            F.scaling = float(comp["scaling"])
+            init_scaling = self._rew_factors_init[i]["scaling"]
+            if isinstance(init_scaling, list):
+                # reward.randomize_scaling (fixed_wing.py:330-334): U(low, high) per reset into a per-env row
+                if not r.get("randomize_scaling", False):
+                    raise ConfigError("reward factor %s: scaling [low, high] needs reward.randomize_scaling" % comp.get("name"))
+                n_scale += 1
+                F.scale_slot1, F.scale_low, F.scale_high = n_scale, float(init_scaling[0]), float(init_scaling[1])
+                F.scaling = 1.0
+            else:
+                F.scaling = float(comp["scaling"])
             F.shaping = 1 if comp.get("shaping", False) else 0
             if comp.get("max", None) is not None:
                 F.has_max, F.max = 1, float(comp["max"])
             F.sign = float(np.sign(comp.get("sign", -1)))
+        e.n_scale_rows = n_scale

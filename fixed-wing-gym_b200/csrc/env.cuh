@@ -419,12 +419,14 @@ __device__ __forceinline__ double fw_reward(const fw_env_t& E, const fw_sim_t& P
         if (goal_bits >> 31) val += F.value;
       }
     }
+    // reward.randomize_scaling: a factor with scaling = [low, high] reads this episode's draw (fw_reset_env)
+    const double scaling = Fs.scale_slot1 ? c.D(Ls.rs_row + Fs.scale_slot1 - 1) : F.scaling;
     if (Fs.fclass == 0) {
-      val = fabs(val) / F.scaling;
+      val = fabs(val) / scaling;
       if (val < 0.0) val = 0.0;
       if (Fs.has_max && val > F.max) val = F.max;
     } else {
-      val = val * val / F.scaling;
+      val = val * val / scaling;
     }
     if (Fs.shaping) shp_t[Fs.fclass] += val * F.sign;
     else val_t[Fs.fclass] += val * F.sign;
@@ -468,6 +470,18 @@ __device__ __forceinline__ void fw_turb_noise(const fw_sim_t& P, uint32_t k0, ui
   fw_normal2_t<INL>(g, FW_RS_TURB, 2u * (uint32_t)s + 1u, u[2], u[3]);
 #pragma unroll
   for (int j = 0; j < 4; ++j) u[j] *= P.turb_noise_scale;
+}
+// ... or the caller's samples (PyFly.reset(turbulence_noise=...), fixed_wing.py:287,308): [4, len, n] unscaled standard
+// normals; a step beyond the array wraps around (pyfly: idx % noise.shape[-1])
+struct FwTurbInject {
+  const double* __restrict__ noise;
+  int64_t len, n;
+};
+__device__ __noinline__ void fw_turb_noise_injected(const fw_sim_t& P, const FwTurbInject& ti, int64_t env, int s,
+                                                    double (&u)[4]) {
+  const int64_t col = (int64_t)s % ti.len;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) u[j] = ti.noise[((int64_t)j * ti.len + col) * ti.n + env] * P.turb_noise_scale;
 }
 
 // advance the six shaping filters by one sample (scipy lsim recurrence) and refresh the gust rows.  The host zero-pads
@@ -638,7 +652,7 @@ template <class SH>
 __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
                                           uint32_t k0, uint32_t k1, uint32_t genv, const double* __restrict__ init_state,
                                           const double* __restrict__ init_target, int64_t in_stride,
-                                          const FwObsWriter& out) {
+                                          const FwTurbInject& ti, const FwObsWriter& out) {
   FW_SHAPE_REFS;
   const uint32_t tick = (uint32_t)c.I(I_TICK);
   c.I(I_TICK) = (int32_t)(tick + 1u);
@@ -687,7 +701,8 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   double gl[3] = {0, 0, 0};
   if (Ps.turbulence) {
     double u0[4];
-    fw_turb_noise<false>(P, k0, k1, genv, tick, 0, u0);
+    if (ti.noise) fw_turb_noise_injected(P, ti, c.env, 0, u0);
+    else fw_turb_noise<false>(P, k0, k1, genv, tick, 0, u0);
     for (int j = 0; j < 4; ++j) c.D(D_TU + j) = u0[j];
 #pragma unroll
     for (int f = 0; f < FW_N_FILT; ++f) {
@@ -785,7 +800,14 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   }
   flags |= FWF_HIST_VALID;
   flags &= ~(7u << FWF_PREVSHAPE_SHIFT);
-  flags &= ~FWF_EP_SUCCESS;
+  flags &= ~(FWF_EP_SUCCESS | FWF_TURB_INJ);
+  if (ti.noise && Ps.turbulence) flags |= FWF_TURB_INJ;
+  // reward.randomize_scaling (fixed_wing.py:330-334): after the observation and the history rebuild, one uniform draw
+  // per factor configured with scaling = [low, high], in factor order
+  if (Es.n_scale_rows > 0)
+    for (int f = 0; f < Es.n_factors; ++f)
+      if (Es.fac[f].scale_slot1)
+        c.D(Ls.rs_row + Es.fac[f].scale_slot1 - 1) = rng.uniform(E.fac[f].scale_low, E.fac[f].scale_high);
   c.I(I_FLAGS) = (int32_t)flags;
   c.I(I_STATUS) = 0;
   c.I(I_LASTK) = 0;

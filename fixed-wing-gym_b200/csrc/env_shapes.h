@@ -91,7 +91,8 @@ inline bool fw_env_same_shape(const fw_env_t& a, const fw_env_t& b) {
       a.has_bounds != b.has_bounds || a.n_targets != b.n_targets || a.resample_every != b.resample_every ||
       a.streak_req != b.streak_req || a.on_success != b.on_success || a.n_factors != b.n_factors ||
       a.potential != b.potential || a.step_fail_timesteps != b.step_fail_timesteps || a.n_terms != b.n_terms ||
-      a.metrics_enabled != b.metrics_enabled || a.n_rand != b.n_rand || a.n_par_rows != b.n_par_rows)
+      a.metrics_enabled != b.metrics_enabled || a.n_rand != b.n_rand || a.n_par_rows != b.n_par_rows ||
+      a.n_scale_rows != b.n_scale_rows)
     return false;
   for (int v = 0; v < a.obs_nvar; ++v) {
     const fw_obs_var_t &x = a.obs[v], &y = b.obs[v];
@@ -107,7 +108,8 @@ inline bool fw_env_same_shape(const fw_env_t& a, const fw_env_t& b) {
   for (int f = 0; f < a.n_factors; ++f) {
     const fw_factor_t &x = a.fac[f], &y = b.fac[f];
     if (x.cls != y.cls || x.type != y.type || x.fclass != y.fclass || x.ref != y.ref || x.window != y.window ||
-        x.shaping != y.shaping || x.has_max != y.has_max || x.value_timesteps != y.value_timesteps)
+        x.shaping != y.shaping || x.has_max != y.has_max || x.value_timesteps != y.value_timesteps ||
+        x.scale_slot1 != y.scale_slot1)
       return false;
   }
   for (int t = 0; t < a.n_terms; ++t)

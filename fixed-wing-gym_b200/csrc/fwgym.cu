@@ -56,6 +56,12 @@ struct fw_handle_s {
   int pdl_dyn;                   // attempt kernel launched as a programmatic dependent of the init kernel (FWGYM_PDL_DYN)
   int shape;                     // env / reset kernel instantiation: index into FW_SHAPE_LIST, -1 generic (env_shapes.h)
   double* ep_out;                // caller's episode-metric buffer (fw_set_episode_out)
+  const double* turb_noise;      // caller's injected Dryden noise [4, turb_len, n] (fw_reset), NULL: Philox streams
+  int64_t turb_len;
+  int* err_flag_host;            // mapped pinned word the env kernel raises when a block's chunk wait times out
+  int* err_flag_dev;             //   (device alias); non-zero = the handle refuses to step (FW_ERR_WATCHDOG)
+  uint32_t spin_limit;           // polls before an env block gives up (fw_debug_watchdog; default ~1 s)
+  int starve_next;               // test hook: block 0 of the next step waits for an aircraft that does not exist
   // init -> attempt -> env pipeline (see "dynamics kernels")
   double* carry_d;               // [CY_ROWS][stride]
   int32_t* carry_i;              // [CI_ROWS][stride]
@@ -88,6 +94,14 @@ static int fail(int code, const char* fmt, const char* a = "") {
   do {                                                                                          \
     cudaError_t e_ = (x);                                                                       \
     if (e_ != cudaSuccess) return fail(FW_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+// sticky watchdog error (fw_env_kernel): the flag lives in mapped pinned memory, so this is a plain host load
+#define CK_POISON(h)                                                                                             \
+  do {                                                                                                           \
+    if (*reinterpret_cast<volatile int*>((h)->err_flag_host))                                                    \
+      return fail(FW_ERR_WATCHDOG, "an env-kernel block gave up waiting for its aircraft (fw_counters().watchdog): "  \
+                                   "state of its envs was not advanced; call fw_reset (all envs) or fw_set_state%s", ""); \
   } while (0)
 
 // ----------------------------------------------------------------------------------------------- dynamics kernels
@@ -437,7 +451,7 @@ __device__ __forceinline__ double fw_cond_s(uint32_t vflags, const fw_var_t& v, 
 template <class SH>
 __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx& c, const double* __restrict__ cd,
                                                const int32_t* __restrict__ ci, int64_t stride, uint32_t k0, uint32_t k1,
-                                               uint32_t genv, int& attempts_out, int& accepted_out) {
+                                               uint32_t genv, const FwTurbInject& ti, int& attempts_out, int& accepted_out) {
   const fw_sim_t& Ps = SH::sim(P);
 #define FW_CS(SV, X) fw_cond_s<false>(Ps.var[SV].flags, P.var[SV], SV, X, failv)
 #define FW_CSW(SV, X) fw_cond_s<true>(Ps.var[SV].flags, P.var[SV], SV, X, failv)
@@ -495,7 +509,8 @@ __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx
       c.D(D_ELEV) = elev; c.D(D_AIL) = ail;
       if (Ps.turbulence) {   // gust column for the next sim step (cur_sim_step + 1)
         double un[4];
-        fw_turb_noise<SH::fixed>(P, k0, k1, genv, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
+        if (ti.noise && ((uint32_t)c.I(I_FLAGS) & FWF_TURB_INJ)) fw_turb_noise_injected(P, ti, c.env, c.I(I_STEPS) + 1, un);
+        else fw_turb_noise<SH::fixed>(P, k0, k1, genv, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
         fw_turb_advance<SH>(P, c, un);
       }
     }
@@ -530,6 +545,10 @@ struct FwEnvArgs {
   double* ep_out;      // [N, ep_dim] episode-metric rows (NULL: not requested)
   int ep_dim;
   int32_t* q;          // queue buffer of the dynamics kernels: per-chunk finished counters behind Q_N
+  FwTurbInject ti;     // injected Dryden noise of the running episodes (fw_reset turb_noise)
+  int* err_flag;       // host-visible sticky error word (watchdog)
+  uint32_t spin_limit;
+  int32_t starve;      // test hook (fw_debug_watchdog)
 };
 
 // Env-side work of one env step for env `env` (fixed_wing.py:338-437 after the simulator call).  Episode-metric
@@ -540,7 +559,7 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
                                             int& accepted, int& failed) {
   FW_SHAPE_REFS;
   FwEnvCtx c{a.d, a.i, L.stride, env};
-  fw_commit_step<SH>(P, c, a.cd + env, a.ci + env, L.stride, a.k0, a.k1, a.env_offset + (uint32_t)env, attempts, accepted);
+  fw_commit_step<SH>(P, c, a.cd + env, a.ci + env, L.stride, a.k0, a.k1, a.env_offset + (uint32_t)env, a.ti, attempts, accepted);
   failed = c.I(I_STATUS) != 0;
   uint32_t flags = (uint32_t)c.I(I_FLAGS);
   int steps = c.I(I_STEPS);
@@ -648,7 +667,7 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   }
   if (do_reset) {
     n_reset += 1;
-    fw_reset_env<SH>(E, P, L, c, a.k0, a.k1, genv, nullptr, nullptr, 0, ow);
+    fw_reset_env<SH>(E, P, L, c, a.k0, a.k1, genv, nullptr, nullptr, 0, FwTurbInject{nullptr, 0, 0}, ow);
   }
 }
 
@@ -686,22 +705,45 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
   // release in fw_attempt_kernel).  One polling thread per block; the others sleep on the barrier.  The attempt kernel
   // never waits for anything, so this cannot deadlock; the watchdog turns a lost update into an error flag
   // (fw_counters reports it) instead of a hung GPU.
+  __shared__ int s_timed_out;
   if (threadIdx.x == 0) {
     const int64_t first = (int64_t)blockIdx.x * FW_ENV_BLOCK;
-    const int need = (int)((a.n - first) < FW_ENV_BLOCK ? (a.n - first) : FW_ENV_BLOCK);
+    int need = (int)((a.n - first) < FW_ENV_BLOCK ? (a.n - first) : FW_ENV_BLOCK);
+    if (a.starve && blockIdx.x == 0) need += 1;
     const volatile int32_t* cnt = FW_CHUNK_DONE(a.q, first);
     unsigned spins = 0;
+    bool ok = true;
     while (*cnt < need) {
       __nanosleep(256);
-      if (++spins > (1u << 22)) { atomicAdd(a.ctr + CTR_WATCHDOG, 1ull); break; }   // ~1 s
+      if (++spins > a.spin_limit) { ok = false; break; }
     }
     __threadfence();
-    // consumed: zero it for the next step (nothing adds to a complete chunk); block 0 also zeroes the priority-list
-    // length, which every attempt warp read before this kernel could start
-    *FW_CHUNK_DONE(a.q, first) = 0;
-    if (blockIdx.x == 0) a.q[Q_LONG_COUNT] = 0;
+    s_timed_out = ok ? 0 : 1;
+    if (ok) {
+      // consumed: zero it for the next step (nothing adds to a complete chunk); block 0 also zeroes the priority-list
+      // length, which every attempt warp read before this kernel could start
+      *FW_CHUNK_DONE(a.q, first) = 0;
+      if (blockIdx.x == 0) a.q[Q_LONG_COUNT] = 0;
+    } else {
+      // Gave up: the carry rows of this chunk may be stale or partial, so NOTHING is committed for its envs, the
+      // counter is left alone (late arrivals would corrupt the next step's count) and the handle is poisoned: the host
+      // sees the flag and refuses to step until the queue has been re-armed (fw_reset / fw_set_state).
+      atomicAdd(a.ctr + CTR_WATCHDOG, 1ull);
+      *reinterpret_cast<volatile int*>(a.err_flag) = 1;
+      __threadfence_system();
+    }
   }
   __syncthreads();
+  if (s_timed_out) {
+    if (env < a.n) {
+      const float nanf_ = __int_as_float(0x7fc00000);
+      if (a.obs_out) for (int j = 0; j < a.obs_dim; ++j) a.obs_out[env * (int64_t)a.obs_dim + j] = nanf_;
+      a.rew_out[env] = nanf_;
+      a.done_out[env] = 0;
+      a.term_out[env] = -1;
+    }
+    return;
+  }
 #ifdef FW_TIMELINE
   const unsigned long long tl_go = fw_gtime();
   if (threadIdx.x == 0) atomicMin(&fw_timeline_buf[6], tl_go);
@@ -747,6 +789,7 @@ struct FwResetArgs {
   double* obs64_out;
   int obs_dim;
   unsigned long long* ctr;
+  FwTurbInject ti;
 };
 
 template <class SH>
@@ -759,7 +802,7 @@ fw_reset_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_s
   FwEnvCtx c{a.d, a.i, L.stride, env};
   FwObsWriter ow{a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim};
   atomicAdd(a.ctr + CTR_RESETS, 1ull);
-  fw_reset_env<SH>(E, P, L, c, a.k0, a.k1, a.env_offset + (uint32_t)env, a.init_state, a.init_target, a.n, ow);
+  fw_reset_env<SH>(E, P, L, c, a.k0, a.k1, a.env_offset + (uint32_t)env, a.init_state, a.init_target, a.n, a.ti, ow);
 }
 
 // ---- shape dispatch: index into FW_SHAPE_LIST (fw_find_shape), -1 = generic -----------------------------------------
@@ -1025,6 +1068,12 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
   h->last_stream = nullptr;
   h->profiling = 0;
   h->ep_out = nullptr;
+  h->turb_noise = nullptr;
+  h->turb_len = 0;
+  h->err_flag_host = nullptr;
+  h->err_flag_dev = nullptr;
+  h->spin_limit = 1u << 22;   // x 256 ns: ~1 s
+  h->starve_next = 0;
   int rc = make_layout(h->cfg, n_envs, h->L);
   if (rc) { delete h; return rc; }
   const size_t db = (size_t)h->L.d_rows * h->L.stride * sizeof(double);
@@ -1043,6 +1092,12 @@ int fw_create(const fw_config_t* cfg, int64_t n_envs, int64_t global_env_offset,
     delete h;
     return fail(FW_ERR_ALLOC, "cudaMalloc (carry) failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  if (cudaHostAlloc(&h->err_flag_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&h->err_flag_dev, h->err_flag_host, 0) != cudaSuccess) {
+    delete h;
+    return fail(FW_ERR_ALLOC, "cudaHostAlloc (error flag) failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  *h->err_flag_host = 0;
   CK(cudaMemset(h->queue, 0, (size_t)h->q_len * sizeof(int32_t)));   // from here on the kernels keep it zeroed (fw_init_kernel)
   CK(cudaMemset(h->carry_d, 0, (size_t)CY_ROWS * h->L.stride * sizeof(double)));
   CK(cudaMemset(h->carry_i, 0, (size_t)CI_ROWS * h->L.stride * sizeof(int32_t)));
@@ -1094,6 +1149,7 @@ int fw_destroy(fw_handle h) {
   cudaSetDevice(h->device);
   cudaFree(h->d); cudaFree(h->i); cudaFree(h->ctr); cudaFree(h->msum);
   cudaFree(h->carry_d); cudaFree(h->carry_i); cudaFree(h->long_list); cudaFree(h->queue);
+  if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
   host_free(h);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
@@ -1103,6 +1159,10 @@ int fw_destroy(fw_handle h) {
 int fw_seed(fw_handle h, uint64_t seed) {
   if (!h) return fail(FW_ERR_ARG, "null handle");
   h->seed = seed;
+  // the per-env draw counters restart with the key (FixedWingAircraft.seed reseeds np_random and the simulator):
+  // seed(s) + reset() reproduces the same episodes on a live handle
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->i + (size_t)I_TICK * h->L.stride, 0, (size_t)h->L.stride * sizeof(int32_t), h->last_stream));
   return FW_OK;
 }
 
@@ -1187,6 +1247,7 @@ const char* fw_state_row_name(fw_handle h, int64_t r) {
   if (!h || r < 0) return nullptr;
   if (r < D_FIXED) return dn[r];
   if (h->L.n_par_rows > 0 && r >= h->L.par_row && r < h->L.par_row + h->L.n_par_rows) return "param";
+  if (h->L.n_rs_rows > 0 && r >= h->L.rs_row && r < h->L.rs_row + h->L.n_rs_rows) return "reward_scaling";
   if (r < h->L.d_rows) return "ring";
   r -= h->L.d_rows;
   if (r < I_GOALRING) return in[r];
@@ -1194,13 +1255,24 @@ const char* fw_state_row_name(fw_handle h, int64_t r) {
   return nullptr;
 }
 
-int fw_reset(fw_handle h, const uint8_t* mask, const double* init_state, const double* init_target, float* obs_out,
-             double* obs64_out, void* stream) {
+int fw_reset(fw_handle h, const uint8_t* mask, const double* init_state, const double* init_target,
+             const double* turb_noise, int64_t turb_len, float* obs_out, double* obs64_out, void* stream) {
   if (!h) return fail(FW_ERR_ARG, "null handle");
+  if (turb_noise && turb_len <= 0) return fail(FW_ERR_ARG, "fw_reset: turb_noise needs turb_len > 0");
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (*reinterpret_cast<volatile int*>(h->err_flag_host)) {
+    if (mask) CK_POISON(h);                    // only a FULL reset recovers from a watchdog error
+    CK(cudaDeviceSynchronize());               // nothing of the abandoned step may still be running
+    *h->err_flag_host = 0;
+  }
+  // injected Dryden noise: kept for the episodes that start here (a partial reset without noise keeps the buffer the
+  // other envs may still be reading; a full reset without noise drops it)
+  if (turb_noise) { h->turb_noise = turb_noise; h->turb_len = turb_len; }
+  else if (!mask) { h->turb_noise = nullptr; h->turb_len = 0; }
   FwResetArgs a{h->d, h->i, h->n, mask, init_state, init_target, (uint32_t)h->seed, (uint32_t)(h->seed >> 32),
-                (uint32_t)h->offset, obs_out, obs64_out, fw_obs_dim(h), h->ctr};
+                (uint32_t)h->offset, obs_out, obs64_out, fw_obs_dim(h), h->ctr,
+                FwTurbInject{turb_noise, turb_len, h->n}};
   const int grid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
   CK(launch_reset(h->shape, grid, s, h->cfg.env, h->cfg.sim, h->L, a));
   // a full reset also re-arms the step queue (the kernels keep it zeroed between steps; this covers a step that was
@@ -1215,6 +1287,7 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
             void* stream) {
   if (!h || !actions || !rew_out || !done_out || !term_out) return fail(FW_ERR_ARG, "fw_step: null argument");
   if (!obs_out && !obs64_out) return fail(FW_ERR_ARG, "fw_step: no observation buffer");
+  CK_POISON(h);
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t k0 = (uint32_t)h->seed, k1 = (uint32_t)(h->seed >> 32);
@@ -1230,7 +1303,9 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   if (h->profiling) CK(cudaEventRecord(pe[1], s));
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
                term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum, h->carry_d,
-               h->carry_i, h->ep_out, fw_episode_dim(h), h->queue};
+               h->carry_i, h->ep_out, fw_episode_dim(h), h->queue, FwTurbInject{h->turb_noise, h->turb_len, h->n},
+               h->err_flag_dev, h->spin_limit, h->starve_next};
+  h->starve_next = 0;
   const int egrid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
   // with per-kernel profiling on, an event sits between the two kernels, so they are serialised anyway
   CK(launch_env(h->shape, egrid, s, h->overlap && !h->profiling, h->cfg.env, h->cfg.sim, h->L, ea));
@@ -1295,6 +1370,7 @@ int fw_host_submit(fw_handle h, const float* actions_host, void* stream, int* sl
   const int k = (int)(h->hs_next % (int64_t)h->hs.size());
   fw_handle_s::HostSlot& sl = h->hs[k];
   if (sl.busy) return fail(FW_ERR_ARG, "fw_host_submit: every slot is in flight; fw_host_wait the oldest one first");
+  CK_POISON(h);
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)h->n, od = (size_t)fw_obs_dim(h);
@@ -1323,6 +1399,7 @@ int fw_host_wait(fw_handle h, int slot, const float** obs, const float** rew, co
   if (!sl.busy) return fail(FW_ERR_ARG, "fw_host_wait: slot was not submitted");
   CK(cudaEventSynchronize(sl.e_out));
   sl.busy = 0;
+  CK_POISON(h);
   if (obs) *obs = sl.h_obs;
   if (rew) *rew = sl.h_rew;
   if (done) *done = sl.h_done;
@@ -1370,6 +1447,33 @@ int fw_profile(fw_handle h, double* dyn_ms, double* env_ms, int64_t* steps) {
   return FW_OK;
 }
 
+__global__ void fw_export_rows_kernel(const double* d, const int32_t* i, int64_t stride, int64_t n, int rows_d, int64_t row0,
+                                      int64_t nrows, double* out) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  for (int64_t r = 0; r < nrows; ++r) {
+    const int64_t row = row0 + r;
+    out[r * n + env] = row < rows_d ? d[row * stride + env] : (double)i[(row - rows_d) * stride + env];
+  }
+}
+
+int fw_get_rows(fw_handle h, int64_t row0, int64_t nrows, double* out, void* stream) {
+  if (!h || !out) return fail(FW_ERR_ARG, "null argument");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > h->L.d_rows + h->L.i_rows) return fail(FW_ERR_ARG, "fw_get_rows: row range");
+  CK(cudaSetDevice(h->device));
+  const int grid = (int)((h->n + 255) / 256);
+  fw_export_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, h->i, h->L.stride, h->n, h->L.d_rows, row0, nrows, out);
+  CK(cudaGetLastError());
+  return FW_OK;
+}
+
+int fw_debug_watchdog(fw_handle h, uint32_t spin_limit, int starve) {
+  if (!h) return fail(FW_ERR_ARG, "null handle");
+  h->spin_limit = spin_limit ? spin_limit : (1u << 22);
+  h->starve_next = starve;
+  return FW_OK;
+}
+
 int fw_get_state(fw_handle h, double* out, void* stream) {
   if (!h || !out) return fail(FW_ERR_ARG, "null argument");
   CK(cudaSetDevice(h->device));
@@ -1382,6 +1486,10 @@ int fw_get_state(fw_handle h, double* out, void* stream) {
 int fw_set_state(fw_handle h, const double* in, void* stream) {
   if (!h || !in) return fail(FW_ERR_ARG, "null argument");
   CK(cudaSetDevice(h->device));
+  if (*reinterpret_cast<volatile int*>(h->err_flag_host)) {   // restoring a checkpoint recovers from a watchdog error
+    CK(cudaDeviceSynchronize());
+    *h->err_flag_host = 0;
+  }
   const int grid = (int)((h->n + 255) / 256);
   fw_import_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, h->i, h->L.stride, h->n, h->L.d_rows, h->L.i_rows, in);
   CK(cudaMemsetAsync(h->queue, 0, (size_t)h->q_len * sizeof(int32_t), (cudaStream_t)stream));   // re-arm the step queue
@@ -1415,6 +1523,7 @@ int fw_counters(fw_handle h, fw_counters_t* out) {
   out->resets = c[CTR_RESETS];
   out->rhs_evals = 2 * c[CTR_ENV_STEPS] + 6 * c[CTR_ATTEMPTS];
   out->watchdog = c[CTR_WATCHDOG];
+  CK_POISON(h);   // (the counters above are filled in either way)
   return FW_OK;
 }
 

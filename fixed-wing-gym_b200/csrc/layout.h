@@ -46,6 +46,7 @@ enum {
 #define FWF_PREVSHAPE_SHIFT 2     // 3 bits: prev_shaping[fclass] is not None
 #define FWF_TCLS_SHIFT 8          // 2 bits per target: current class (reset(target=) may force constant)
 #define FWF_EP_SUCCESS (1u << 16) // streak achieved in this episode (metric "success"["all"])
+#define FWF_TURB_INJ (1u << 17)   // this episode's Dryden noise was injected at reset (fw_reset turb_noise), not drawn
 
 // variable part, computed from the config by fw_layout_build below (host: make_layout in fwgym.cu; device: folded)
 struct FwLayout {
@@ -64,6 +65,8 @@ struct FwLayout {
   int32_t met, m_drow, m_irow, end_row;
   // per-env model parameters (simulator-parameter randomisation): n_par_rows rows starting at par_row
   int32_t par_row, n_par_rows;
+  // per-env reward scalings (reward.randomize_scaling): n_rs_rows rows starting at rs_row
+  int32_t rs_row, n_rs_rows;
 };
 
 // metric accumulators, relative to FwLayout.m_drow (double) / m_irow (int32); k = target index
@@ -132,6 +135,10 @@ constexpr int fw_layout_build(const fw_env_t& E, int scale_actions, int64_t n, F
   L.par_row = row;
   L.n_par_rows = E.n_par_rows;
   row += E.n_par_rows;
+  if (E.n_scale_rows < 0 || E.n_scale_rows > FW_MAX_FACTORS) return 7;
+  L.rs_row = row;
+  L.n_rs_rows = E.n_scale_rows;
+  row += E.n_scale_rows;
   L.d_rows = row;
   return 0;
 }
@@ -143,6 +150,7 @@ inline const char* fw_layout_error(int code) {
     case 4: return "success_streak_req > 256 unsupported";
     case 5: return "integrator observation / int_error reward need integration_window > 0";
     case 6: return "bad simulator-parameter randomisation table";
+    case 7: return "bad reward-scaling randomisation table";
   }
   return "";
 }

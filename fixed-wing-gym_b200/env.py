@@ -40,9 +40,10 @@ class FixedWingAircraft:
         return self._vec._obs64[0].cpu().numpy().reshape(self._vec.cc.obs_shape).copy()
 
     def reset(self, state=None, target=None, **sim_reset_kw):
+        noise = sim_reset_kw.pop("turbulence_noise", None)   # PyFly.reset's only other keyword (fixed_wing.py:308)
         if sim_reset_kw:
-            raise NotImplementedError("sim reset kwargs (e.g. turbulence_noise) are replaced by the Philox stream")
-        self._vec.reset(state=state, target=target)
+            raise TypeError("reset() got unexpected simulator keywords %s" % sorted(sim_reset_kw))
+        self._vec.reset(state=state, target=target, turbulence_noise=noise)
         return self._obs()
 
     def step(self, action):

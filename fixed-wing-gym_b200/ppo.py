@@ -146,6 +146,8 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
     adv = torch.zeros((n_steps, n), device=dev)
     ret = torch.zeros((n_steps, n), device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    act_low = torch.as_tensor(venv.action_space.low, dtype=torch.float32, device=dev)
+    act_high = torch.as_tensor(venv.action_space.high, dtype=torch.float32, device=dev)
 
     def rollout(marks=None):
         """n_steps x (policy forward, sample, env step, normalise) + GAE into the static buffers."""
@@ -154,14 +156,15 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
                 if marks is not None:
                     a0, a1, a2 = ev(), ev(), ev()
                     a0.record()
-                act, logp = model.sample(obs)
+                act, logp = model.sample(obs)   # the buffer keeps the unclipped action and its log-probability
                 buf["obs"][t].copy_(obs)
                 buf["act"][t].copy_(act)
                 buf["logp"][t].copy_(logp)
                 buf["val"][t].copy_(model.value(obs))
                 if marks is not None:
                     a1.record()
-                o, rew, done, _ = norm.step(act)
+                # PPO2's runner clips to the action space before stepping (finite for actuator-limited spaces)
+                o, rew, done, _ = norm.step(torch.max(torch.min(act, act_high), act_low))
                 obs.copy_(o)
                 buf["rew"][t].copy_(rew)
                 buf["done"][t].copy_(done.float())
@@ -181,7 +184,7 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
     t_env = t_pol = t_upd = t_roll = 0.0
     iters = max(1, int(total_env_steps) // B)
     stats = {"iterations": iters, "batch": B, "history": [], "cuda_graph": bool(cuda_graph)}
-    graph = None
+    graph, graph_version = None, -1
     torch.cuda.synchronize(dev)
     wall0 = time.perf_counter()
     for it in range(iters):
@@ -193,7 +196,12 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
         elif it == 0:
             rollout()                                   # eager: warms up allocations, cuBLAS handles, the env
         else:
+            # seed / configuration are kernel PARAMETERS frozen into a captured graph: after venv.seed() or
+            # set_curriculum_level() (train_rl_controller.py:80-87 changes the curriculum during training) re-capture
+            if graph is not None and graph_version != venv.config_version:
+                graph = None
             if graph is None:
+                graph_version = venv.config_version
                 torch.cuda.synchronize(dev)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):           # capture only; nothing runs here

@@ -120,11 +120,15 @@ class FixedWingVecEnv:
         self._obs64 = self._rew64 = None
         self._actions = None
         self._ep_out = None
+        self._turb_noise = None
         if self.metrics:
             self.ep_dim = self._lib.fw_episode_dim(self._h)
             self._ep_out = torch.full((n, self.ep_dim), float("nan"), dtype=torch.float64, device=d)
             _capi.check(self._lib.fw_set_episode_out(self._h, self._ptr(self._ep_out)))
         self.training = True
+        self.config_version = 0   # bumped by seed() / set_curriculum_level(): captured CUDA graphs must be re-captured
+        self._target_row0 = self.state_rows().index("target0")
+        self._steps_row = self.state_rows().index("steps_count")
         self.seed(seed)
 
     # ------------------------------------------------------------------------------------------------ plumbing
@@ -151,11 +155,15 @@ class FixedWingVecEnv:
         seed = 0 if seed is None else int(seed)
         _capi.check(self._lib.fw_seed(self._h, ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF)))
         self._seed = seed
+        self.config_version += 1   # the key is a kernel parameter: a captured graph would replay the old one
         return [seed + self.env_offset + i for i in range(self.num_envs)] if self.num_envs <= 64 else [seed]
 
-    def reset(self, indices=None, state=None, target=None):
+    def reset(self, indices=None, state=None, target=None, turbulence_noise=None):
         """Reset all envs (or `indices`).  `state` / `target`: dict name -> scalar or array over the reset envs,
-        like FixedWingAircraft.reset(state=, target=) (fixed_wing.py:287-315)."""
+        like FixedWingAircraft.reset(state=, target=) (fixed_wing.py:287-315).  `turbulence_noise`: the reference's
+        `**sim_reset_kw` pass-through to PyFly.reset (fixed_wing.py:287,308): unscaled standard-normal samples of the four
+        Dryden noise streams for the episodes that start now, [4, T] (the same for every reset env) or [n_reset, 4, T];
+        later auto-resets go back to the env's own Philox stream."""
         n, d = self.num_envs, self.device
         mask = None
         idx = None
@@ -191,8 +199,27 @@ class FixedWingVecEnv:
                     init_target[row, :] = v
                 else:
                     init_target[row, idx] = v
+        noise, noise_len = None, 0
+        if turbulence_noise is not None:
+            tn = torch.as_tensor(np.asarray(turbulence_noise, dtype=np.float64), device=d)
+            if tn.dim() == 2:
+                tn = tn.unsqueeze(0)
+            if tn.dim() != 3 or tn.shape[1] != 4:
+                raise ValueError("turbulence_noise must have shape [4, T] or [n_reset, 4, T]")
+            noise_len = int(tn.shape[2])
+            noise = torch.zeros((4, noise_len, n), dtype=torch.float64, device=d)   # C-ABI layout [4, T, N]
+            if idx is None:
+                noise[:] = tn.expand(n, 4, noise_len).permute(1, 2, 0)
+            else:
+                noise[:, :, idx] = tn.expand(len(idx), 4, noise_len).permute(1, 2, 0)
+            if indices is not None and self._turb_noise is not None and self._turb_noise.shape[1] == noise_len:
+                keep = torch.ones(n, dtype=torch.bool, device=d)
+                keep[idx] = False
+                noise[:, :, keep] = self._turb_noise[:, :, keep]    # other envs may still be reading their columns
+            self._turb_noise = noise    # the library reads it until those episodes end
         _capi.check(self._lib.fw_reset(self._h, self._ptr(mask), self._ptr(init_state), self._ptr(init_target),
-                                       self._ptr(self._obs), self._ptr(self._obs64), self._stream()))
+                                       self._ptr(noise), noise_len, self._ptr(self._obs), self._ptr(self._obs64),
+                                       self._stream()))
         return self._shape_obs(self._obs)
 
     def step_tensors(self, actions, out=None):
@@ -223,7 +250,8 @@ class FixedWingVecEnv:
         obs, rew, done, term = self._pending
         # the episode rows are snapshotted here: the next step may overwrite them
         ep = self._ep_out.clone() if self._ep_out is not None else None
-        infos = VecInfos(self, done.clone(), term.clone(), self._term_obs, self.get_targets(), ep)
+        tobs = self._term_obs.clone() if self._term_obs is not None else None   # the next step overwrites it
+        infos = VecInfos(self, done.clone(), term.clone(), tobs, self.get_targets(), ep)
         return obs, rew, done.bool(), infos
 
     def step(self, actions):
@@ -307,11 +335,14 @@ class FixedWingVecEnv:
         st = self.get_state()
         return {n: st[rows.index(n)] for n in names}
 
+    def get_rows(self, row0, nrows):
+        """Rows [row0, row0 + nrows) of the state matrix (state_rows() names them): device float64 [nrows, N]."""
+        out = torch.empty((nrows, self.num_envs), dtype=torch.float64, device=self.device)
+        _capi.check(self._lib.fw_get_rows(self._h, int(row0), int(nrows), self._ptr(out), self._stream()))
+        return out
+
     def get_targets(self):
-        rows = self.state_rows()
-        st = self.get_state()
-        r0 = rows.index("target0")
-        return st[r0:r0 + len(self.target_names)]
+        return self.get_rows(self._target_row0, len(self.target_names))
 
     def last_attempts(self):
         out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
@@ -393,7 +424,7 @@ class FixedWingVecEnv:
             ids = range(self.num_envs) if indices is None else np.atleast_1d(indices)
             return [{t: float(tg[k, i]) for k, t in enumerate(self.target_names)} for i in ids]
         if name == "steps_count":
-            sc = self.get_named_state(["steps_count"])["steps_count"].cpu().numpy().astype(int)
+            sc = self.get_rows(self._steps_row, 1)[0].cpu().numpy().astype(int)
             ids = range(self.num_envs) if indices is None else np.atleast_1d(indices)
             return [int(sc[i]) for i in ids]
         if name == "simulator":
@@ -409,7 +440,7 @@ class FixedWingVecEnv:
             self.set_curriculum_level(*args, **kwargs)
             return [None] * n
         if name == "reset":
-            obs = self.reset(indices=indices, **kwargs)
+            obs = self.reset(indices=indices, **kwargs)   # state=, target=, turbulence_noise=
             ids = range(self.num_envs) if indices is None else np.atleast_1d(indices)
             host = obs.cpu().numpy()
             return [host[i] for i in ids]
@@ -423,6 +454,7 @@ class FixedWingVecEnv:
         self.cc.set_curriculum_level(level)
         pod = self.cc.pod()
         _capi.check(self._lib.fw_set_config(self._h, ctypes.byref(pod)))
+        self.config_version += 1   # the configuration is a kernel parameter: captured graphs hold the old one
 
 
 class HostStepper:

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 9
+#define FW_ABI_VERSION 10
 
 /* ---------------------------------------------------------------------------------------------- limits */
 #define FW_MAX_OBS_VARS 32
@@ -66,7 +66,9 @@ enum fw_par {
 };
 
 enum fw_status {
-  FW_OK = 0, FW_ERR_ARG = -1, FW_ERR_CUDA = -2, FW_ERR_CONFIG = -3, FW_ERR_ALLOC = -4, FW_ERR_ABI = -5
+  FW_OK = 0, FW_ERR_ARG = -1, FW_ERR_CUDA = -2, FW_ERR_CONFIG = -3, FW_ERR_ALLOC = -4, FW_ERR_ABI = -5,
+  FW_ERR_WATCHDOG = -6   /* an env-kernel block gave up waiting for its aircraft: the handle refuses to step until a full
+                          * fw_reset (or fw_set_state); see fw_step */
 };
 
 /* termination codes written to term_code_out (fixed_wing.py:366-368,383-385,409-416) */
@@ -124,6 +126,10 @@ typedef struct {
   int32_t ref;         /* state.value: fw_sv id ; state.error/int_error: target index */
   int32_t window, shaping, has_max, value_timesteps;
   double scaling, max, sign, value;
+  /* reward.randomize_scaling (fixed_wing.py:330-334): a factor configured with scaling = [low, high] draws a new
+   * scaling at every reset; scale_slot1 = 1 + per-env scaling row, 0 = the fixed `scaling` above */
+  int32_t scale_slot1, _pad;
+  double scale_low, scale_high;
 } fw_factor_t;
 
 /* Flat configuration, compiled on the host from the reference's JSON files (config.py) */
@@ -196,6 +202,7 @@ typedef struct {
   /* simulator-parameter randomisation at every reset */
   int32_t n_rand, n_par_rows;     /* draws per reset; per-env parameter rows (randomised + derived) */
   fw_rand_t rand[FW_MAX_RAND];
+  int32_t n_scale_rows, _pad5;    /* per-env reward-scaling rows (reward.randomize_scaling) */
 } fw_env_t;
 
 typedef struct {
@@ -227,25 +234,35 @@ const char* fw_last_error(void);
 int fw_abi_version(void);
 int64_t fw_config_sizeof(void);   /* sizeof(fw_config_t) as compiled, checked by the ctypes mirror */
 
-/* Replaces FixedWingAircraft.seed (fixed_wing.py:214-222): Philox key for every env of the handle. */
+/* Replaces FixedWingAircraft.seed (fixed_wing.py:214-222): Philox key for every env of the handle; the per-env draw
+ * counters (ticks) restart, so seed(s) followed by a full reset reproduces the same episodes. */
 int fw_seed(fw_handle h, uint64_t seed);
 
 /* Replace the compiled configuration (set_curriculum_level / set_attr paths, fixed_wing.py:224-285). */
 int fw_set_config(fw_handle h, const fw_config_t* cfg);
 
 /* Replaces FixedWingAircraft.reset (fixed_wing.py:287-336) for the envs selected by `mask` (device uint8[N], NULL =
- * all).  init_state: optional device double [FW_N_SV, N] (SoA; NaN entries = "sample it"), init_target: optional
- * device double [FW_MAX_TARGETS, N] (NaN = sampled target kept).  obs_out: device float [N, obs_dim] (rows of the
- * envs not selected are left untouched); obs64_out: optional device double copy for parity checks. */
+ * all).  init_state: optional device double [FW_N_SV + 3, N] (SoA; NaN entries = "sample it"; the last three rows are
+ * the steady wind n, e, d), init_target: optional device double [FW_MAX_TARGETS, N] (NaN = sampled target kept).
+ * turb_noise: optional device double [4, turb_len, N] = PyFly.reset(turbulence_noise=...) forwarded by
+ * fixed_wing.py:287,308: the UNSCALED standard-normal samples of the four Dryden noise streams for the episode that
+ * starts now (sim step s reads column s mod turb_len); the buffer must stay valid until those episodes end; envs that
+ * auto-reset later go back to their Philox streams.  obs_out: device float [N, obs_dim] (rows of the envs not
+ * selected are left untouched); obs64_out: optional device double copy for parity checks. */
 int fw_reset(fw_handle h, const uint8_t* mask, const double* init_state, const double* init_target,
-             float* obs_out, double* obs64_out, void* stream);
+             const double* turb_noise, int64_t turb_len, float* obs_out, double* obs64_out, void* stream);
 
 /* Replaces FixedWingAircraft.step (fixed_wing.py:338-437) + SubprocVecEnv auto-reset for all N envs.
  * actions: device [N, FW_N_ACT] row-major, float (actions_f64 = 0) or double (actions_f64 = 1).
  * obs_out float [N, obs_dim] (post-reset observation for envs that finished), rew_out float [N], done_out uint8 [N],
  * term_out int32 [N] (FW_TERM_*).  Optional (may be NULL): obs64_out / rew64_out double copies; term_obs_out float
  * [N, obs_dim] terminal observation of finished envs (rows of others untouched). auto_reset = 0 leaves finished envs
- * un-reset (single-env facade semantics). */
+ * un-reset (single-env facade semantics).
+ * Errors are sticky where they must be: the env kernel starts while the attempt kernel is still running and each of its
+ * blocks waits for its 128 aircraft; a block that gives up (~1 s: a lost update, never observed) commits NOTHING for
+ * its envs (their outputs are NaN / done = 0 / term = -1), raises a flag in host-visible memory, and from then on
+ * fw_step, fw_host_submit, fw_host_wait and fw_counters return FW_ERR_WATCHDOG until a full fw_reset or fw_set_state
+ * re-arms the step queue. */
 int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, float* rew_out, uint8_t* done_out,
             int32_t* term_out, double* obs64_out, double* rew64_out, float* term_obs_out, int auto_reset,
             void* stream);
@@ -265,6 +282,10 @@ int fw_host_close(fw_handle h);
 int fw_host_submit(fw_handle h, const float* actions_host, void* stream, int* slot_out);
 int fw_host_wait(fw_handle h, int slot, const float** obs, const float** rew, const uint8_t** done,
                  const int32_t** term);
+
+/* Rows [row0, row0 + nrows) of the state matrix below: device double [nrows, N] (e.g. the three target rows without
+ * exporting the whole state). */
+int fw_get_rows(fw_handle h, int64_t row0, int64_t nrows, double* out, void* stream);
 
 /* Full per-env state for parity, checkpoint/resume: device double [fw_state_rows(h), N]. */
 int64_t fw_state_rows(fw_handle h);
@@ -332,6 +353,10 @@ int fw_attempt_warps_per_group(fw_handle h);
  * order in which the attempt kernel's warps adopt aircraft (NULL restores the natural order).  Results do not depend
  * on it; the time does.  The buffer must stay valid while it is set. */
 int fw_debug_set_order(fw_handle h, const int32_t* order);
+
+/* Test hook for the watchdog path: spin_limit = polls of the chunk counter before an env block gives up (0 restores the
+ * default, ~1 s); starve != 0 makes block 0 of the NEXT step wait for one aircraft more than exist, so it must time out. */
+int fw_debug_watchdog(fw_handle h, uint32_t spin_limit, int starve);
 
 /* Experiment hook (library built with -DFW_TIMELINE only; otherwise the values never change): out8 = GPU global-timer
  * stamps in ns {init first start, init last end, attempt first start, attempt last end, env first start, env last end,

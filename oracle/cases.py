@@ -94,4 +94,11 @@ CASES = {
                                                           2: {"class": "sinusoidal", "amplitude_low": 1.0,
                                                               "amplitude_high": 3.0}}}},
                          sim_kw={"turbulence": True, "turbulence_intensity": "moderate"}, n=4, steps=50, amp=0.8),
+    # reward.randomize_scaling (fixed_wing.py:330-334): factors with scaling = [low, high] redraw it at every reset
+    "reward_rand_scaling": dict(config="fixed_wing_config_zoo.json",
+                                config_kw={"steps_max": 20,
+                                           "reward": {"randomize_scaling": True,
+                                                      "factors": {0: {"scaling": [2.0, 5.0]}, 3: {"scaling": [40, 80]},
+                                                                  6: {"scaling": [5.0, 20.0]}}}},
+                                sim_kw={"turbulence": False}, n=4, steps=50, amp=1.0),
 }

@@ -93,6 +93,7 @@ class RestatedEnv:
         self.tprops = None
         self.tprops_init = None
         self.prev_shaping = {}
+        self.rew_factors_init = copy.deepcopy(self.cfg["reward"]["factors"])   # fixed_wing.py:198 (randomize_scaling)
         self.set_curriculum_level(1)
 
     # ----------------------------------------------------------------------------------------------- curriculum
@@ -400,6 +401,10 @@ class RestatedEnv:
             self.history["goal"] = {k: [v] for k, v in self.goal_status().items()}
         for term in self.cfg["reward"]["terms"]:
             self.prev_shaping[term["function_class"]] = None
+        if self.cfg["reward"].get("randomize_scaling", False):   # fixed_wing.py:330-334
+            for i, fac in enumerate(self.rew_factors_init):
+                if isinstance(fac["scaling"], list):
+                    self.cfg["reward"]["factors"][i]["scaling"] = self.np_random.uniform(fac["scaling"][0], fac["scaling"][1])
         return obs
 
     def step(self, action):

@@ -60,12 +60,15 @@ class OracleRunner:
         self._wind_rng.tick, self._wind_rng.n = t, 0
         return t
 
-    def reset(self, state=None, target=None):
+    def reset(self, state=None, target=None, turbulence_noise=None):
+        """turbulence_noise: an explicit [4, T] standard-normal array for this episode (the reference's
+        reset(**sim_reset_kw) pass-through, fixed_wing.py:287,308) instead of the env's Philox stream."""
         self.ep_return = 0.0
         t = self._begin()
         kw = {}
         if self.turbulence:
-            kw["turbulence_noise"] = self.key.turbulence_noise(t, self.env.cfg["steps_max"])
+            kw["turbulence_noise"] = (self.key.turbulence_noise(t, self.env.cfg["steps_max"])
+                                      if turbulence_noise is None else np.asarray(turbulence_noise, dtype=np.float64))
         return self.env.reset(state=state, target=target, **kw)
 
     def step(self, action):

@@ -361,6 +361,92 @@ def test_fp32_mode_feature_config_integer_state(built_lib):
     v32.close(), v64.close()
 
 
+def test_seed_then_reset_reproduces_episodes(built_lib):
+    """FixedWingAircraft.seed reseeds the env's generator and the simulator (fixed_wing.py:214-222): on a LIVE env,
+    seed(s) + reset() must replay the same episodes (the per-env draw counters restart with the key)."""
+    c = CASES["turb_noise"]
+    vec = make_vec(c, n=64, seed=5)
+    acts = torch.rand((8, 64, 3), dtype=torch.float64, device=vec.device) * 2 - 1
+    runs = []
+    for rep in range(2):
+        vec.seed(123)
+        obs = [vec.reset().clone()]
+        for a in acts:
+            obs.append(vec.step_tensors(a)[0].clone())
+        runs.append(torch.stack(obs))
+    assert torch.equal(runs[0], runs[1])
+    vec.seed(124)
+    assert not torch.equal(vec.reset(), runs[0][0])
+    vec.close()
+
+
+def test_watchdog_error_is_sticky(built_lib):
+    """An env-kernel block that gives up waiting for its aircraft must not pass silently: nothing is committed for
+    its envs, and fw_step / fw_counters / the host pipeline fail until a full reset re-arms the step queue."""
+    from fwgym_b200 import _capi
+    c = CASES["default"]
+    vec = make_vec(c, n=300, seed=2)
+    vec.reset()
+    acts = torch.zeros((300, 3), dtype=torch.float64, device=vec.device)
+    vec.step_tensors(acts)
+    before = vec.get_state().clone()
+    _capi.check(vec._lib.fw_debug_watchdog(vec._h, 64, 1))       # block 0 of the next step waits for a 129th aircraft
+    obs, rew, done, term = vec.step_tensors(acts)                 # enqueues; the error surfaces at the next call
+    torch.cuda.synchronize()
+    assert torch.isnan(obs[:128]).all() and torch.isnan(rew[:128]).all() and (term[:128] == -1).all()
+    assert torch.isfinite(obs[128:]).all()                        # the other blocks stepped normally
+    with pytest.raises(_capi.FwError, match="gave up waiting"):
+        vec.step_tensors(acts)
+    with pytest.raises(_capi.FwError, match="gave up waiting"):
+        vec.counters()
+    with pytest.raises(_capi.FwError):
+        vec.reset(indices=[0])                                    # a partial reset does not recover
+    _capi.check(vec._lib.fw_debug_watchdog(vec._h, 0, 0))
+    rows = vec.state_rows()
+    after = vec.get_state()
+    assert torch.equal(after[:, :128], before[:, :128])           # nothing was committed for the starved chunk
+    assert (after[rows.index("steps_count"), 128:] == before[rows.index("steps_count"), 128:] + 1).all()
+    vec.reset()                                                   # full reset: flag cleared, queue re-armed
+    for _ in range(3):
+        obs, rew, done, term = vec.step_tensors(acts)
+    assert torch.isfinite(obs).all() and vec.counters()["watchdog"] >= 1
+    vec.close()
+
+
+def test_injected_turbulence_noise(built_lib):
+    """reset(turbulence_noise=...) (fixed_wing.py:287,308 -> PyFly.reset): the caller's [4, T] standard-normal samples
+    drive the Dryden filters of the episode instead of the env's own stream; compared with the CPU oracle given the
+    same arrays, per env, incl. the wrap-around past T and the return to the Philox stream after an auto-reset."""
+    c = dict(CASES["turb_noise"])
+    c["config_kw"] = dict(c["config_kw"], steps_max=25)
+    n, T = 4, 12
+    noise = np.random.RandomState(7).standard_normal((n, 4, T))
+    vec = make_vec(c, n=n, seed=9)
+    vec.enable_f64_outputs(True)
+    vec.reset(turbulence_noise=noise)
+    orc = pu.make_oracles(n, harness.config_path(c["config"]), c["config_kw"], c["sim_kw"], 9)
+    obs_o = np.stack([np.asarray(o.reset(turbulence_noise=noise[i]), dtype=np.float64).ravel() for i, o in enumerate(orc)])
+    assert pu.rel_err(vec._obs64.cpu().numpy(), obs_o, 1e-3).max() <= TOL
+    acts = np.random.RandomState(8).uniform(-1, 1, (40, n, 3))
+    dones = 0
+    for a in acts:
+        _, _, done, _ = vec.step_tensors(torch.as_tensor(a, dtype=torch.float64, device=vec.device))
+        res = [o.step(a[i]) for i, o in enumerate(orc)]
+        assert np.array_equal(done.cpu().numpy().astype(bool), np.array([r[2] for r in res]))
+        dones += int(done.sum())
+        assert pu.rel_err(vec._obs64.cpu().numpy(), np.stack([np.ravel(r[0]) for r in res]), 1e-3).max() <= TOL
+        assert pu.rel_err(pu.gpu_state(vec), np.stack([o.ode_state() for o in orc]), 1e-3).max() <= TOL
+    assert dones >= n          # every env went through an auto-reset and back to its own stream
+    # the single-env facade forwards the keyword like the reference
+    from fwgym_b200 import FixedWingAircraft
+    env = FixedWingAircraft(harness.config_path(c["config"]), config_kw=c["config_kw"], sim_config_kw=c["sim_kw"])
+    env.seed(9)
+    o1 = env.reset(turbulence_noise=noise[0])
+    assert pu.rel_err(o1, obs_o[0], 1e-3).max() <= TOL
+    env.close()
+    vec.close()
+
+
 def test_single_env_facade(built_lib):
     """FixedWingAircraft facade (N=1): reference constructor / reset / step signatures and 4-tuple."""
     from fwgym_b200 import FixedWingAircraft
