@@ -41,7 +41,10 @@ def parse():
                          "same moment, and with random actions the whole batch reaches stall / failure together around "
                          "step 50-65 (a burst of dopri5 stragglers with 15-35 attempts); after ~200 steps the episode ages "
                          "are mixed and the step time is the stationary one")
-    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
+    ap.add_argument("--e2e-steps", type=int, default=0,
+                    help="steps of the end-to-end passes (default: max(--steps, 200): a 20-step window is 4-8 ms of wall "
+                         "clock and +-10 %% noisy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -171,17 +174,13 @@ def run_gpu_arm(a):
     os.dup2(2, 1)
     if world != a.gpus and world > 1:
         a.gpus = world
-    if world > 1 and hasattr(os, "sched_setaffinity"):
-        # one block of host cores per rank: the e2e loop is a tight submit / wait cycle, and 8 such loops plus the
-        # driver's helper threads migrating over the same cores cost the slowest rank (= the reported time) up to 1.6x
-        try:
-            cores = sorted(os.sched_getaffinity(0))
-            per = max(1, len(cores) // world)
-            mine = cores[local * per:(local + 1) * per] or cores
-            os.sched_setaffinity(0, mine)
-        except OSError:
-            pass
     torch.cuda.set_device(local)
+    placement = None
+    if world > 1:
+        # one block of host cores per rank ON THE NUMA NODE OF ITS GPU, chosen before any pinned host memory exists: the
+        # e2e loop is a tight submit / wait cycle and its results cross PCIe into host DRAM every step
+        from fwgym_b200.parallel import bind_to_gpu_numa_node
+        placement = bind_to_gpu_numa_node(local, world)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -242,72 +241,138 @@ def run_gpu_arm(a):
         ev[k][1].record()
     barrier()
     wall = time.perf_counter() - t_wall0
-    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    step_ms = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+    ms = sum(step_ms)
     ctr = vec.counters()
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel times for the roofline: a separate pass with an event between the dynamics kernels and the env
     # kernel (that event serialises the two; in the timed region above the env kernel runs as a programmatic dependent
     # of the attempt kernel and overlaps its tail)
     vec.set_profiling(True)
+    k_hist = torch.zeros(64, dtype=torch.int64, device=dev)     # dopri5 attempts per env step; bin 63 = 63 and more
+    k_max = torch.zeros((), dtype=torch.int32, device=dev)
     for k in range(prof_steps_n):
         flush_l2()
         vec.step_tensors(actions[a.warmup + a.steps + k])
+        la = vec.last_attempts()
+        k_hist += torch.bincount(la.clamp(max=63).long(), minlength=64)
+        k_max = torch.maximum(k_max, la.max())
     dyn_ms, env_ms, prof_steps = vec.profile()
     vec.set_profiling(False)
     ctr_prof = vec.counters()
+    msum_local = vec.metric_sums()        # episode metric sums of the device-resident passes
+    launches_per_step = vec.launches_per_step
     prof_env_steps = ctr_prof["env_steps"] - ctr["env_steps"]
     prof_attempts = ctr_prof["attempts"] - ctr["attempts"]
 
-    # ---- end-to-end through the public API with HOST buffers (fwgym_b200.HostStepper): every step moves its actions
-    # pinned-host -> device and its observations / rewards / dones device -> pinned-host; two submissions in flight,
-    # so the PCIe traffic of step t overlaps the kernels of step t+1.  The loop ends when the LAST step's results
-    # are on the host.
+    # ---- end-to-end through the public API with HOST buffers (fwgym_b200.HostStepper over the C-ABI fw_host_submit /
+    # fw_host_wait): every step moves its actions pinned-host -> device and its observations / rewards / dones /
+    # termination codes device -> pinned-host.  Three call patterns, all from a fresh reset + the same burn-in:
+    #   closed loop, two half-batches ping-ponged (THE e2e value): a policy needs obs_t before it can send a_{t+1}
+    #     (evaluate_controller.py:153-154, train_rl_controller.py:223), so each half-batch handle has ONE step in flight
+    #     and its next submit happens only after its previous results are on the host; while half A's results travel and
+    #     the host turns them around, half B's kernels run.
+    #   closed loop, one handle, depth 1: the same dependency without the second half: the GPU idles during the copies.
+    #   open loop, depth 2 (round 1's number): action t+1 is sent before observation t is read - an upper bound no
+    #     policy can use.
     from fwgym_b200 import HostStepper
-    stepper = HostStepper(vec, depth=int(os.environ.get("FWGYM_HOST_DEPTH", "2")))
-    host_actions = (torch.rand((a.steps + a.warmup, n, 3)) * 2 - 1).pin_memory()
-    e2e_steps = a.steps
+    e2e_steps = a.e2e_steps or max(a.steps, 200)
+    n_act = 48
+    host_actions = (torch.rand((n_act, n, 3)) * 2 - 1).pin_memory()
     checksum = 0.0
+    host_split = [0.0, 0.0]     # seconds inside submit() / wait() of the ping-pong pass (diagnostics)
 
-    host_split = [0.0, 0.0]     # seconds inside submit() / wait() (diagnostics)
-
-    def e2e_run(first, count):
+    def e2e_open(stepper, first, count):
         nonlocal checksum
         pending = []
         for i in range(count):
-            ta = time.perf_counter()
-            pending.append(stepper.submit(host_actions[first + i]))
-            tb = time.perf_counter()
-            host_split[0] += tb - ta
+            pending.append(stepper.submit(host_actions[(first + i) % n_act]))
             if len(pending) == stepper.depth:
                 obs, rew, done = stepper.wait(pending.pop(0))
-                host_split[1] += time.perf_counter() - tb
                 checksum += float(rew[0])          # touch the host result of every step
         while pending:
-            tb = time.perf_counter()
             obs, rew, done = stepper.wait(pending.pop(0))
-            host_split[1] += time.perf_counter() - tb
             checksum += float(rew[0])
 
-    # same position in the episodes as the device-timed region above: fresh reset, burn-in, W warm-up steps, K timed steps
-    # (the dopri5 work per step drifts as the aircraft of a batch age, so a region further into the episodes would not
-    # be comparable)
+    def timed(fn, warm, count):
+        fn(0, warm)
+        barrier()
+        t0 = time.perf_counter()
+        fn(warm, count)
+        torch.cuda.synchronize(dev)
+        local = time.perf_counter() - t0       # this rank's own time (the reported one is the max over ranks)
+        barrier()
+        return time.perf_counter() - t0, local
+
+    # (c) open loop, depth 2, and (b) closed loop depth 1 on the full-batch handle
+    stepper2 = HostStepper(vec, depth=int(os.environ.get("FWGYM_HOST_DEPTH", "2")))
     vec.reset()
     burn_in()
-    e2e_run(0, a.warmup)
-    barrier()
-    t0 = time.perf_counter()
-    host_split[0] = host_split[1] = 0.0
-    e2e_run(a.warmup, e2e_steps)
+    open_s, _ = timed(lambda f, c: e2e_open(stepper2, f, c), a.warmup, e2e_steps)
+    stepper2.close()
+    stepper1 = HostStepper(vec, depth=1)
+    vec.reset()
+    burn_in()
+    d1_s, _ = timed(lambda f, c: e2e_open(stepper1, f, c), a.warmup, e2e_steps)
+    stepper1.close()
+    h2d_bytes, d2h_bytes = stepper1.h2d_bytes, stepper1.d2h_bytes
+    vec.close()
+
+    # (a) two half-batch handles (global env ids [rank*n, rank*n + n/2) and [rank*n + n/2, (rank+1)*n)), one stream each
+    nh = n // 2
+    halves, steppers, streams = [], [], []
+    for j in range(2):
+        v = FixedWingVecEnv(DEFAULT_ENV_CONFIG, nh if j == 0 else n - nh, device=dev, config_kw=CONFIG_KW,
+                            sim_config_kw=SIM_KW, seed=20261017, env_offset=rank * n + j * nh)
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            v.reset()
+            for i in range(a.burn_in):
+                v.step_tensors(burn_actions[i % 16][j * nh:j * nh + v.num_envs])
+        halves.append(v); streams.append(st); steppers.append(HostStepper(v, depth=1))
     torch.cuda.synchronize(dev)
-    e2e_local = time.perf_counter() - t0       # this rank's own time (the reported one is the max over ranks)
+    half_actions = [host_actions[:, :nh], host_actions[:, nh:]]
+    half_actions = [torch.empty_like(h).copy_(h).pin_memory() for h in half_actions]   # contiguous per half
+
+    def e2e_pingpong(first, count):
+        nonlocal checksum
+        slots = [None, None]
+        for i in range(count + 1):
+            for j in range(2):
+                tb = time.perf_counter()
+                if slots[j] is not None:
+                    obs, rew, done = steppers[j].wait(slots[j])      # obs_t of this half is on the host ...
+                    checksum += float(rew[0]) + float(obs[0, 0])
+                    slots[j] = None
+                tc = time.perf_counter()
+                host_split[1] += tc - tb
+                if i < count:
+                    with torch.cuda.stream(streams[j]):               # ... before its a_{t+1} is sent
+                        slots[j] = steppers[j].submit(half_actions[j][(first + i) % n_act])
+                    host_split[0] += time.perf_counter() - tc
+
+    e2e_pingpong(0, a.warmup)
+    barrier()
+    host_split[0] = host_split[1] = 0.0
+    t0 = time.perf_counter()
+    e2e_pingpong(a.warmup, e2e_steps)
+    torch.cuda.synchronize(dev)
+    e2e_local = time.perf_counter() - t0
     barrier()
     e2e_s = time.perf_counter() - t0
+    half_watchdog = sum(v.counters()["watchdog"] for v in halves)
 
-    tt = torch.tensor([ms, e2e_s * 1e3, dyn_ms, env_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    place_all = [placement]
+    if world > 1:
+        place_all = [None] * world
+        dist.all_gather_object(place_all, placement)
+    tt = torch.tensor([ms, e2e_s * 1e3, dyn_ms, env_ms, wall * 1e3, open_s * 1e3, d1_s * 1e3, step_ms[-1]],
+                      dtype=torch.float64, device=dev)
     cnt = torch.tensor([ctr["env_steps"], ctr["attempts"], ctr["warp_max_attempts"], ctr["warp_steps"],
-                        ctr["failures"], ctr["resets"], prof_env_steps, prof_attempts, ctr_prof["watchdog"]],
+                        ctr["failures"], ctr["resets"], prof_env_steps, prof_attempts,
+                        ctr_prof["watchdog"] + half_watchdog],
                        dtype=torch.float64, device=dev)
-    msum = torch.tensor(vec.metric_sums(), dtype=torch.float64, device=dev)
+    msum = torch.tensor(msum_local, dtype=torch.float64, device=dev)
     e2e_each = [e2e_local * 1e6 / e2e_steps]
     if world > 1:
         g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
@@ -316,11 +381,14 @@ def run_gpu_arm(a):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)     # time = max over ranks
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         dist.all_reduce(msum, op=dist.ReduceOp.SUM)   # the only data-path collective: episode metric sums
-    ms, e2e_ms, dyn_ms, env_ms, wall_ms = tt.tolist()
+    ms, e2e_ms, dyn_ms, env_ms, wall_ms, open_ms, d1_ms, step_max_ms = tt.tolist()
     env_steps, attempts, wmax, wsteps, failures, resets, p_env_steps, p_attempts, watchdog = cnt.tolist()
     if rank == 0:
         total_env_steps = float(n) * a.steps * world
+        e2e_env_steps = float(n) * e2e_steps * world
         value = total_env_steps / (ms * 1e-3)
+        pct = lambda q: step_ms[min(len(step_ms) - 1, int(q * len(step_ms)))]
+        kh = k_hist.cpu().numpy()
         k_mean = attempts / max(1.0, env_steps)
         # roofline of the dominant kernel (dynamics, FP64 pipe): algorithmic flops of ONE rank / its kernel time
         fl = ctypes.c_double()
@@ -328,12 +396,15 @@ def run_gpu_arm(a):
         _capi.check(_capi.lib().fw_dfma_peak(local, ctypes.byref(fl), ctypes.byref(pk_ms)))
         flops_rank = (F_FIXED * p_env_steps + F_ATTEMPT * p_attempts) / world   # of the profiled pass
         achieved = flops_rank / (dyn_ms * 1e-3) / 1e12
-        traffic, ncu_notes = None, None
+        # DRAM traffic cannot be measured outside a profiler: the number is COPIED from the committed ncu capture named
+        # in traffic_from (profiles/traffic.json says which file, commit and workload), it is not a live measurement
+        traffic, ncu_notes, traffic_from = None, None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
             traffic, ncu_notes = tj.get("dyn_kernel_dram_bytes_per_launch"), tj.get("ncu")
+            traffic_from = tj.get("from")
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -344,15 +415,28 @@ def run_gpu_arm(a):
                                 if flush_mode == "write+read" else ""),
                        "parallelism": "env-sharded x%d, no step-path collective" % world},
             "clocks": clocks,
-            "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
-                    "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes,
+            "step_ms": {"p50": pct(0.5), "p99": pct(0.99), "max_rank0": step_ms[-1], "max_any_rank": step_max_ms,
+                        "min": step_ms[0], "note": "per-step CUDA-event times of the timed region on rank 0: rare dopri5 "
+                        "stragglers (attempts_per_env_step.max) stretch single steps"},
+            "e2e": {"value": e2e_env_steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "pattern": "closed loop: 2 half-batch handles per GPU ping-ponged, one step in flight each; a "
+                               "half's a_{t+1} is submitted only after its obs_t / reward_t / done_t are in host memory",
+                    "closed_loop_depth1": {"value": e2e_env_steps / (d1_ms * 1e-3),
+                                           "pattern": "one handle, one step in flight (GPU idle during copies)"},
+                    "open_loop_depth2": {"value": e2e_env_steps / (open_ms * 1e-3),
+                                         "pattern": "round 1's figure: a_{t+1} sent before obs_t is read; an upper bound "
+                                                    "no policy can use"},
                     "us_per_step_by_rank": [round(x, 1) for x in e2e_each],
+                    "host_placement_by_rank": place_all,
                     "rank0_host_us_per_step": {"submit": round(host_split[0] * 1e6 / e2e_steps, 1),
                                                "wait": round(host_split[1] * 1e6 / e2e_steps, 1)},
-                    "how": "C-ABI fw_host_submit / fw_host_wait (HostStepper, depth 2): actions from pinned host memory, observations / rewards / dones / termination codes to pinned host memory every step, copies on their own streams, wall clock"},
-            "gpu_launches": int(vec.launches_per_step * a.steps),
+                    "how": "C-ABI fw_host_submit / fw_host_wait (HostStepper): actions from pinned host memory, "
+                           "observations / rewards / dones / termination codes to pinned host memory every step, copies "
+                           "on their own streams, wall clock over %d steps after %d warm-up steps" % (e2e_steps, a.warmup)},
+            "gpu_launches": int(launches_per_step * a.steps),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fl.value / 1e12, "unit": "TFLOP/s",
-                         "frac": achieved / (fl.value / 1e12), "traffic": traffic,
+                         "frac": achieved / (fl.value / 1e12), "traffic": traffic, "traffic_from": traffic_from,
                          "peak_source": "DFMA micro-benchmark run in this process (fw_dfma_peak); MEASURED_PEAKS.json "
                                         "has no FP64 entry",
                          "kernel": "fw_init_kernel + fw_attempt_kernel <double> (the simulator step; timed together)",
@@ -361,8 +445,11 @@ def run_gpu_arm(a):
                          "how": "%d extra steps with an event between the dynamics and env kernels (serialised); the "
                                 "timed region runs them overlapped" % prof_steps,
                          "flops_per_env_step": "1080 + 3660*k, k = dopri5 attempts counted on device",
-                         "ncu_capture": ncu_notes,   # from the committed ncu --set full capture (profiles/), not live
+                         "ncu_capture": ncu_notes,   # ditto: from the committed capture, not live
                          "mean_attempts_per_env_step": k_mean,
+                         "attempts_per_env_step": {"histogram_1_to_16": [int(x) for x in kh[1:17]],
+                                                   "more_than_16": int(kh[17:].sum()), "zero": int(kh[0]),
+                                                   "max": int(k_max.item()), "over": "%d profiled steps" % prof_steps},
                          "warp_divergence": {"warp_passes": wmax / world, "lane_attempts": wsteps / world,
                                              "lane_efficiency": wsteps / max(1.0, 32.0 * wmax)}},
             "env_kernel": {"bound": "hbm", "ms_per_launch": env_ms / max(1, prof_steps),

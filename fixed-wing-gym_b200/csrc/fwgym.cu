@@ -75,8 +75,9 @@ struct fw_handle_s {
   std::vector<cudaEvent_t> ev;   // 3 events per profiled step: before dyn, between, after env
   // host-buffer pipeline (fw_host_*): `depth` slots of device staging + pinned host result buffers, copy streams
   struct HostSlot {
-    float* d_act; float* d_obs; float* d_rew; uint8_t* d_done; int32_t* d_term;
-    float* h_obs; float* h_rew; uint8_t* h_done; int32_t* h_term;
+    float* d_act; float* d_obs; float* d_rew; uint8_t* d_done; int32_t* d_term;   // d_obs .. d_done: ONE block, one D2H copy
+    float* h_obs; float* h_rew; uint8_t* h_done; int32_t* h_term;                   // likewise one pinned block
+    size_t out_bytes;
     cudaEvent_t e_in, e_step, e_out;
     int busy;
   };
@@ -1317,8 +1318,8 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
 // ---- host-buffer stepping ---------------------------------------------------------------------------------------
 static void host_free(fw_handle h) {
   for (auto& sl : h->hs) {
-    cudaFree(sl.d_act); cudaFree(sl.d_obs); cudaFree(sl.d_rew); cudaFree(sl.d_done); cudaFree(sl.d_term);
-    cudaFreeHost(sl.h_obs); cudaFreeHost(sl.h_rew); cudaFreeHost(sl.h_done); cudaFreeHost(sl.h_term);
+    cudaFree(sl.d_act); cudaFree(sl.d_obs);
+    cudaFreeHost(sl.h_obs);
     if (sl.e_in) cudaEventDestroy(sl.e_in);
     if (sl.e_step) cudaEventDestroy(sl.e_step);
     if (sl.e_out) cudaEventDestroy(sl.e_out);
@@ -1339,13 +1340,11 @@ int fw_host_open(fw_handle h, int depth) {
     fw_handle_s::HostSlot sl = {};
     h->hs.push_back(sl);
     fw_handle_s::HostSlot& r = h->hs.back();
+    // results of a step in one block [obs | reward | termination code | done]: one device -> host copy per step
+    r.out_bytes = n * (od * sizeof(float) + sizeof(float) + sizeof(int32_t) + 1);
     if (cudaMalloc(&r.d_act, n * FW_N_ACT * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&r.d_obs, n * od * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&r.d_rew, n * sizeof(float)) != cudaSuccess || cudaMalloc(&r.d_done, n) != cudaSuccess ||
-        cudaMalloc(&r.d_term, n * sizeof(int32_t)) != cudaSuccess ||
-        cudaMallocHost(&r.h_obs, n * od * sizeof(float)) != cudaSuccess ||
-        cudaMallocHost(&r.h_rew, n * sizeof(float)) != cudaSuccess || cudaMallocHost(&r.h_done, n) != cudaSuccess ||
-        cudaMallocHost(&r.h_term, n * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc(&r.d_obs, r.out_bytes) != cudaSuccess ||
+        cudaMallocHost(&r.h_obs, r.out_bytes) != cudaSuccess ||
         cudaEventCreateWithFlags(&r.e_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&r.e_step, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&r.e_out, cudaEventDisableTiming | (getenv("FWGYM_HOST_BLOCKING") ? cudaEventBlockingSync : 0)) != cudaSuccess) {
@@ -1353,6 +1352,10 @@ int fw_host_open(fw_handle h, int depth) {
       host_free(h);
       return fail(FW_ERR_ALLOC, "fw_host_open: allocation failed: %s", msg);
     }
+    r.d_rew = r.d_obs + n * od; r.d_term = reinterpret_cast<int32_t*>(r.d_rew + n);
+    r.d_done = reinterpret_cast<uint8_t*>(r.d_term + n);
+    r.h_rew = r.h_obs + n * od; r.h_term = reinterpret_cast<int32_t*>(r.h_rew + n);
+    r.h_done = reinterpret_cast<uint8_t*>(r.h_term + n);
   }
   return FW_OK;
 }
@@ -1381,10 +1384,7 @@ int fw_host_submit(fw_handle h, const float* actions_host, void* stream, int* sl
   if (rc) return rc;
   CK(cudaEventRecord(sl.e_step, s));
   CK(cudaStreamWaitEvent(h->hs_out, sl.e_step, 0));
-  CK(cudaMemcpyAsync(sl.h_obs, sl.d_obs, n * od * sizeof(float), cudaMemcpyDeviceToHost, h->hs_out));
-  CK(cudaMemcpyAsync(sl.h_rew, sl.d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs_out));
-  CK(cudaMemcpyAsync(sl.h_done, sl.d_done, n, cudaMemcpyDeviceToHost, h->hs_out));
-  CK(cudaMemcpyAsync(sl.h_term, sl.d_term, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->hs_out));
+  CK(cudaMemcpyAsync(sl.h_obs, sl.d_obs, sl.out_bytes, cudaMemcpyDeviceToHost, h->hs_out));
   CK(cudaEventRecord(sl.e_out, h->hs_out));
   sl.busy = 1;
   h->hs_next += 1;

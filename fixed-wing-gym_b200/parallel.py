@@ -60,3 +60,60 @@ def allreduce_metric_sums(env_or_sums, device=None):
     out.update(success_rate=out["successes"] / ep, mean_return=out["sum_return"] / ep,
                mean_length=out["sum_length"] / ep, failure_rate=out["failures"] / ep)
     return out
+
+
+# ---- host placement: the host-buffer pipeline (HostStepper) is PCIe + host-DRAM traffic ------------------------------
+def _parse_cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(index):
+    """NUMA node the GPU's PCIe root hangs off (sysfs), or -1 when the platform does not say."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            return int(f.read().strip())
+    except Exception:
+        return -1
+
+
+def bind_to_gpu_numa_node(local_rank, n_local_ranks):
+    """Pin the calling process to host cores on the NUMA node of GPU `local_rank`, sharing that node's cores with the
+    other local ranks whose GPU sits on the same node.  Call it BEFORE allocating pinned host memory (cudaHostAlloc
+    places pages on the calling thread's node): results then travel GPU -> PCIe root -> local DRAM instead of crossing
+    the socket interconnect.  Returns a dict describing what was done (for the bench line); a no-op where sysfs has no
+    topology."""
+    import os
+    info = {"numa_node": -1, "cores": None}
+    if not hasattr(os, "sched_setaffinity"):
+        return info
+    allowed = sorted(os.sched_getaffinity(0))
+    nodes = [gpu_numa_node(i) for i in range(n_local_ranks)]
+    mine = nodes[local_rank]
+    info["numa_node"] = mine
+    pool = allowed
+    if mine >= 0:
+        try:
+            with open("/sys/devices/system/node/node%d/cpulist" % mine) as f:
+                local = [c for c in _parse_cpulist(f.read()) if c in set(allowed)]
+            if local:
+                pool = local
+        except OSError:
+            pass
+    peers = [r for r in range(n_local_ranks) if nodes[r] == mine] if pool is not allowed else list(range(n_local_ranks))
+    per = max(1, len(pool) // max(1, len(peers)))
+    k = peers.index(local_rank)
+    cores = pool[k * per:(k + 1) * per] or pool
+    try:
+        os.sched_setaffinity(0, cores)
+        info["cores"] = [cores[0], cores[-1]]
+    except OSError:
+        pass
+    return info

@@ -8,7 +8,7 @@ set_curriculum_level :224-285, reset :287-336, step :338-437, linear_action_scal
 (SURVEY App. A): value-target sign for wrapped states, observation computed before the history is rebuilt at reset,
 goal_achieved latch never cleared, float32 accumulation of the action-delta observation, noise "var" used as a std.
 
-It is PINNED against the reference's own code: tests/test_oracle_env.py runs the unmodified reference file
+It is PINNED against the reference's own code: tests/test_oracle_cpu.py (test_restated_env_matches_reference_file) runs the unmodified reference file
 (oracle/reference_env.py) and this restatement side by side on identical Philox streams and requires bit-identical
 observations / rewards / dones (in this container, where /root/reference exists), and against the committed fixtures
 under tests/golden/ (generated from the reference file by oracle/make_golden.py) everywhere.

@@ -10,7 +10,7 @@ import numpy as np
 from . import philox
 from .env_restated import RestatedEnv
 
-# PyFly variable order == enum fw_sv in include/fwgym.h (checked by tests/test_capi_cpu.py)
+# PyFly variable order == enum fw_sv in include/fwgym.h (checked by tests/test_oracle_cpu.py::test_capi_exports_every_declared_symbol)
 SV_ORDER = ["roll", "pitch", "yaw", "omega_p", "omega_q", "omega_r", "position_n", "position_e", "position_d",
             "velocity_u", "velocity_v", "velocity_w", "Va", "alpha", "beta", "elevator", "aileron", "rudder",
             "throttle", "elevon_left", "elevon_right"]

@@ -16,7 +16,7 @@ PARITY STATUS: "parity unpinned" at the PyFly boundary — there is no PyFly sou
 that pins intermediate simulator states.  All aircraft/actuator constants come from DATA files
 (`fixed-wing-gym_b200/params/x8_param.json`, `pyfly_config.json`), never from literals here.  The only golden data
 that constrains it is the end-to-end PID reward trace (`examples/evaluations/eval_res_PID_none.npy`); the gap to that
-trace is *reported* by tests/test_golden_trace.py, see DESIGN.md.
+trace is *reported* by tests/test_oracle_cpu.py::test_golden_pid_trace_gap_is_reported, see DESIGN.md.
 
 The integrator is `scipy.integrate.solve_ivp` called literally with defaults (RK45, rtol 1e-3, atol 1e-6), exactly as
 PyFly does, so integrator parity is by construction (scipy/integrate/_ivp/rk.py, common.py in this image: 1.18.1).
