@@ -176,9 +176,11 @@ def run_gpu_arm(a):
         a.gpus = world
     torch.cuda.set_device(local)
     placement = None
-    if world > 1:
-        # one block of host cores per rank ON THE NUMA NODE OF ITS GPU, chosen before any pinned host memory exists: the
-        # e2e loop is a tight submit / wait cycle and its results cross PCIe into host DRAM every step
+    if world > 1 and os.environ.get("FWGYM_BENCH_BIND", "0") == "1":
+        # Opt-in: one block of host cores per rank on the NUMA node of its GPU, chosen before any pinned host memory
+        # exists.  OFF by default: this pool's 8-GPU boxes are VMs with one virtual NUMA node and no GPU affinity in sysfs,
+        # where pinning ranks to core blocks LOWERED the concurrent device -> host bandwidth (12.9 / 21 GB/s per GPU
+        # against 18 / 42 GB/s unpinned; scripts/gpu_d2h_concurrent.py, profiles/r2_n8_d2h_concurrent.txt)
         from fwgym_b200.parallel import bind_to_gpu_numa_node
         placement = bind_to_gpu_numa_node(local, world)
     dev = torch.device("cuda", local)
