@@ -116,6 +116,44 @@ def load_sb2_parameters(model, params):
     return model
 
 
+def compute_gae(rew, val, done, last_val, gamma, lam, adv_out):
+    """Generalised advantage estimation over a rollout [T, N] (PPO2's runner: `done[t]` says the episode ended IN step
+    t, so nothing is bootstrapped across it); writes adv_out in place, row by row."""
+    T = rew.shape[0]
+    gae = torch.zeros_like(last_val)
+    for t in reversed(range(T)):
+        nv = last_val if t == T - 1 else val[t + 1]
+        nonterm = 1.0 - done[t]
+        delta = rew[t] + gamma * nv * nonterm - val[t]
+        gae = delta + gamma * lam * nonterm * gae
+        adv_out[t].copy_(gae)
+    return adv_out
+
+
+class CurriculumCallback:
+    """The curriculum rule of the reference's training callback (train_rl_controller.py:80-87): while the level is below
+    1 and the cooldown has run out, a success rate above the current level raises the level to min(2 * success, 1) on
+    every env and starts a cooldown of 15 callbacks.  `success` = fraction of the episodes that ended since the last
+    callback whose info["success"]["all"] is true (the device's episode-metric sums)."""
+
+    def __init__(self, venv, level=0.25, cooldown=25, cooldown_after_bump=15):
+        self.venv, self.level, self.cooldown, self.after = venv, float(level), int(cooldown), int(cooldown_after_bump)
+        self.bumps = []
+        venv.env_method("set_curriculum_level", self.level)
+
+    def __call__(self, rec):
+        if self.level < 1 and rec.get("episodes", 0) > 0:
+            if self.cooldown <= 0:
+                if rec["success_rate"] > self.level:
+                    self.level = min(rec["success_rate"] * 2, 1)
+                    self.venv.env_method("set_curriculum_level", self.level)
+                    self.cooldown = self.after
+                    self.bumps.append((rec["iter"], self.level))
+            else:
+                self.cooldown -= 1
+        rec["curriculum_level"] = self.level
+
+
 def _allreduce_grads(model):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         w = dist.get_world_size()
@@ -126,12 +164,16 @@ def _allreduce_grads(model):
 
 
 def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.5e-4, gamma=0.99, lam=0.95,
-          clip_range=0.2, ent_coef=0.01, vf_coef=0.5, max_grad_norm=0.5, seed=0, model=None, log=None, cuda_graph=True):
+          clip_range=0.2, ent_coef=0.01, vf_coef=0.5, max_grad_norm=0.5, seed=0, model=None, log=None, cuda_graph=True,
+          callback=None):
     """PPO2-default training on a FixedWingVecEnv.  Returns (model, normalizer, stats); stats has env-steps/s inside
     training and the split of the device time (CUDA events): eager mode env / policy_forward / ppo_update, graph mode
     rollout / ppo_update (the rollout is one graph launch, so it has no inner split).
     cuda_graph: capture the rollout + GAE of an iteration once (at the second iteration; the first runs eagerly and
-    warms every allocation up) and replay it afterwards."""
+    warms every allocation up) and replay it afterwards.
+    callback(rec): called after every iteration with its record (episodes that ended in it, their success rate / mean
+    return / mean length from the device's metric sums, losses, timings), e.g. CurriculumCallback; it may change the env
+    configuration (the rollout graph is re-captured when it does)."""
     dev = venv.device
     torch.manual_seed(seed)
     norm = DeviceVecNormalize(venv, gamma=gamma)
@@ -171,20 +213,14 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
                 if marks is not None:
                     a2.record()
                     marks.append((a0, a1, a2))
-            last_val = model.value(obs)
-            gae = torch.zeros(n, device=dev)
-            for t in reversed(range(n_steps)):
-                nv = last_val if t == n_steps - 1 else buf["val"][t + 1]
-                nonterm = 1.0 - buf["done"][t]
-                delta = buf["rew"][t] + gamma * nv * nonterm - buf["val"][t]
-                gae = delta + gamma * lam * nonterm * gae
-                adv[t].copy_(gae)
+            compute_gae(buf["rew"], buf["val"], buf["done"], model.value(obs), gamma, lam, adv)
             torch.add(adv, buf["val"], out=ret)
 
     t_env = t_pol = t_upd = t_roll = 0.0
     iters = max(1, int(total_env_steps) // B)
     stats = {"iterations": iters, "batch": B, "history": [], "cuda_graph": bool(cuda_graph)}
     graph, graph_version = None, -1
+    sums_prev = np.asarray(venv.metric_sums(), dtype=np.float64)
     torch.cuda.synchronize(dev)
     wall0 = time.perf_counter()
     for it in range(iters):
@@ -236,9 +272,20 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
         pol_ms = sum(a0.elapsed_time(a1) for a0, a1, _ in marks)
         env_ms = sum(a1.elapsed_time(a2) for _, a1, a2 in marks)
         t_env, t_pol, t_upd, t_roll = t_env + env_ms, t_pol + pol_ms, t_upd + upd_ms, t_roll + roll_ms
+        sums = np.asarray(venv.metric_sums(), dtype=np.float64)     # episodes, successes, sum_return, sum_length, ...
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from .parallel import allreduce_sum
+            sums = allreduce_sum(sums, dev)
+        d_ep = sums - sums_prev
+        sums_prev = sums
+        ep = max(d_ep[0], 1.0)
         rec = {"iter": it, "loss": float(loss.detach()), "mean_norm_reward": float(buf["rew"].mean()),
                "value_loss": float(vl.detach()), "rollout_ms": roll_ms, "env_ms": env_ms, "policy_ms": pol_ms,
-               "update_ms": upd_ms}
+               "update_ms": upd_ms, "episodes": int(d_ep[0]), "success_rate": float(d_ep[1] / ep),
+               "mean_episode_return": float(d_ep[2] / ep), "mean_episode_length": float(d_ep[3] / ep),
+               "failure_rate": float(d_ep[4] / ep)}
+        if callback is not None:
+            callback(rec)
         stats["history"].append(rec)
         if log:
             log(rec)

@@ -96,3 +96,10 @@ def test_ppo_loop_runs(built_lib, graph):
     print("PPO smoke (cuda_graph=%s): %.3g env-steps/s inside training; time split %s"
           % (graph, stats["env_steps_per_s"], {k: round(v, 3) for k, v in stats["time_fraction"].items()}))
     env.close()
+
+
+def test_vecnormalize_and_gae_on_device(built_lib):
+    """DeviceVecNormalize / compute_gae on cuda:0 against the numpy twins of stable-baselines' VecNormalize and PPO2's
+    GAE (tests/test_ppo_cpu.py holds the oracle and runs the same check on the CPU)."""
+    import test_ppo_cpu
+    test_ppo_cpu.check_vecnormalize_and_gae("cuda:0")
