@@ -448,6 +448,7 @@ class CompiledConfig:
         s.exp_2Ma0 = float(np.exp(2.0 * P["M"] * P["a_0"]))
         s.drag_model = {"induced": 0, "polynomial": 1}[sc.get("drag_model", "induced")]
         s.turbulence = 1 if sc["turbulence"] else 0
+        s.max_attempts = int(sc.get("dopri5_max_attempts", 0) or 0)   # opt-in, not a PyFly key: 0 = the reference's behaviour
         s.wind_mag_min, s.wind_mag_max = sc["wind_magnitude_min"], sc["wind_magnitude_max"]
         s.wind_enabled = 1 if (sc["wind_magnitude_max"] != 0 or sc["wind_magnitude_min"] != 0
                                or sc.get("allow_wind_injection", False)) else 0

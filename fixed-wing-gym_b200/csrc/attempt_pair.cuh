@@ -434,7 +434,14 @@ fw_attempt_pair_kernel(const __grid_constant__ fw_sim_t P, const FwDynArgs a) {
     const double tb = P.dt;
     const double min_step = 10 * fabs(FwMath<double>::next_up(S.t) - S.t);
     if (act && !S.rejected && S.h_abs < min_step) S.h_abs = min_step;
-    if (act && (S.h_abs < min_step || S.attempts >= FW_MAX_ATTEMPTS)) { S.status = FW_STATUS_TOO_SMALL; act = false; }
+    if (act) {   // NaN step sizes and the attempt cap end the step as a NUMERIC failure (dynamics.cuh, fw_ivp_attempt)
+      const int cap = P.max_attempts > 0 ? P.max_attempts : FW_MAX_ATTEMPTS;
+      if (!(S.h_abs >= min_step) || S.attempts >= cap) {
+        if (S.h_abs < min_step) S.status = FW_STATUS_TOO_SMALL;
+        else { S.fail = FW_TERM_NUMERIC; S.status = FW_STATUS_FINISHED; }
+        act = false;
+      }
+    }
     double t_new = S.t + S.h_abs;
     if (t_new - tb > 0) t_new = tb;
     const double h = act ? t_new - S.t : 0.0;

@@ -11,7 +11,10 @@
 #define FW_STATUS_RUNNING 0
 #define FW_STATUS_FINISHED 1
 #define FW_STATUS_TOO_SMALL 2
-#define FW_MAX_ATTEMPTS 100000   // hang guard; a healthy env step takes 2..10 attempts
+// Hang guard: a healthy env step takes 2..10 attempts; the worst finite case observed (a sideways-sliding aircraft
+// sitting on the atan2(w, u) singularity of alpha, turbulence off) 4 300.  Beyond the guard are only states that have
+// left physics (unconstrained body rates of 1e150 rad/s: step sizes of 1e-17 s, i.e. 1e15 attempts in scipy).
+#define FW_MAX_ATTEMPTS 20000
 
 template <typename T> struct FwMath;
 // fp64: the branch-free routines of fwmath.cuh (straight-line, Estrin polynomials, constant-bank coefficients) so
@@ -509,9 +512,16 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
   // ---- start a step attempt (rk.py:111-147); min_step = 10 * |nextafter(t, inf) - t|
   const T min_step = 10 * fabs(Mt::next_up(S.t) - S.t);
   if (!S.rejected && S.h_abs < min_step) S.h_abs = min_step;      // clamp on entry to _step_impl only
-  if (S.h_abs < min_step || S.attempts >= FW_MAX_ATTEMPTS) {
-    S.status = FW_STATUS_TOO_SMALL;   // (the attempt cap is a hang guard: NaN step sizes never shrink)
-    return;
+  {
+    // A NaN step size never shrinks below min_step: scipy's loop would spin forever.  That, and an env step that
+    // exceeds the attempt cap (the opt-in fw_sim_t.max_attempts, else the hang guard), ends the step as a NUMERIC
+    // failure.  (`!(a >= b)` is true for NaN.)
+    const int cap = P.max_attempts > 0 ? P.max_attempts : FW_MAX_ATTEMPTS;
+    if (!(S.h_abs >= min_step) || S.attempts >= cap) {
+      if (S.h_abs < min_step) S.status = FW_STATUS_TOO_SMALL;     // scipy: "step size too small"; PyFly carries on
+      else { S.fail = FW_TERM_NUMERIC; S.status = FW_STATUS_FINISHED; }
+      return;
+    }
   }
   T t_new = S.t + S.h_abs;
   if (t_new - tb > 0) t_new = tb;

@@ -238,7 +238,8 @@ fw_init_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDy
     for (int j = 0; j < FW_N_ODE; ++j) y[j] = (T)c.D(j);
     const FwPar<T, Spec::rand ? FW_PAR_GLOBAL : FW_PAR_CONST> PP{P, a.d + (int64_t)a.par_row * a.stride + env, a.stride,
                                                                    nullptr};
-    const int failv = fw_ivp_init<T, Spec>(P, PP, in, y, f0, h_abs);
+    int failv = fw_ivp_init<T, Spec>(P, PP, in, y, f0, h_abs);
+    if (!failv && !((double)h_abs * 0.0 == 0.0)) failv = FW_TERM_NUMERIC;   // non-finite first step: nothing to integrate
     double* cd = a.cd + env;
     int32_t* ci = a.ci + env;
 #pragma unroll
@@ -464,6 +465,13 @@ __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx
     double yd[FW_N_ODE];
 #pragma unroll
     for (int j = 0; j < FW_N_ODE; ++j) yd[j] = __ldcg(cd + (CY_RES + j) * stride);
+    {   // a state that left the representable range ends the episode (FW_TERM_NUMERIC) instead of feeding NaNs back;
+        // the checks below keep the first failure and the state rows are only written when there is none
+      double chk = 0.0;
+#pragma unroll
+      for (int j = 0; j < FW_N_ODE; ++j) chk = fma(yd[j], 0.0, chk);
+      if (chk != 0.0) failv = FW_TERM_NUMERIC;
+    }
     double roll = 0, pitch = 0, yaw = 0, Va = 0, alpha = 0, beta = 0, elev = 0, ail = 0;
     // quaternion / |quaternion|, Euler angles: fwmath routines (asin(x) = atan2(x, sqrt((1 - x)(1 + x))))
     double qn, iqn;

@@ -15,7 +15,7 @@ import torch
 from . import _capi
 from .config import CompiledConfig
 
-TERM_NAMES = {0: None, 1: "steps", 2: "success"}
+TERM_NAMES = {0: None, 1: "steps", 2: "success", 3: "numeric"}
 N_INIT_ROWS = _capi.DEFINES["FW_N_SV"] + 3
 WIND_KEYS = ("wind_n", "wind_e", "wind_d")
 

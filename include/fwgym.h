@@ -75,6 +75,10 @@ enum fw_status {
 #define FW_TERM_NONE 0
 #define FW_TERM_STEPS 1
 #define FW_TERM_SUCCESS 2
+#define FW_TERM_NUMERIC 3      /* the integration left the representable range (non-finite state or step size: scipy's RK45
+                                * loop would never return, rk.py:111-147 with a NaN h_abs) or needed more dopri5 attempts
+                                * than fw_sim_t.max_attempts allows; handled like a constraint failure (done, step_fail
+                                * reward); info["termination"] = "numeric" */
 #define FW_TERM_FAIL_BASE 16   /* FW_TERM_FAIL_BASE + fw_sv id of the variable whose constraint was violated */
 
 /* variable condition flags (PyFly Variable.apply_conditions) */
@@ -150,7 +154,8 @@ typedef struct {
   int32_t drag_model;             /* 0 induced (1-sigma)CL^2/(pi e AR) + flat plate, 1 polynomial */
   int32_t turbulence;             /* Dryden gusts on */
   int32_t wind_enabled;           /* steady wind may be non-zero */
-  int32_t _pad0;
+  int32_t max_attempts;           /* opt-in cap on dopri5 step attempts per env step (sim_config_kw "dopri5_max_attempts");
+                                   * 0 = none, the reference's behaviour (a hang guard of 20000 remains) */
   double wind_mag_min, wind_mag_max;
   double turb_noise_scale;        /* sqrt(pi/dt) */
   fw_filter_t filt[FW_N_FILT];

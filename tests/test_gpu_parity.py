@@ -21,10 +21,10 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 1e-9
 
 
-def make_vec(c, n=None, seed=SEED, **kw):
+def make_vec(c, n=None, seed=SEED, sim_config_kw=None, **kw):
     from fwgym_b200 import FixedWingVecEnv
     return FixedWingVecEnv(harness.config_path(c["config"]), n or c["n"], config_kw=c["config_kw"],
-                           sim_config_kw=c["sim_kw"], seed=seed, keep_terminal_obs=True, **kw)
+                           sim_config_kw=sim_config_kw or c["sim_kw"], seed=seed, keep_terminal_obs=True, **kw)
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -444,6 +444,51 @@ def test_injected_turbulence_noise(built_lib):
     o1 = env.reset(turbulence_noise=noise[0])
     assert pu.rel_err(o1, obs_o[0], 1e-3).max() <= TOL
     env.close()
+    vec.close()
+
+
+def test_numeric_failure_and_attempt_cap(built_lib):
+    """Hardening beyond the reference: (a) a simulator state that leaves the representable range (the dev configuration
+    has no body-rate constraints; under random actions its rates grow without bound) ends the episode with termination
+    "numeric" instead of spinning in dopri5 (scipy's loop never returns on a NaN step size) or feeding NaNs back;
+    (b) sim_config_kw dopri5_max_attempts caps the attempts of one env step the same way (off by default)."""
+    from fwgym_b200 import FixedWingVecEnv
+    from fwgym_b200.vec_env import term_name
+    cfg = harness.config_path("fixed_wing_config_dev.json")
+    vec = FixedWingVecEnv(cfg, 64, sim_config_kw={"turbulence": False}, seed=3)
+    vec.reset()
+    st, rows = vec.get_state(), vec.state_rows()
+    for k in ("omega_p", "omega_q", "omega_r"):
+        st[rows.index(k), :8] = 1e153   # where unconstrained rates end up after ~100 random-action steps: products overflow
+    vec.set_state(st)
+    acts = torch.zeros((64, 3), dtype=torch.float64, device=vec.device)
+    ended = torch.zeros(64, dtype=torch.bool, device=vec.device)
+    for _ in range(3):     # step sizes of 1e-17 s: the hang guard (or a non-finite value) ends these episodes
+        obs, rew, done, term = vec.step_tensors(acts)
+        assert all(term_name(int(t)) == "numeric" for t in term[:8][done[:8].bool()])
+        assert not done[8:].any() and torch.isfinite(obs[8:]).all()  # the others fly on
+        assert torch.isfinite(obs[:8][done[:8].bool()]).all()         # a finished env is reset on the spot
+        assert int(vec.last_attempts().max()) <= 20000
+        ended |= done.bool()
+    assert ended[:8].all()
+    for _ in range(5):
+        obs, rew, done, term = vec.step_tensors(acts)
+    assert torch.isfinite(obs).all() and torch.isfinite(vec.get_state()[:27]).all()
+    vec.close()
+    c = CASES["default"]
+    vec = make_vec(c, n=2048, seed=12, sim_config_kw={"turbulence": False, "dopri5_max_attempts": 4})
+    vec.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    n_numeric = 0
+    for t in range(10):
+        a = torch.rand((2048, 3), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+        _, _, done, term = vec.step_tensors(a)
+        k = vec.last_attempts()
+        assert int(k.max()) <= 4
+        numeric = term == 3
+        assert (k[numeric] == 4).all() and done[numeric.bool()].all()
+        n_numeric += int(numeric.sum())
+    assert n_numeric > 0
     vec.close()
 
 
