@@ -30,16 +30,21 @@ struct FwEnvCtx {
   __device__ __forceinline__ int32_t& I(int row) const { return i[(int64_t)row * stride + env]; }
 };
 
-template <bool INL>
+// NZ > 0: the first n_zpre (even, <= NZ) normals of this tick were drawn ahead of time (fw_env_kernel, before its chunk
+// wait) and sit in zpre - an array MEMBER, so that the unrolled observation loop of a fixed shape indexes registers
+template <bool INL, int NZ = 0>
 struct FwEnvRngT {
   FwRng g;
   uint32_t n_u, n_n;        // uniform / normal draws consumed in this tick
   double z_cached;
+  int n_zpre;
+  double zpre[NZ > 0 ? NZ : 1];
   __device__ __forceinline__ double uniform(double lo, double hi) { return fw_uniform<INL>(g, FW_RS_ENV_U, n_u++, lo, hi); }
   __device__ __forceinline__ double uniform01() { return fw_uniform01<INL>(g, FW_RS_ENV_U, n_u++); }
   __device__ __forceinline__ double normal(double mean, double std) {
     double z;
-    if (n_n & 1u) z = z_cached;
+    if ((int)n_n < n_zpre) z = zpre[n_n];
+    else if (n_n & 1u) z = z_cached;
     else { double z1; fw_normal2_t<INL>(g, FW_RS_ENV_N, n_n >> 1, z, z1); z_cached = z1; }
     ++n_n;
     return mean + std * z;
@@ -477,8 +482,11 @@ struct FwTurbInject {
   const double* __restrict__ noise;
   int64_t len, n;
 };
-__device__ __noinline__ void fw_turb_noise_injected(const fw_sim_t& P, const FwTurbInject& ti, int64_t env, int s,
-                                                    double (&u)[4]) {
+// (forceinline, arguments by value: a reference to a member of the kernel's parameter struct handed to an out-of-line
+// function makes nvcc copy the whole struct to local memory, after which every pointer loaded from it is GENERIC -
+// LD / ST / ATOM instead of LDG / STG / ATOMG throughout the kernel; measured +4 us on the env kernel)
+__device__ __forceinline__ void fw_turb_noise_injected(const fw_sim_t& P, const FwTurbInject ti, int64_t env, int s,
+                                                       double (&u)[4]) {
   const int64_t col = (int64_t)s % ti.len;
 #pragma unroll
   for (int j = 0; j < 4; ++j) u[j] = ti.noise[((int64_t)j * ti.len + col) * ti.n + env] * P.turb_noise_scale;
@@ -652,7 +660,7 @@ template <class SH>
 __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
                                           uint32_t k0, uint32_t k1, uint32_t genv, const double* __restrict__ init_state,
                                           const double* __restrict__ init_target, int64_t in_stride,
-                                          const FwTurbInject& ti, const FwObsWriter& out) {
+                                          const FwTurbInject ti, const FwObsWriter& out) {
   FW_SHAPE_REFS;
   const uint32_t tick = (uint32_t)c.I(I_TICK);
   c.I(I_TICK) = (int32_t)(tick + 1u);

@@ -453,7 +453,8 @@ __device__ __forceinline__ double fw_cond_s(uint32_t vflags, const fw_var_t& v, 
 template <class SH>
 __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx& c, const double* __restrict__ cd,
                                                const int32_t* __restrict__ ci, int64_t stride, uint32_t k0, uint32_t k1,
-                                               uint32_t genv, const FwTurbInject& ti, int& attempts_out, int& accepted_out) {
+                                               uint32_t genv, const FwTurbInject ti, const double* un_pre,
+                                               int& attempts_out, int& accepted_out) {
   const fw_sim_t& Ps = SH::sim(P);
 #define FW_CS(SV, X) fw_cond_s<false>(Ps.var[SV].flags, P.var[SV], SV, X, failv)
 #define FW_CSW(SV, X) fw_cond_s<true>(Ps.var[SV].flags, P.var[SV], SV, X, failv)
@@ -519,6 +520,7 @@ __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx
       if (Ps.turbulence) {   // gust column for the next sim step (cur_sim_step + 1)
         double un[4];
         if (ti.noise && ((uint32_t)c.I(I_FLAGS) & FWF_TURB_INJ)) fw_turb_noise_injected(P, ti, c.env, c.I(I_STEPS) + 1, un);
+        else if (un_pre) { un[0] = un_pre[0]; un[1] = un_pre[1]; un[2] = un_pre[2]; un[3] = un_pre[3]; }
         else fw_turb_noise<SH::fixed>(P, k0, k1, genv, (uint32_t)c.I(I_EPTICK), c.I(I_STEPS) + 1, un);
         fw_turb_advance<SH>(P, c, un);
       }
@@ -562,13 +564,35 @@ struct FwEnvArgs {
 
 // Env-side work of one env step for env `env` (fixed_wing.py:338-437 after the simulator call).  Episode-metric
 // contributions are returned in m[] / n_reset and summed per warp by the caller (one atomic per warp and metric).
+// Random draws of a step that depend on nothing the integration produces (keyed by counters the previous step left):
+// the gust noise of the next sim step and the observation-noise normals.  fw_env_kernel draws them BEFORE it waits for its
+// chunk's aircraft, in the shadow of the attempt kernel (Philox + Box-Muller are ~40 % of the env step's instructions).
+template <int NZ>
+struct FwEnvPre {
+  bool have_un;
+  int nz;                      // normals drawn: 0 or NZ
+  double un[4];                // scaled gust noise of the next sim step
+  double z[NZ > 0 ? NZ : 1];   // standard normals of the env stream of this tick
+};
+// observation-noise normals a fixed shape draws ahead (a 5 x 12 matrix observation would need 120 registers: none)
+template <class SH>
+__host__ __device__ constexpr int fw_env_nz() {
+  if constexpr (SH::fixed) {
+    const int n = SH::cenv.obs_noise ? ((SH::cenv.obs_len * SH::cenv.obs_nvar + 1) / 2) * 2 : 0;
+    return n <= 16 ? n : 0;
+  } else {
+    return 0;
+  }
+}
 template <class SH>
 __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvArgs& a,
-                                            int64_t env, double (&m)[FW_N_METRIC_SUMS], int& n_reset, int& attempts,
-                                            int& accepted, int& failed) {
+                                            int64_t env, const FwEnvPre<fw_env_nz<SH>()>& pre,
+                                            double (&m)[FW_N_METRIC_SUMS], int& n_reset, int& attempts, int& accepted,
+                                            int& failed) {
   FW_SHAPE_REFS;
   FwEnvCtx c{a.d, a.i, L.stride, env};
-  fw_commit_step<SH>(P, c, a.cd + env, a.ci + env, L.stride, a.k0, a.k1, a.env_offset + (uint32_t)env, a.ti, attempts, accepted);
+  fw_commit_step<SH>(P, c, a.cd + env, a.ci + env, L.stride, a.k0, a.k1, a.env_offset + (uint32_t)env, a.ti,
+                     pre.have_un ? pre.un : nullptr, attempts, accepted);
   failed = c.I(I_STATUS) != 0;
   uint32_t flags = (uint32_t)c.I(I_FLAGS);
   int steps = c.I(I_STEPS);
@@ -593,7 +617,12 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   const uint32_t tick = (uint32_t)c.I(I_TICK);
   c.I(I_TICK) = (int32_t)(tick + 1u);
   const uint32_t genv = a.env_offset + (uint32_t)env;
-  FwEnvRngT<SH::fixed> rng{FwRng{a.k0, a.k1, genv, tick}, 0u, 0u, 0.0};
+  constexpr int NZ = fw_env_nz<SH>();
+  FwEnvRngT<SH::fixed, NZ> rng{FwRng{a.k0, a.k1, genv, tick}, 0u, 0u, 0.0, pre.nz};
+  if constexpr (NZ > 0) {
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) rng.zpre[j] = pre.z[j];
+  }
 
   bool done = false;
   int term = FW_TERM_NONE;
@@ -707,14 +736,40 @@ __device__ __forceinline__ void fw_flush_metrics(const FwEnvArgs& a, double (&m)
 template <class SH>
 __global__ void __launch_bounds__(FW_ENV_BLOCK, FW_ENV_MIN_BLOCKS)
 fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim_t P, const __grid_constant__ FwLayout L,
-              const FwEnvArgs a) {
+              const __grid_constant__ FwEnvArgs a) {
   const int64_t env = (int64_t)blockIdx.x * FW_ENV_BLOCK + threadIdx.x;
   FW_TL_BEGIN(2);
+  // ---- before the wait: this step's random draws (FwEnvPre).  Everything read here was written by the env / reset
+  // kernels of EARLIER launches (tick counters), never by the dynamics kernels that may still be running.
+  constexpr int NZ = fw_env_nz<SH>();
+  FwEnvPre<NZ> pre;
+  pre.have_un = false;
+  pre.nz = 0;
+#ifndef FW_ENV_NO_PREDRAW   // (experiment build: draw in place, as before round 2)
+  if constexpr (SH::fixed) {
+    const fw_sim_t& Ps = SH::sim(P);
+    if (env < a.n) {
+      const uint32_t genv = a.env_offset + (uint32_t)env;
+      const int32_t* ip = a.i + env;
+      if (Ps.turbulence)
+        fw_turb_noise<true>(P, a.k0, a.k1, genv, (uint32_t)ip[(int64_t)I_EPTICK * L.stride], ip[(int64_t)I_STEPS * L.stride] + 1,
+                            pre.un);
+      if constexpr (NZ > 0) {
+        const FwRng g{a.k0, a.k1, genv, (uint32_t)ip[(int64_t)I_TICK * L.stride]};
+#pragma unroll
+        for (int j = 0; j < NZ / 2; ++j) fw_normal2_inl(g, FW_RS_ENV_N, (uint32_t)j, pre.z[2 * j], pre.z[2 * j + 1]);
+      }
+    }
+    // compile-time for a fixed shape: the draw-in-place paths (fw_commit_step, FwEnvRngT::normal) fold away
+    pre.have_un = Ps.turbulence != 0;
+    pre.nz = NZ;
+  }
+#endif
   // Wait until every aircraft of this block's chunk has been parked by the dynamics kernels (acquire side of the
   // release in fw_attempt_kernel).  One polling thread per block; the others sleep on the barrier.  The attempt kernel
   // never waits for anything, so this cannot deadlock; the watchdog turns a lost update into an error flag
   // (fw_counters reports it) instead of a hung GPU.
-  __shared__ int s_timed_out;
+  int timed_out = 0;   // (block-wide OR below: no shared variable, which would turn every access of the kernel generic)
   if (threadIdx.x == 0) {
     const int64_t first = (int64_t)blockIdx.x * FW_ENV_BLOCK;
     int need = (int)((a.n - first) < FW_ENV_BLOCK ? (a.n - first) : FW_ENV_BLOCK);
@@ -727,7 +782,7 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
       if (++spins > a.spin_limit) { ok = false; break; }
     }
     __threadfence();
-    s_timed_out = ok ? 0 : 1;
+    timed_out = ok ? 0 : 1;
     if (ok) {
       // consumed: zero it for the next step (nothing adds to a complete chunk); block 0 also zeroes the priority-list
       // length, which every attempt warp read before this kernel could start
@@ -742,8 +797,7 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
       __threadfence_system();
     }
   }
-  __syncthreads();
-  if (s_timed_out) {
+  if (__syncthreads_or(timed_out)) {
     if (env < a.n) {
       const float nanf_ = __int_as_float(0x7fc00000);
       if (a.obs_out) for (int j = 0; j < a.obs_dim; ++j) a.obs_out[env * (int64_t)a.obs_dim + j] = nanf_;
@@ -761,7 +815,7 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
 #pragma unroll
   for (int k = 0; k < FW_N_METRIC_SUMS; ++k) m[k] = 0.0;
   int n_reset = 0, attempts = 0, accepted = 0, failed = 0, nv = 0;
-  if (env < a.n) { fw_env_step<SH>(E, P, L, a, env, m, n_reset, attempts, accepted, failed); nv = 1; }
+  if (env < a.n) { fw_env_step<SH>(E, P, L, a, env, pre, m, n_reset, attempts, accepted, failed); nv = 1; }
   fw_flush_metrics(a, m, n_reset);
   // dopri5 counters (fw_counters): one atomic per warp
   const unsigned full = 0xffffffffu;

@@ -76,6 +76,9 @@ def cpu_arm(seconds, warm):
     return out
 
 
+GPU_VARIANTS = [("1", {}), ("1", {"dopri5_max_attempts": 64}), ("3'", {}), ("5'", {})]
+
+
 def gpu_arm(sizes, steps=40, warm=5, burn=200):
     import torch
     import __graft_entry__ as ge
@@ -88,10 +91,11 @@ def gpu_arm(sizes, steps=40, warm=5, burn=200):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     params = os.path.dirname(DEFAULT_ENV_CONFIG)
     out = {"dfma_peak_tflops": fl.value / 1e12, "rows": []}
-    for key, c in CONFIGS.items():
+    for key, extra in GPU_VARIANTS:
+        c = CONFIGS[key]
         for n in sizes:
             vec = FixedWingVecEnv(os.path.join(params, c["config"]), n, device=dev, config_kw=c["config_kw"],
-                                  sim_config_kw=c["sim_kw"], seed=7)
+                                  sim_config_kw=dict(c["sim_kw"], **extra), seed=7)
             vec.reset()
             g = torch.Generator(device=dev); g.manual_seed(1)
             acts = torch.rand((16, n, 3), generator=g, device=dev) * 2 - 1
@@ -99,11 +103,14 @@ def gpu_arm(sizes, steps=40, warm=5, burn=200):
                 vec.step_tensors(acts[i % 16])
             vec.reset_counters()
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            kmax = torch.zeros((), dtype=torch.int32, device=dev)
             for k in range(steps):
                 flush.zero_()
                 ev[k][0].record(); vec.step_tensors(acts[k % 16]); ev[k][1].record()
+                kmax = torch.maximum(kmax, vec.last_attempts().max())
             torch.cuda.synchronize(dev)
-            ms = sum(a.elapsed_time(b) for a, b in ev)
+            per = sorted(a.elapsed_time(b) for a, b in ev)
+            ms = sum(per)
             ctr = vec.counters()
             vec.set_profiling(True)
             for k in range(10):
@@ -111,16 +118,21 @@ def gpu_arm(sizes, steps=40, warm=5, burn=200):
             dyn_ms, env_ms, ps = vec.profile()
             c2 = vec.counters()
             flops = 1080.0 * (c2["env_steps"] - ctr["env_steps"]) + 3660.0 * (c2["attempts"] - ctr["attempts"])
-            row = {"config": key, "envs_per_gpu": n, "env_steps_per_s": n * steps / (ms * 1e-3), "us_per_step": 1e3 * ms / steps,
+            sums = vec.metric_sums()
+            row = {"config": key + (" + %s" % json.dumps(extra) if extra else ""), "envs_per_gpu": n,
+                   "us_per_step_p50": 1e3 * per[len(per) // 2], "us_per_step_max": 1e3 * per[-1],
+                   "max_attempts_of_one_env_step": int(kmax.item()),
+                   "episodes_ended": int(sums[0]), "constraint_failures": int(sums[4]), "env_steps_per_s": n * steps / (ms * 1e-3), "us_per_step": 1e3 * ms / steps,
                    "mean_attempts": ctr["attempts"] / max(1, ctr["env_steps"]),
                    "lane_efficiency": ctr["warp_steps"] / max(1.0, 32.0 * ctr["warp_max_attempts"]),
                    "dyn_kernels_us": 1e3 * dyn_ms / ps, "env_kernel_us": 1e3 * env_ms / ps,
                    "achieved_fp64_tflops": flops / (dyn_ms * 1e-3) / 1e12,
                    "frac_of_dfma_peak": flops / (dyn_ms * 1e-3) / fl.value, "kernels": vec.kernel_variant()}
             out["rows"].append(row)
-            print("GPU config %s, %6d envs: %.4g env-steps/s (%.1f us / step), k %.2f, FP64 %.2f TFLOP/s = %.3f of peak"
-                  % (key, n, row["env_steps_per_s"], row["us_per_step"], row["mean_attempts"],
-                     row["achieved_fp64_tflops"], row["frac_of_dfma_peak"]), flush=True)
+            print("GPU config %s, %6d envs: %.4g env-steps/s (%.1f us / step, p50 %.1f, max %.1f), k mean %.2f max %d, FP64 %.2f "
+                  "TFLOP/s = %.3f of peak" % (row["config"], n, row["env_steps_per_s"], row["us_per_step"], row["us_per_step_p50"],
+                                              row["us_per_step_max"], row["mean_attempts"], row["max_attempts_of_one_env_step"],
+                                              row["achieved_fp64_tflops"], row["frac_of_dfma_peak"]), flush=True)
             vec.close()
     return out
 
@@ -130,8 +142,13 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-seconds", type=float, default=30.0)
     ap.add_argument("--cpu-warmup", type=float, default=5.0)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "baseline_report.json"))
+    ap.add_argument("--reuse-cpu", default=None, help="take the CPU arm from an earlier report instead of timing it again")
     a = ap.parse_args()
-    rep = {"cpu": cpu_arm(a.cpu_seconds, a.cpu_warmup)}      # CPU first: no CUDA context exists in the forking parent
+    if a.reuse_cpu:
+        with open(a.reuse_cpu) as f:
+            rep = {"cpu": json.load(f)["cpu"]}
+    else:
+        rep = {"cpu": cpu_arm(a.cpu_seconds, a.cpu_warmup)}      # CPU first: no CUDA context exists in the forking parent
     rep["gpu_1x_b200"] = gpu_arm([4096, 16384, 65536])
     with open(a.out, "w") as f:
         json.dump(rep, f, indent=1)
