@@ -156,10 +156,13 @@ def evaluate_on_set(scenarios, config_path, controller="pid", config_kw=None, me
     rows = ep_rows.cpu().numpy()
     res = {m: {} for m in metrics}
     for i in range(n):
+        if not np.isfinite(rows[i][1]):
+            continue                       # still flying at max_steps: no episode row, length = max_steps below
         info = vec.episode_info(rows[i])
         for m in metrics:
             for st, val in info.get(m, {}).items():
                 res[m].setdefault(st, []).append(val)
+    lengths[alive] = min(t + 1, steps_cap)
     tr, ln = rew_trace.cpu().numpy(), lengths.cpu().numpy()
     res["rewards"] = [tr[:ln[i], i].copy() for i in range(n)]
     res["lengths"] = ln

@@ -179,7 +179,9 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
     norm = DeviceVecNormalize(venv, gamma=gamma)
     n, od = venv.num_envs, venv.obs_dim
     model = model or ActorCritic(od, 3).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-5)
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    graph_update = bool(cuda_graph) and not distributed       # (the gradient all-reduce stays outside a captured graph)
+    opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-5, capturable=graph_update)
     obs = norm.reset().clone()          # static: the rollout reads and overwrites it in place
     B = n_steps * n
     buf = dict(obs=torch.zeros((n_steps, n, od), device=dev), act=torch.zeros((n_steps, n, 3), device=dev),
@@ -216,6 +218,34 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
             compute_gae(buf["rew"], buf["val"], buf["done"], model.value(obs), gamma, lam, adv)
             torch.add(adv, buf["val"], out=ret)
 
+    flat = {k: v.reshape((B,) + v.shape[2:]) for k, v in buf.items()}
+    f_adv, f_ret = adv.reshape(B), ret.reshape(B)
+    mb = B // n_minibatches
+    mb_idx = torch.zeros(mb, dtype=torch.long, device=dev)      # static: the captured update reads its minibatch from here
+    loss_out = torch.zeros(2, device=dev)
+    upd_graph = None
+
+    def minibatch_update():
+        """One PPO2 gradient step on the minibatch mb_idx points at (clipped surrogate + clipped value loss + entropy)."""
+        idx = mb_idx
+        d = model.dist(flat["obs"][idx])
+        logp = d.log_prob(flat["act"][idx]).sum(-1)
+        a = f_adv[idx]
+        a = (a - a.mean()) / (a.std() + 1e-8)
+        ratio = (logp - flat["logp"][idx]).exp()
+        pg = torch.max(-a * ratio, -a * torch.clamp(ratio, 1 - clip_range, 1 + clip_range)).mean()
+        v = model.value(flat["obs"][idx])
+        vclip = flat["val"][idx] + torch.clamp(v - flat["val"][idx], -clip_range, clip_range)
+        vl = 0.5 * torch.max((v - f_ret[idx]) ** 2, (vclip - f_ret[idx]) ** 2).mean()
+        loss = pg - ent_coef * d.entropy().sum(-1).mean() + vf_coef * vl
+        opt.zero_grad(set_to_none=False)        # gradients keep their storage
+        loss.backward()
+        _allreduce_grads(model)
+        nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
+        opt.step()
+        loss_out[0].copy_(loss.detach())
+        loss_out[1].copy_(vl.detach())
+
     t_env = t_pol = t_upd = t_roll = 0.0
     iters = max(1, int(total_env_steps) // B)
     stats = {"iterations": iters, "batch": B, "history": [], "cuda_graph": bool(cuda_graph)}
@@ -244,28 +274,20 @@ def train(venv, total_env_steps, n_steps=128, n_minibatches=4, n_epochs=4, lr=2.
                     rollout()
             graph.replay()
         e[1].record()
-        flat = {k: v.reshape((B,) + v.shape[2:]) for k, v in buf.items()}
-        f_adv, f_ret = adv.reshape(B), ret.reshape(B)
-        mb = B // n_minibatches
         for ep in range(n_epochs):
             perm = torch.randperm(B, device=dev)
             for k in range(n_minibatches):
-                idx = perm[k * mb:(k + 1) * mb]
-                d = model.dist(flat["obs"][idx])
-                logp = d.log_prob(flat["act"][idx]).sum(-1)
-                a = f_adv[idx]
-                a = (a - a.mean()) / (a.std() + 1e-8)
-                ratio = (logp - flat["logp"][idx]).exp()
-                pg = torch.max(-a * ratio, -a * torch.clamp(ratio, 1 - clip_range, 1 + clip_range)).mean()
-                v = model.value(flat["obs"][idx])
-                vclip = flat["val"][idx] + torch.clamp(v - flat["val"][idx], -clip_range, clip_range)
-                vl = 0.5 * torch.max((v - f_ret[idx]) ** 2, (vclip - f_ret[idx]) ** 2).mean()
-                loss = pg - ent_coef * d.entropy().sum(-1).mean() + vf_coef * vl
-                opt.zero_grad(set_to_none=False)        # gradients keep their storage
-                loss.backward()
-                _allreduce_grads(model)
-                nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
-                opt.step()
+                mb_idx.copy_(perm[k * mb:(k + 1) * mb])
+                if not graph_update or it == 0:
+                    minibatch_update()                  # eager (also the warm-up of the captured version)
+                else:
+                    if upd_graph is None:               # one gradient step = one graph: ~100 small kernels per replay
+                        torch.cuda.synchronize(dev)
+                        upd_graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(upd_graph):
+                            minibatch_update()
+                    upd_graph.replay()
+        loss, vl = loss_out[0], loss_out[1]
         e[2].record()
         torch.cuda.synchronize(dev)
         roll_ms, upd_ms = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
