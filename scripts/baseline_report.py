@@ -76,7 +76,7 @@ def cpu_arm(seconds, warm):
     return out
 
 
-GPU_VARIANTS = [("1", {}), ("1", {"dopri5_max_attempts": 64}), ("3'", {}), ("5'", {})]
+GPU_VARIANTS = [("1", {}), ("1", {"dopri5_max_attempts": 64}), ("3'", {}), ("5'", {}), ("5'", {"dopri5_max_attempts": 64})]
 
 
 def gpu_arm(sizes, steps=40, warm=5, burn=200):
