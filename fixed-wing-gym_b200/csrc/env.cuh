@@ -675,7 +675,9 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   auto init_var = [&](int sv) -> double {
     double v;
     if (given(sv, v)) return fw_cond_wrap<double>(P.var[sv], sv, v, dummy);
-    return fw_uniform(g, FW_RS_INIT, (uint32_t)sv, P.var[sv].init_min, P.var[sv].init_max);
+    // (fixed shapes inline Philox: the ~15 independent draws of a reset interleave instead of running as serial calls -
+    // a reset is ONE lane of a warp working while 31 wait, and half of the env blocks of a step contain one)
+    return fw_uniform<SH::fixed>(g, FW_RS_INIT, (uint32_t)sv, P.var[sv].init_min, P.var[sv].init_max);
   };
   // ---- PyFly.reset ----
   const double roll = init_var(FW_SV_ROLL), pitch = init_var(FW_SV_PITCH), yaw = init_var(FW_SV_YAW);
@@ -696,11 +698,15 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
     const bool have = given(FW_N_SV + 0, wv[0]) & given(FW_N_SV + 1, wv[1]) & given(FW_N_SV + 2, wv[2]);
     if (have) { wind[0] = wv[0]; wind[1] = wv[1]; wind[2] = wv[2]; }
     else {
-      const double mag = fw_uniform(g, FW_RS_WIND, 0, P.wind_mag_min, P.wind_mag_max);
-      wind[0] = fw_uniform(g, FW_RS_WIND, 1, -mag, mag);
-      const double we_max = sqrt(mag * mag - wind[0] * wind[0]);
-      wind[1] = fw_uniform(g, FW_RS_WIND, 2, -we_max, we_max);
-      wind[2] = sqrt(mag * mag - wind[0] * wind[0] - wind[1] * wind[1]);
+      // counter-based draws: with a zero magnitude range all three are exactly 0 whatever the random words, so the
+      // Philox blocks can be skipped without moving any other draw
+      if (P.wind_mag_min != 0.0 || P.wind_mag_max != 0.0) {
+        const double mag = fw_uniform<SH::fixed>(g, FW_RS_WIND, 0, P.wind_mag_min, P.wind_mag_max);
+        wind[0] = fw_uniform<SH::fixed>(g, FW_RS_WIND, 1, -mag, mag);
+        const double we_max = sqrt(mag * mag - wind[0] * wind[0]);
+        wind[1] = fw_uniform<SH::fixed>(g, FW_RS_WIND, 2, -we_max, we_max);
+        wind[2] = sqrt(mag * mag - wind[0] * wind[0] - wind[1] * wind[1]);
+      }
     }
   }
   for (int j = 0; j < 3; ++j) c.D(D_WIND + j) = wind[j];
@@ -710,7 +716,7 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   if (Ps.turbulence) {
     double u0[4];
     if (ti.noise) fw_turb_noise_injected(P, ti, c.env, 0, u0);
-    else fw_turb_noise<false>(P, k0, k1, genv, tick, 0, u0);
+    else fw_turb_noise<SH::fixed>(P, k0, k1, genv, tick, 0, u0);
     for (int j = 0; j < 4; ++j) c.D(D_TU + j) = u0[j];
 #pragma unroll
     for (int f = 0; f < FW_N_FILT; ++f) {
@@ -724,16 +730,20 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
     for (int j = 0; j < 6; ++j) c.D(D_GUST + j) = 0.0;
   }
   // Va, alpha, beta from the Euler-angle rotation of the steady wind + gust
-  double wb[3];
-  fw_rot_euler(roll, pitch, yaw, wind, wb);
+  double wb[3] = {0.0, 0.0, 0.0};
+  if (wind[0] != 0.0 || wind[1] != 0.0 || wind[2] != 0.0) fw_rot_euler(roll, pitch, yaw, wind, wb);   // (R * 0 = 0)
   const double ur = vel[0] - (wb[0] + gl[0]), vr = vel[1] - (wb[1] + gl[1]), wr = vel[2] - (wb[2] + gl[2]);
-  const double Va = sqrt(ur * ur + vr * vr + wr * wr);
+  // branch-free fwmath routines as in the step path (fw_commit_step): asin(vr / Va) = atan2(vr, hypot(ur, wr))
+  const double hxz2 = ur * ur + wr * wr;
+  const double Va = fwm_sqrt(hxz2 + vr * vr);
   c.D(D_VA) = fw_cond<double>(P.var[FW_SV_VA], FW_SV_VA, Va, dummy);
-  c.D(D_ALPHA) = fw_cond<double>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, atan2(wr, ur), dummy);
-  c.D(D_BETA) = fw_cond<double>(P.var[FW_SV_BETA], FW_SV_BETA, asin(vr / Va), dummy);
+  c.D(D_ALPHA) = fw_cond<double>(P.var[FW_SV_ALPHA], FW_SV_ALPHA, fwm_atan2(wr, ur), dummy);
+  c.D(D_BETA) = fw_cond<double>(P.var[FW_SV_BETA], FW_SV_BETA, fwm_atan2(vr, fwm_sqrt(hxz2)), dummy);
   {
     double sphi, cphi, sth, cth, spsi, cpsi;
-    sincos(roll / 2, &sphi, &cphi); sincos(pitch / 2, &sth, &cth); sincos(yaw / 2, &spsi, &cpsi);
+    // sin / cos of the half angles through sincospi (straight-line; the libdevice sincos slow path is ~3x the code)
+    const double inv2pi = 0.15915494309189535;   // 1 / (2 pi)
+    fwm_sincospi(roll * inv2pi, &sphi, &cphi); fwm_sincospi(pitch * inv2pi, &sth, &cth); fwm_sincospi(yaw * inv2pi, &spsi, &cpsi);
     c.D(D_Q + 0) = cpsi * cth * cphi + spsi * sth * sphi;
     c.D(D_Q + 1) = cpsi * cth * sphi - spsi * sth * cphi;
     c.D(D_Q + 2) = cpsi * sth * cphi + spsi * cth * sphi;
@@ -743,7 +753,7 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   uint32_t flags = (uint32_t)c.I(I_FLAGS);
   const int old_hist_len = c.I(I_HISTLEN);
   c.I(I_STEPS) = 0;
-  FwEnvRngT<false> rng{g, 0u, 0u, 0.0};
+  FwEnvRngT<SH::fixed> rng{g, 0u, 0u, 0.0};
   // sample_simulator_parameters (fixed_wing.py:523-570) runs between simulator.reset and sample_target (:308-310) and
   // draws from the env's generator in table order.  Fixed shapes have no table (n_rand == 0).
   if (Es.n_rand > 0) {

@@ -11,6 +11,10 @@ n = 65536
 vec = FixedWingVecEnv(DEFAULT_ENV_CONFIG, n, config_kw=bench.CONFIG_KW, sim_config_kw=bench.SIM_KW, seed=1)
 vec.reset()
 lib = vec._lib
+BURN = int(os.environ.get("FWGYM_TIMELINE_BURN", "0"))      # 200: the stationary episode mix of bench.py (auto-resets every step)
+_b = torch.rand((16, n, 3), device="cuda") * 2 - 1
+for i in range(BURN):
+    vec.step_tensors(_b[i % 16])
 acts = torch.rand((40, n, 3), device="cuda") * 2 - 1
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 buf = (ctypes.c_ulonglong * 8)()
@@ -31,6 +35,6 @@ for t in range(40):
         rows.append([(b[1] - t0), (b[2] - t0), (b[3] - t0), (b[4] - t0), (b[6] - t0), (b[5] - t0), b[7] / ((n + 127) // 128),
                      e0.elapsed_time(e1) * 1e6])
 r = np.array(rows).mean(0) / 1e3
-print("overlap=%s  us from the first init block: init end %.1f | attempt start %.1f end %.1f | env first block resident %.1f, "
+print("burn_in=%d overlap=%s  us from the first init block: init end %.1f | attempt start %.1f end %.1f | env first block resident %.1f, "
       "first past its wait %.1f, last end %.1f | mean env block run time %.1f | events around fw_step %.1f"
-      % (os.environ.get("FWGYM_OVERLAP", "1"), r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]))
+      % (BURN, os.environ.get("FWGYM_OVERLAP", "1"), r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]))
