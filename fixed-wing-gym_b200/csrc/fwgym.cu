@@ -277,7 +277,11 @@ fw_init_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDy
 
 // fp32 aircraft need half the registers and half the K-stage shared memory: twice the resident warps
 template <typename T, class Spec>
+#ifdef FW_DYN_MAXNREG   // experiment build: a register cap instead of launch bounds (e.g. 224 = 9 warps per SM)
+__global__ void __maxnreg__(sizeof(T) == 4 ? 128 : FW_DYN_MAXNREG)
+#else
 __global__ void __launch_bounds__(FW_DYN_BLOCK, sizeof(T) == 4 ? FW_DYN_MIN_BLOCKS_F32 : FW_DYN_MIN_BLOCKS)
+#endif
 fw_attempt_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDynArgs a) {
   const fw_sim_t& P = fw_sim_of(Px);
   FW_TL_BEGIN(1);
