@@ -218,9 +218,10 @@ __device__ __forceinline__ void fw_ring_put(const FwEnvCtx& c, int row0, int dep
 struct FwObsWriter {
   float* o32;
   double* o64;
-  int64_t base;
+  int64_t base;     // first element of this env's row in o64 (and in o32 unless base32 >= 0)
+  int64_t base32;   // >= 0: o32 is a staging tile (fw_env_kernel, zero-copy host results) and this is the row's offset in it
   __device__ __forceinline__ void operator()(int idx, double v) const {
-    if (o32) o32[base + idx] = (float)v;
+    if (o32) o32[(base32 >= 0 ? base32 : base) + idx] = (float)v;
     if (o64) o64[base + idx] = v;
   }
 };

@@ -78,6 +78,7 @@ struct fw_handle_s {
     float* d_act; float* d_obs; float* d_rew; uint8_t* d_done; int32_t* d_term;   // d_obs .. d_done: ONE block, one D2H copy
     float* h_obs; float* h_rew; uint8_t* h_done; int32_t* h_term;                   // likewise one pinned block
     size_t out_bytes;
+    int zero_copy;   // results are written by the env kernel straight into mapped pinned host memory: no D2H copy
     cudaEvent_t e_in, e_step, e_out;
     int busy;
   };
@@ -537,6 +538,11 @@ __device__ __forceinline__ void fw_commit_step(const fw_sim_t& P, const FwEnvCtx
 }
 
 // ---------------------------------------------------------------------------------------------------- env kernel
+// Observation tile of an env block (dynamic shared memory, only when FwEnvArgs.stage_obs): zero-copy host results write
+// observations straight into MAPPED PINNED host memory, and 14 floats per thread at a 56-byte stride would cross PCIe as
+// 4-byte writes; staged, a block's rows (contiguous in the output) leave as 16-byte stores, 512 B per warp instruction.
+extern __shared__ __align__(16) float fw_env_tile[];
+
 struct FwEnvArgs {
   double* d;
   int32_t* i;
@@ -564,6 +570,7 @@ struct FwEnvArgs {
   int* err_flag;       // host-visible sticky error word (watchdog)
   uint32_t spin_limit;
   int32_t starve;      // test hook (fw_debug_watchdog)
+  int32_t stage_obs;   // float32 observations through a shared-memory tile (dynamic smem: FW_ENV_BLOCK * obs_dim floats)
 };
 
 // Env-side work of one env step for env `env` (fixed_wing.py:338-437 after the simulator call).  Episode-metric
@@ -633,7 +640,9 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   if (E.steps_max > 0 && steps >= E.steps_max) { done = true; term = FW_TERM_STEPS; }
   double reward;
   int hist_len = c.I(I_HISTLEN);
-  FwObsWriter ow{a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim};
+  // a.stage_obs: float32 observations go to the block's shared-memory tile and leave in one coalesced burst (fw_env_kernel)
+  FwObsWriter ow{a.stage_obs ? fw_env_tile : a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim,
+                 a.stage_obs ? (int64_t)threadIdx.x * a.obs_dim : (int64_t)-1};
   if (status == 0) {
     const uint32_t gb = fw_goal_status<SH>(E, c);
     bool achieved_on_step = false, resample = false;
@@ -687,7 +696,8 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
   const bool do_reset = done && a.auto_reset;
   if (!do_reset || a.term_obs_out) {
     // an env that is about to be reset writes its terminal observation (float32 only) to term_obs_out instead
-    const FwObsWriter w{do_reset ? a.term_obs_out : a.obs_out, do_reset ? nullptr : a.obs64_out, ow.base};
+    const FwObsWriter w{do_reset ? a.term_obs_out : ow.o32, do_reset ? nullptr : a.obs64_out, ow.base,
+                        do_reset ? (int64_t)-1 : ow.base32};
     fw_observation<SH>(E, P, L, c, rng, flags, steps, hist_len, false, w);
   }
   c.I(I_FLAGS) = (int32_t)flags;
@@ -820,6 +830,17 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
   for (int k = 0; k < FW_N_METRIC_SUMS; ++k) m[k] = 0.0;
   int n_reset = 0, attempts = 0, accepted = 0, failed = 0, nv = 0;
   if (env < a.n) { fw_env_step<SH>(E, P, L, a, env, pre, m, n_reset, attempts, accepted, failed); nv = 1; }
+  if (a.stage_obs) {
+    __syncthreads();
+    const int64_t first = (int64_t)blockIdx.x * FW_ENV_BLOCK;
+    const int nval = (int)((a.n - first) < FW_ENV_BLOCK ? (a.n - first) : FW_ENV_BLOCK);
+    const int nfl = nval * a.obs_dim;                 // this block's rows: contiguous floats of obs_out, 512-byte aligned
+    float* dst = a.obs_out + first * a.obs_dim;
+    const int n4 = nfl >> 2;
+    for (int i = threadIdx.x; i < n4; i += FW_ENV_BLOCK)
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(fw_env_tile)[i];
+    for (int i = (n4 << 2) + threadIdx.x; i < nfl; i += FW_ENV_BLOCK) dst[i] = fw_env_tile[i];
+  }
   fw_flush_metrics(a, m, n_reset);
   // dopri5 counters (fw_counters): one atomic per warp
   const unsigned full = 0xffffffffu;
@@ -867,7 +888,7 @@ fw_reset_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_s
   if (env >= a.n) return;
   if (a.mask && !a.mask[env]) return;
   FwEnvCtx c{a.d, a.i, L.stride, env};
-  FwObsWriter ow{a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim};
+  FwObsWriter ow{a.obs_out, a.obs64_out, env * (int64_t)a.obs_dim, -1};
   atomicAdd(a.ctr + CTR_RESETS, 1ull);
   fw_reset_env<SH>(E, P, L, c, a.k0, a.k1, a.env_offset + (uint32_t)env, a.init_state, a.init_target, a.n, a.ti, ow);
 }
@@ -881,7 +902,7 @@ static cudaError_t launch_env_t(int grid, cudaStream_t s, int overlap, const fw_
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)grid);
   lc.blockDim = dim3(FW_ENV_BLOCK);
-  lc.dynamicSmemBytes = 0;
+  lc.dynamicSmemBytes = a.stage_obs ? (size_t)FW_ENV_BLOCK * a.obs_dim * sizeof(float) : 0;
   lc.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1349,9 +1370,22 @@ int fw_reset(fw_handle h, const uint8_t* mask, const double* init_state, const d
   return FW_OK;
 }
 
+static int step_impl(fw_handle h, const void* actions, int actions_f64, float* obs_out, float* rew_out, uint8_t* done_out,
+                     int32_t* term_out, double* obs64_out, double* rew64_out, float* term_obs_out, int auto_reset,
+                     void* stream, int stage_obs);
+
 int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, float* rew_out, uint8_t* done_out,
             int32_t* term_out, double* obs64_out, double* rew64_out, float* term_obs_out, int auto_reset,
             void* stream) {
+  return step_impl(h, actions, actions_f64, obs_out, rew_out, done_out, term_out, obs64_out, rew64_out, term_obs_out,
+                   auto_reset, stream, 0);
+}
+
+// stage_obs: obs_out is mapped pinned HOST memory (fw_host_open zero-copy mode): observations leave the env kernel as
+// coalesced bursts through a shared-memory tile
+static int step_impl(fw_handle h, const void* actions, int actions_f64, float* obs_out, float* rew_out, uint8_t* done_out,
+                     int32_t* term_out, double* obs64_out, double* rew64_out, float* term_obs_out, int auto_reset,
+                     void* stream, int stage_obs) {
   if (!h || !actions || !rew_out || !done_out || !term_out) return fail(FW_ERR_ARG, "fw_step: null argument");
   if (!obs_out && !obs64_out) return fail(FW_ERR_ARG, "fw_step: no observation buffer");
   CK_POISON(h);
@@ -1371,7 +1405,8 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
   FwEnvArgs ea{h->d, h->i, h->n, actions, actions_f64, k0, k1, (uint32_t)h->offset, obs_out, rew_out, done_out,
                term_out, obs64_out, rew64_out, term_obs_out, auto_reset, fw_obs_dim(h), h->ctr, h->msum, h->carry_d,
                h->carry_i, h->ep_out, fw_episode_dim(h), h->queue, FwTurbInject{h->turb_noise, h->turb_len, h->n},
-               h->err_flag_dev, h->spin_limit, h->starve_next};
+               h->err_flag_dev, h->spin_limit, h->starve_next,
+               (stage_obs && obs_out && (size_t)FW_ENV_BLOCK * fw_obs_dim(h) * sizeof(float) <= 48 * 1024) ? 1 : 0};
   h->starve_next = 0;
   const int egrid = (int)((h->n + FW_ENV_BLOCK - 1) / FW_ENV_BLOCK);
   // with per-kernel profiling on, an event sits between the two kernels, so they are serialised anyway
@@ -1384,7 +1419,8 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
 // ---- host-buffer stepping ---------------------------------------------------------------------------------------
 static void host_free(fw_handle h) {
   for (auto& sl : h->hs) {
-    cudaFree(sl.d_act); cudaFree(sl.d_obs);
+    cudaFree(sl.d_act);
+    if (!sl.zero_copy) cudaFree(sl.d_obs);
     cudaFreeHost(sl.h_obs);
     if (sl.e_in) cudaEventDestroy(sl.e_in);
     if (sl.e_step) cudaEventDestroy(sl.e_step);
@@ -1394,7 +1430,9 @@ static void host_free(fw_handle h) {
   h->hs.clear();
 }
 
-int fw_host_open(fw_handle h, int depth) {
+int fw_host_open(fw_handle h, int depth) { return fw_host_open_ex(h, depth, 0); }
+
+int fw_host_open_ex(fw_handle h, int depth, int zero_copy) {
   if (!h || depth < 1 || depth > 8) return fail(FW_ERR_ARG, "fw_host_open: bad argument");
   CK(cudaSetDevice(h->device));
   host_free(h);
@@ -1408,9 +1446,14 @@ int fw_host_open(fw_handle h, int depth) {
     fw_handle_s::HostSlot& r = h->hs.back();
     // results of a step in one block [obs | reward | termination code | done]: one device -> host copy per step
     r.out_bytes = n * (od * sizeof(float) + sizeof(float) + sizeof(int32_t) + 1);
-    if (cudaMalloc(&r.d_act, n * FW_N_ACT * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&r.d_obs, r.out_bytes) != cudaSuccess ||
-        cudaMallocHost(&r.h_obs, r.out_bytes) != cudaSuccess ||
+    r.zero_copy = zero_copy ? 1 : 0;
+    bool ok = cudaMalloc(&r.d_act, n * FW_N_ACT * sizeof(float)) == cudaSuccess;
+    if (ok && zero_copy)    // the device alias of the pinned block is what the env kernel writes
+      ok = cudaHostAlloc(&r.h_obs, r.out_bytes, cudaHostAllocMapped) == cudaSuccess &&
+           cudaHostGetDevicePointer(&r.d_obs, r.h_obs, 0) == cudaSuccess;
+    else if (ok)
+      ok = cudaMalloc(&r.d_obs, r.out_bytes) == cudaSuccess && cudaMallocHost(&r.h_obs, r.out_bytes) == cudaSuccess;
+    if (!ok ||
         cudaEventCreateWithFlags(&r.e_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&r.e_step, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&r.e_out, cudaEventDisableTiming | (getenv("FWGYM_HOST_BLOCKING") ? cudaEventBlockingSync : 0)) != cudaSuccess) {
@@ -1446,12 +1489,17 @@ int fw_host_submit(fw_handle h, const float* actions_host, void* stream, int* sl
   CK(cudaMemcpyAsync(sl.d_act, actions_host, n * FW_N_ACT * sizeof(float), cudaMemcpyHostToDevice, h->hs_in));
   CK(cudaEventRecord(sl.e_in, h->hs_in));
   CK(cudaStreamWaitEvent(s, sl.e_in, 0));
-  int rc = fw_step(h, sl.d_act, 0, sl.d_obs, sl.d_rew, sl.d_done, sl.d_term, nullptr, nullptr, nullptr, 1, stream);
+  int rc = step_impl(h, sl.d_act, 0, sl.d_obs, sl.d_rew, sl.d_done, sl.d_term, nullptr, nullptr, nullptr, 1, stream,
+                     sl.zero_copy);
   if (rc) return rc;
-  CK(cudaEventRecord(sl.e_step, s));
-  CK(cudaStreamWaitEvent(h->hs_out, sl.e_step, 0));
-  CK(cudaMemcpyAsync(sl.h_obs, sl.d_obs, sl.out_bytes, cudaMemcpyDeviceToHost, h->hs_out));
-  CK(cudaEventRecord(sl.e_out, h->hs_out));
+  if (sl.zero_copy) {
+    CK(cudaEventRecord(sl.e_out, s));       // the results are in host memory when the env kernel has completed
+  } else {
+    CK(cudaEventRecord(sl.e_step, s));
+    CK(cudaStreamWaitEvent(h->hs_out, sl.e_step, 0));
+    CK(cudaMemcpyAsync(sl.h_obs, sl.d_obs, sl.out_bytes, cudaMemcpyDeviceToHost, h->hs_out));
+    CK(cudaEventRecord(sl.e_out, h->hs_out));
+  }
   sl.busy = 1;
   h->hs_next += 1;
   *slot_out = k;

@@ -466,10 +466,12 @@ class HostStepper:
     env).  submit() never blocks on the GPU; wait() blocks until that step's results are on the host.  With depth=1
     this is a plain synchronous host step."""
 
-    def __init__(self, vec, depth=2):
-        self.vec, self.depth = vec, int(depth)
+    def __init__(self, vec, depth=2, zero_copy=False):
+        """zero_copy: the env kernel writes the results straight into mapped pinned host memory (no device -> host copy
+        after the step; include/fwgym.h fw_host_open_ex)."""
+        self.vec, self.depth, self.zero_copy = vec, int(depth), bool(zero_copy)
         n, od = vec.num_envs, vec.obs_dim
-        _capi.check(vec._lib.fw_host_open(vec._h, self.depth))
+        _capi.check(vec._lib.fw_host_open_ex(vec._h, self.depth, 1 if zero_copy else 0))
         self._views = {}
         self.h2d_bytes = n * 3 * 4
         self.d2h_bytes = n * (od * 4 + 4 + 1 + 4)

@@ -283,6 +283,11 @@ int fw_step(fw_handle h, const void* actions, int actions_f64, float* obs_out, f
  * pageable memory is staged by the driver before the call returns.  Results: obs float [N, obs_dim], reward float
  * [N], done uint8 [N], term int32 [N] (FW_TERM_*), auto-reset semantics as fw_step(auto_reset = 1). */
 int fw_host_open(fw_handle h, int depth);
+/* zero_copy != 0: the result buffers are MAPPED pinned host memory and the env kernel writes observations (as coalesced
+ * bursts through a shared-memory tile), rewards, dones and termination codes straight into them while the dynamics
+ * kernels of the step are still finishing other chunks: no device -> host copy follows the step, fw_host_wait returns
+ * when the env kernel has completed.  Results are identical. */
+int fw_host_open_ex(fw_handle h, int depth, int zero_copy);
 int fw_host_close(fw_handle h);
 int fw_host_submit(fw_handle h, const float* actions_host, void* stream, int* slot_out);
 int fw_host_wait(fw_handle h, int slot, const float** obs, const float** rew, const uint8_t** done,

@@ -220,11 +220,15 @@ def test_overlapped_env_kernel_is_bitwise_identical(built_lib, monkeypatch):
     assert np.array_equal(states[0], states[1], equal_nan=True)
 
 
-def test_host_buffer_pipeline_matches_device_step(built_lib):
+@pytest.mark.parametrize("zero_copy", [False, True])
+def test_host_buffer_pipeline_matches_device_step(built_lib, zero_copy):
     """fw_host_submit / fw_host_wait (HostStepper): host actions in, host results out, two submissions in flight -
-    the same numbers as stepping on device tensors, ragged env count, pageable and pinned action buffers."""
+    the same numbers as stepping on device tensors, ragged env count, pageable and pinned action buffers; with a
+    device -> host copy per step and with the env kernel writing straight into mapped pinned memory (zero_copy: the
+    observations leave through a shared-memory tile), incl. envs that finish and are reset in the step."""
     from fwgym_b200 import HostStepper
-    c = CASES["turb_noise"]
+    c = dict(CASES["turb_noise"])
+    c["config_kw"] = dict(c["config_kw"], steps_max=6)
     n, steps = 1000, 9
     acts = (torch.rand((steps, n, 3)) * 2 - 1)
     ref = make_vec(c, n=n, seed=17)
@@ -236,7 +240,7 @@ def test_host_buffer_pipeline_matches_device_step(built_lib):
     ref.close()
     vec = make_vec(c, n=n, seed=17)
     vec.reset()
-    hs = HostStepper(vec, depth=2)
+    hs = HostStepper(vec, depth=2, zero_copy=zero_copy)
     pinned = acts.pin_memory()
     pending, got = [], []
     for i in range(steps):
