@@ -286,6 +286,37 @@ def run_gpu_arm(a):
     ms32 = sum(e0.elapsed_time(e1) for e0, e1 in ev32)
     vec32.close()
 
+    # ---- second workload, stated separately (the headline workload flies random actions into constraint
+    # failures, so steps_max / success / target-resample paths never run in its timed region): the reference's PID
+    # controller (evaluate_controller.py:141-151; fw_pid_step on the device) closes the loop on every env, same
+    # turbulence + noise, same envs per GPU, same burn-in / flush / events.  Episodes here end on steps_max or success.
+    from fwgym_b200.evaluate import DevicePID
+    ckw_pid = dict(CONFIG_KW or {})
+    ckw_pid["action"] = dict(ckw_pid.get("action", {}), scale_space=False)
+    vecp = FixedWingVecEnv(DEFAULT_ENV_CONFIG, n, device=dev, config_kw=ckw_pid, sim_config_kw=SIM_KW,
+                           seed=20261017, env_offset=rank * n)
+    pid = DevicePID(vecp)
+    vecp.reset()
+    pid_done = None
+    for i in range(a.burn_in + a.warmup):
+        _, _, pid_done, _ = vecp.step_tensors(pid(pid_done))
+    vecp.reset_counters()
+    msum_p0 = vecp.metric_sums()
+    evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kp_max = torch.zeros((), dtype=torch.int32, device=dev)
+    barrier()
+    for k in range(a.steps):
+        flush_l2()
+        evp[k][0].record()
+        _, _, pid_done, _ = vecp.step_tensors(pid(pid_done))   # controller launch + env step inside the timed interval
+        evp[k][1].record()
+        kp_max = torch.maximum(kp_max, vecp.last_attempts().max())
+    barrier()
+    msp = sum(e0.elapsed_time(e1) for e0, e1 in evp)
+    ctr_p = vecp.counters()
+    msum_p = vecp.metric_sums() - msum_p0
+    vecp.close()
+
     # ---- end-to-end through the public API with HOST buffers (fwgym_b200.HostStepper over the C-ABI fw_host_submit /
     # fw_host_wait): every step moves its actions pinned-host -> device and its observations / rewards / dones /
     # termination codes device -> pinned-host.  Three call patterns, all from a fresh reset + the same burn-in:
@@ -343,26 +374,27 @@ def run_gpu_arm(a):
     vec.close()
 
     # (a) two half-batch handles (global env ids [rank*n, rank*n + n/2) and [rank*n + n/2, (rank+1)*n)), one stream each
-    nh = n // 2
+    parts = int(os.environ.get("FWGYM_E2E_PARTS", "2"))      # sub-batch handles per rank (2 measured best)
+    bounds = [n * j // parts for j in range(parts + 1)]
     halves, steppers, streams = [], [], []
-    for j in range(2):
-        v = FixedWingVecEnv(DEFAULT_ENV_CONFIG, nh if j == 0 else n - nh, device=dev, config_kw=CONFIG_KW,
-                            sim_config_kw=SIM_KW, seed=20261017, env_offset=rank * n + j * nh)
+    for j in range(parts):
+        v = FixedWingVecEnv(DEFAULT_ENV_CONFIG, bounds[j + 1] - bounds[j], device=dev, config_kw=CONFIG_KW,
+                            sim_config_kw=SIM_KW, seed=20261017, env_offset=rank * n + bounds[j])
         st = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(st):
             v.reset()
             for i in range(a.burn_in):
-                v.step_tensors(burn_actions[i % 16][j * nh:j * nh + v.num_envs])
+                v.step_tensors(burn_actions[i % 16][bounds[j]:bounds[j + 1]])
         halves.append(v); streams.append(st); steppers.append(HostStepper(v, depth=1, zero_copy=zc))
     torch.cuda.synchronize(dev)
-    half_actions = [host_actions[:, :nh], host_actions[:, nh:]]
-    half_actions = [torch.empty_like(h).copy_(h).pin_memory() for h in half_actions]   # contiguous per half
+    half_actions = [host_actions[:, bounds[j]:bounds[j + 1]] for j in range(parts)]
+    half_actions = [torch.empty_like(h).copy_(h).pin_memory() for h in half_actions]   # contiguous per part
 
     def e2e_pingpong(first, count):
         nonlocal checksum
-        slots = [None, None]
+        slots = [None] * parts
         for i in range(count + 1):
-            for j in range(2):
+            for j in range(parts):
                 tb = time.perf_counter()
                 if slots[j] is not None:
                     obs, rew, done = steppers[j].wait(slots[j])      # obs_t of this half is on the host ...
@@ -390,13 +422,15 @@ def run_gpu_arm(a):
     if world > 1:
         place_all = [None] * world
         dist.all_gather_object(place_all, placement)
-    tt = torch.tensor([ms, e2e_s * 1e3, dyn_ms, env_ms, wall * 1e3, open_s * 1e3, d1_s * 1e3, step_ms[-1], ms32],
+    tt = torch.tensor([ms, e2e_s * 1e3, dyn_ms, env_ms, wall * 1e3, open_s * 1e3, d1_s * 1e3, step_ms[-1], ms32, msp],
                       dtype=torch.float64, device=dev)
     cnt = torch.tensor([ctr["env_steps"], ctr["attempts"], ctr["warp_max_attempts"], ctr["warp_steps"],
                         ctr["failures"], ctr["resets"], prof_env_steps, prof_attempts,
                         ctr_prof["watchdog"] + half_watchdog],
                        dtype=torch.float64, device=dev)
     msum = torch.tensor(msum_local, dtype=torch.float64, device=dev)
+    pidc = torch.tensor([ctr_p["env_steps"], ctr_p["attempts"]] + [float(x) for x in msum_p], dtype=torch.float64, device=dev)
+    kp_max_t = kp_max.to(torch.float64).reshape(1)
     e2e_each = [e2e_local * 1e6 / e2e_steps]
     if world > 1:
         g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
@@ -405,7 +439,9 @@ def run_gpu_arm(a):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)     # time = max over ranks
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         dist.all_reduce(msum, op=dist.ReduceOp.SUM)   # the only data-path collective: episode metric sums
-    ms, e2e_ms, dyn_ms, env_ms, wall_ms, open_ms, d1_ms, step_max_ms, ms32 = tt.tolist()
+        dist.all_reduce(pidc, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kp_max_t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, dyn_ms, env_ms, wall_ms, open_ms, d1_ms, step_max_ms, ms32, msp = tt.tolist()
     env_steps, attempts, wmax, wsteps, failures, resets, p_env_steps, p_attempts, watchdog = cnt.tolist()
     if rank == 0:
         total_env_steps = float(n) * a.steps * world
@@ -466,6 +502,18 @@ def run_gpu_arm(a):
                           "note": "precision='fp32' dynamics kernels on the same workload, same steps / flush / events; "
                                   "stated separately: fp32 adaptive stepping is not held to the 1e-9 parity bar (integer "
                                   "state still is, tests/test_gpu_parity.py::test_fp32_mode_feature_config_integer_state)"},
+            "controlled_flight": {
+                "value": total_env_steps / (msp * 1e-3), "unit": "env-steps/s", "dtype": "f64", "ms_per_step": msp / a.steps,
+                "controller": "the reference's PID controller on the device (fw_pid_step), one launch per step inside "
+                              "the timed interval; action.scale_space = False; otherwise the headline workload",
+                "mean_attempts_per_env_step": pidc[1].item() / max(1.0, pidc[0].item()),
+                "max_attempts_per_env_step": int(kp_max_t.item()),
+                "episodes": {"finished": pidc[2].item(), "successes": pidc[3].item(), "failures": pidc[6].item(),
+                             "ended_on_steps_max": pidc[7].item(), "ended_on_success": pidc[8].item(),
+                             "mean_length": pidc[5].item() / max(1.0, pidc[2].item())},
+                "note": "stated separately: same envs / turbulence / noise / burn-in / L2 flush / events as `value`, but "
+                        "the aircraft are FLOWN (no constraint failures; episodes end on steps_max or success, targets are "
+                        "resampled), so dopri5 needs fewer attempts and has no stragglers"},
             "gpu_launches": int(launches_per_step * a.steps),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fl.value / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / (fl.value / 1e12), "traffic": traffic, "traffic_from": traffic_from,

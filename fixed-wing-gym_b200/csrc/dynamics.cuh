@@ -253,8 +253,14 @@ __device__ __forceinline__ void fw_rhs(const fw_sim_t& P, const PAR& PP, const F
 #pragma unroll
   for (int i = 0; i < 3; ++i)
     if (!RAW && ((Spec::clip >> (FW_R_AD0 + i)) & 1u)) {
+      // two selects (compares keep NaN), never a branch: nvcc turned the nested conditional into a BSSY / BRA / BSYNC
+      // region per actuator and stage (~40 issue cycles each for a lone warp); identical values for m >= 0
       const T m = P.act_has_dot_max[i] ? fw_rd<T>(P, P.act_dot_max[i]) : (T)CUDART_INF;
-      ad[i] = ad[i] < -m ? -m : (ad[i] > m ? m : ad[i]);
+      const T nm = -m;
+      T x = ad[i];
+      x = x < nm ? nm : x;
+      x = x > m ? m : x;
+      ad[i] = x;
     }
   const T ail = fw_cond_r<T, Spec, FW_R_AIL>(P, P.var[FW_SV_AILERON], (-er + el) * (T)0.5, failmask);
   const T elev = fw_cond_r<T, Spec, FW_R_ELEV>(P, P.var[FW_SV_ELEVATOR], (er + el) * (T)0.5, failmask);
@@ -411,12 +417,39 @@ template <typename T> __device__ __forceinline__ T fw_dpE(int s) {
 #define FW_N_KC 16
 __device__ __forceinline__ constexpr int fw_kc_to_ode(int kc) { return kc < 7 ? kc : kc + 3; }
 
-// K-stage storage: shared memory, [slot][component][thread] so a warp's access to one (slot, component) is 32
-// consecutive words -> conflict-free.
+// K-stage storage: shared memory, one lane's values of a (slot, component pair) 16 bytes apart from the next lane's ->
+// conflict-free.
 template <typename T, int BLOCK> struct FwKStore {
   T* base;
+#ifndef FW_K_SINGLE
+  // components in pairs, [slot][pair][thread][2]: the unrolled stage code reads / writes two components per 16-byte
+  // access (LDS.128 / STS.128, 512 B per warp instruction, conflict-free) - half the shared-memory instructions of the
+  // [slot][component][thread] layout (round 2: dynamics kernels 143.2 -> 139.2 us; -DFW_K_SINGLE restores it for A/B)
+  __device__ __forceinline__ T& at(int slot, int kc) {
+    return base[((slot * (FW_N_KC / 2) + (kc >> 1)) * BLOCK + threadIdx.x) * 2 + (kc & 1)];
+  }
+#else
   __device__ __forceinline__ T& at(int slot, int kc) { return base[(slot * FW_N_KC + kc) * BLOCK + threadIdx.x]; }
+#endif
 };
+
+// Stage state of stage S_ for the 16 stored components: ys = y + h * sum_{j < S_} a_{S_ j} K_j, accumulated exactly as
+// the former run-time loop did (ys = fma(h a_sj, K_j, ys), j ascending, zero coefficients included) but with stage and
+// term as compile-time numbers: tableau entries become constant-bank operands, K addresses immediates, no loop / remainder
+// branches and no copy of y (round 2: that loop was 22 % of the executed instructions and 27 % of a warp's time,
+// profiles/r2y_attempt_kernel_ncu_full.csv joined with the SASS).
+template <typename T, int BLOCK, int S_, class KS>
+__device__ __forceinline__ void fw_stage_state(const T (&y)[FW_N_ODE], T h, KS K, T (&ys)[FW_N_ODE]) {
+#pragma unroll
+  for (int j = 0; j < S_; ++j) {
+    const T ha = h * fw_dpA<T>(S_, j);
+#pragma unroll
+    for (int kc = 0; kc < FW_N_KC; ++kc) {
+      const int c = fw_kc_to_ode(kc);
+      ys[c] = fma(ha, K.at(j, kc), j == 0 ? y[c] : ys[c]);
+    }
+  }
+}
 
 // 1/x to ~1 ulp without the division slow path (x is a tolerance scale >= atol > 0, always a normal number)
 __device__ __forceinline__ double fw_rcp(double x) {
@@ -531,11 +564,20 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
   T accB[3], accE[3];    // running B-row / E-row sums of the position components (never stored as K stages)
 #pragma unroll
   for (int j = 0; j < 3; ++j) { accB[j] = fw_dpA<T>(6, 0) * S.k0pos[j]; accE[j] = fw_dpE<T>(0) * S.k0pos[j]; }
+#ifdef FW_FLAT_PASS
+  // experiment build: the six stages as ONE straight-line block (six copies of the right-hand side); a constraint
+  // violation is recorded (first stage wins, as the raise would) and acted on after the last stage instead of branching
+  // out, so that the scheduler may fill the tail of one stage's dependency chain with the next stage's partial sums
+  uint32_t failmask_first = 0u;
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (int s = 1; s <= 6; ++s) {
     T ys[FW_N_ODE], f[FW_N_ODE];
     {
       // y_s = y + h * sum_j a_sj K_j, accumulated as y += (h a_sj) K_j (one fma per term, no separate scaling pass)
+#ifdef FW_COMBINE_LOOP   // experiment build: the former run-time loop over the terms
 #pragma unroll
       for (int kc = 0; kc < FW_N_KC; ++kc) ys[fw_kc_to_ode(kc)] = S.y[fw_kc_to_ode(kc)];
       for (int j = 0; j < s; ++j) {
@@ -543,17 +585,36 @@ __device__ __forceinline__ void fw_ivp_attempt(const fw_sim_t& P, const PAR& PP,
 #pragma unroll
         for (int kc = 0; kc < FW_N_KC; ++kc) ys[fw_kc_to_ode(kc)] = fma(ha, K.at(j, kc), ys[fw_kc_to_ode(kc)]);
       }
+#else
+      switch (s) {
+        case 1: fw_stage_state<T, BLOCK, 1>(S.y, h, K, ys); break;
+        case 2: fw_stage_state<T, BLOCK, 2>(S.y, h, K, ys); break;
+        case 3: fw_stage_state<T, BLOCK, 3>(S.y, h, K, ys); break;
+        case 4: fw_stage_state<T, BLOCK, 4>(S.y, h, K, ys); break;
+        case 5: fw_stage_state<T, BLOCK, 5>(S.y, h, K, ys); break;
+        default: fw_stage_state<T, BLOCK, 6>(S.y, h, K, ys); break;
+      }
+#endif
       // position stage states are never read by the RHS; y_new[pos] is formed from accB when s == 6
 #pragma unroll
       for (int j = 0; j < 3; ++j) ys[7 + j] = S.y[7 + j] + h * accB[j];
     }
     uint32_t failmask = 0u;
     fw_rhs<T, Spec>(P, PP, in, ys, f, failmask);
+#ifdef FW_FLAT_PASS
+    failmask_first = failmask_first ? failmask_first : failmask;
+    if (s == 6 && failmask_first) {
+      S.fail = fw_fail_code<T>(failmask_first);
+      S.status = FW_STATUS_FINISHED;
+      return;
+    }
+#else
     if (failmask) {
       S.fail = fw_fail_code<T>(failmask);
       S.status = FW_STATUS_FINISHED;
       return;
     }
+#endif
     if (s < 6) {
 #pragma unroll
       for (int kc = 0; kc < FW_N_KC; ++kc) K.at(s, kc) = f[fw_kc_to_ode(kc)];

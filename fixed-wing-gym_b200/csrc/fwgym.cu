@@ -356,8 +356,14 @@ fw_attempt_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const F
           // skipped: aircraft that raised inside RK45.__init__ (the init kernel parked that result), and the
           // natural-order visit of an aircraft that is on the priority list
           const bool skip = failv != 0 || (!from_long && h0s < 0.0);
+#ifndef FW_REFILL_LAZY
+          // this lane holds no aircraft, so its registers and K slot 0 are free: every load of the candidate is issued
+          // before `skip` (which depends on two of them) is known - one dependent L2 round trip less per refill
+          // (-DFW_REFILL_LAZY: load only what will be used, as before)
+          {
+#else
           if (!skip) {
-            env = e;
+#endif
             par_base = a.d + (int64_t)a.par_row * a.stride + e;
             if constexpr (Spec::rand)
               for (int r = 0; r < a.n_par_rows; ++r) par_cache[r * 32] = (T)par_base[(int64_t)r * a.stride];
@@ -370,6 +376,9 @@ fw_attempt_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const F
             for (int j = 0; j < 3; ++j) { S.k0pos[j] = (T)cd[(CY_KP + j) * a.stride]; in.cmd[j] = (T)cd[(CY_CMD + j) * a.stride]; }
             fw_load_gusts<T>(P, c, in);
             S.t = 0; S.h_abs = (T)h0; S.rejected = 0; S.attempts = 0; S.accepted = 0; S.fail = 0;
+          }
+          if (!skip) {
+            env = e;
             S.status = FW_STATUS_RUNNING;
           }
         }
