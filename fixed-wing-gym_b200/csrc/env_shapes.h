@@ -89,7 +89,7 @@ inline bool fw_env_same_shape(const fw_env_t& a, const fw_env_t& b) {
   if (a.integration_window != b.integration_window || a.obs_len != b.obs_len || a.obs_step != b.obs_step ||
       a.obs_nvar != b.obs_nvar || a.obs_shape != b.obs_shape || a.obs_norm != b.obs_norm || a.obs_noise != b.obs_noise ||
       a.has_bounds != b.has_bounds || a.n_targets != b.n_targets || a.resample_every != b.resample_every ||
-      a.streak_req != b.streak_req || a.on_success != b.on_success || a.n_factors != b.n_factors ||
+      a.streak_req != b.streak_req || a.n_factors != b.n_factors ||
       a.potential != b.potential || a.step_fail_timesteps != b.step_fail_timesteps || a.n_terms != b.n_terms ||
       a.metrics_enabled != b.metrics_enabled || a.n_rand != b.n_rand || a.n_par_rows != b.n_par_rows ||
       a.n_scale_rows != b.n_scale_rows)

@@ -207,7 +207,9 @@ __device__ __forceinline__ void fw_load_gusts(const fw_sim_t& P, const FwEnvCtx&
   }
 }
 
+#ifndef FW_INIT_BLOCK
 #define FW_INIT_BLOCK 64
+#endif
 template <typename T, class Spec>
 #ifndef FW_INIT_MIN_BLOCKS
 #define FW_INIT_MIN_BLOCKS 8   // 128 registers: one wave at 65536 envs (1024 blocks on 148 x 8 slots); 4 -> 8: init 18 -> 13 us
@@ -668,8 +670,9 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
       if (steps_tgt >= Es.streak_req && (double)cnt / (double)Es.streak_req >= E.streak_fraction) {
         achieved_on_step = !(flags & FWF_GOAL_ACHIEVED);
         flags |= FWF_GOAL_ACHIEVED | FWF_EP_SUCCESS;
-        if (Es.on_success == 1) { done = true; term = FW_TERM_SUCCESS; }
-        else if (Es.on_success == 2) resample = true;
+        // (on_success is a runtime number in every instantiation: env_shapes.h does not compare it)
+        if (E.on_success == 1) { done = true; term = FW_TERM_SUCCESS; }
+        else if (E.on_success == 2) resample = true;
       }
     }
     if (Ls.met) fw_metrics_goal(E, L, c, gb, hist_len);

@@ -18,4 +18,4 @@ for k in attempt env init; do
   tail -1 gpurun_out/ncu_${k}_$TAG.log
 done
 bash scripts/gpu_sanitize.sh $TAG
-python scripts/baseline_report.py --reuse-cpu profiles/r2_baseline_report_cpu_arm.json 2>&1 | grep -E "^GPU|wrote"
+[ -n "$WITH_BASELINE_REPORT" ] && python scripts/baseline_report.py --reuse-cpu profiles/r2_baseline_report_cpu_arm.json 2>&1 | grep -E "^GPU|wrote"

@@ -111,6 +111,23 @@ def test_live_oracle_64_envs(built_lib):
     assert max(out["obs"]) <= TOL and max(out["rew"]) <= TOL and max(out["state"]) <= TOL, out
 
 
+def test_on_success_override_stays_on_specialised_kernels(built_lib):
+    """`target.on_success` is a runtime number in every instantiation (the evaluation harness overrides it on the
+    examples configuration, evaluate_controller.py:68-76): the examples shape is kept, the 100-step success streak ends
+    the episode exactly when the oracle's does, and the steps after the auto-reset still match."""
+    c = dict(config="fixed_wing_config_examples.json", n=4, sim_kw={"turbulence": False},
+             config_kw={"target": {"on_success": "done", "states": {0: {"bound": 150}, 1: {"bound": 80}, 2: {"bound": 25}}}})
+    n, steps = 4, 108
+    vec = make_vec(c, n=n, seed=5)
+    assert vec.kernel_variant().endswith("env=examples"), vec.kernel_variant()
+    orc = pu.make_oracles(n, harness.config_path(c["config"]), c["config_kw"], c["sim_kw"], 5)
+    acts = np.random.RandomState(3).uniform(-0.3, 0.3, (steps, n, 3))
+    out = pu.run_parity(vec, orc, acts)
+    assert out["dones"] == n and out["done_mismatch"] == 0 and out["k_mismatch"] == 0
+    assert max(out["obs"]) <= TOL and max(out["rew"]) <= TOL and max(out["state"]) <= TOL, out
+    vec.close()
+
+
 def test_config1_4096_envs_100_steps(built_lib):
     """BASELINE configs[1] at its STATED size: 4096 envs, fp64 dopri5, turbulence off, 100 steps against
     the CPU oracle stepped on every host core (identical actions and Philox streams).  Two device envs:
