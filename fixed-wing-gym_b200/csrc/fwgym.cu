@@ -214,7 +214,11 @@ template <typename T, class Spec>
 #ifndef FW_INIT_MIN_BLOCKS
 #define FW_INIT_MIN_BLOCKS 8   // 128 registers: one wave at 65536 envs (1024 blocks on 148 x 8 slots); 4 -> 8: init 18 -> 13 us
 #endif
+#ifdef FW_INIT_MAXNREG   // experiment build: a register cap instead of launch bounds
+__global__ void __maxnreg__(FW_INIT_MAXNREG)
+#else
 __global__ void __launch_bounds__(FW_INIT_BLOCK, FW_INIT_MIN_BLOCKS)
+#endif
 fw_init_kernel(const __grid_constant__ typename FwSimArg<T>::type Px, const FwDynArgs a) {
   const fw_sim_t& P = fw_sim_of(Px);
   FW_TL_BEGIN(0);

@@ -1,6 +1,6 @@
 """CPU ORACLE (test infrastructure): numpy twin of fixed-wing-gym_b200/csrc/philox.cuh.
 
-Philox4x32-10 (Salmon et al., SC'11; Random123 known-answer vectors are pinned in tests/test_philox.py) and the draw
+Philox4x32-10 (Salmon et al., SC'11; Random123 known-answer vectors are pinned in tests/test_oracle_cpu.py::test_philox_known_answers) and the draw
 conventions both sides share:
     counter = (global env id, tick, stream, index), key = 64-bit seed (lo, hi)
     uniform : 53-bit double from words 0,1
