@@ -128,6 +128,70 @@ def test_on_success_override_stays_on_specialised_kernels(built_lib):
     vec.close()
 
 
+@pytest.mark.parametrize("n", [33, 197])
+def test_ragged_env_counts(built_lib, n):
+    """Env counts that fill neither a warp (32), an init block (64) nor an env chunk (128): the partial last warp /
+    block / chunk is stepped, counted and handed over like a full one (turbulence + noise on, so every kernel's tail
+    lanes run the full path), and the row stride padding never leaks into results."""
+    c = CASES["turb_noise"]
+    steps = 6
+    vec = make_vec(c, n=n, seed=9)
+    orc = pu.make_oracles(n, harness.config_path(c["config"]), c["config_kw"], c["sim_kw"], 9)
+    acts = np.random.RandomState(n).uniform(-1, 1, (steps, n, 3))
+    out = pu.run_parity(vec, orc, acts)
+    assert out["done_mismatch"] == 0 and out["k_mismatch"] == 0
+    # free-running (device and oracle each continue from their OWN state), under turbulence: observations / rewards hold
+    # the per-step bar; a raw simulator state near a zero crossing of one sensitive aircraft showed 1.7e-9 for one step
+    # (absolute 1.7e-12, env 3 of 197 - not in the ragged part; scripts/gpu_debug_ragged.py), hence the rollout bar there
+    assert max(out["obs"]) <= TOL and max(out["rew"]) <= TOL and max(out["state"]) <= 1e-7, out
+    ctr = vec.counters()
+    assert ctr["env_steps"] == n * steps and ctr["watchdog"] == 0
+    vec.close()
+
+
+def test_capi_argument_errors(built_lib):
+    """The boundary refuses bad calls with a status and a message instead of launching anything: null buffers, a slot that
+    was never submitted, a row range outside the state, an ABI version the library was not built for."""
+    import ctypes
+    from fwgym_b200 import _capi
+    lib = _capi.lib()
+    vec = make_vec(CASES["default"], n=8)
+    vec.reset()
+    h, null = vec._h, ctypes.c_void_p(0)
+    before = vec.get_state().clone()
+    # fw_step without actions / without any observation buffer
+    rc = lib.fw_step(h, null, 0, vec._ptr(vec._obs), vec._ptr(vec._rew), vec._ptr(vec._done), vec._ptr(vec._term),
+                     null, null, null, 1, vec._stream())
+    assert rc == -1 and b"fw_step" in lib.fw_last_error()
+    acts = torch.zeros((8, 3), dtype=torch.float64, device=vec.device)
+    rc = lib.fw_step(h, vec._ptr(acts), 1, null, vec._ptr(vec._rew), vec._ptr(vec._done), vec._ptr(vec._term),
+                     null, null, null, 1, vec._stream())
+    assert rc == -1 and b"observation" in lib.fw_last_error()
+    # host pipeline: waiting on a slot that was never submitted, submitting without fw_host_open
+    slot = ctypes.c_int(0)
+    hact = torch.zeros((8, 3), dtype=torch.float32).pin_memory()
+    assert lib.fw_host_submit(h, ctypes.c_void_p(hact.data_ptr()), vec._stream(), ctypes.byref(slot)) == -1
+    pp = [ctypes.c_void_p() for _ in range(4)]
+    assert lib.fw_host_wait(h, 3, *[ctypes.byref(x) for x in pp]) == -1
+    # row export outside the state
+    buf = torch.zeros(16, dtype=torch.float64, device=vec.device)
+    assert lib.fw_get_rows(h, 10 ** 6, 1, vec._ptr(buf), vec._stream()) == -1
+    # a configuration of another ABI version
+    pod = vec.cc.pod()
+    pod.abi_version += 1
+    out = ctypes.c_void_p()
+    assert lib.fw_create(ctypes.byref(pod), 8, 0, vec.device.index or 0, ctypes.byref(out)) == -5
+    assert lib.fw_set_config(h, ctypes.byref(pod)) == -5
+    # nothing above touched the state, and the handle still steps
+    torch.cuda.synchronize()
+    assert torch.equal(before, vec.get_state())
+    vec.step_tensors(acts)
+    assert vec.counters()["env_steps"] == 8
+    with pytest.raises(_capi.FwError):
+        _capi.check(lib.fw_host_wait(h, 3, *[ctypes.byref(x) for x in pp]))
+    vec.close()
+
+
 def test_config1_4096_envs_100_steps(built_lib):
     """BASELINE configs[1] at its STATED size: 4096 envs, fp64 dopri5, turbulence off, 100 steps against
     the CPU oracle stepped on every host core (identical actions and Philox streams).  Two device envs:
