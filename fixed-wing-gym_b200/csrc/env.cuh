@@ -220,7 +220,9 @@ struct FwObsWriter {
   double* o64;
   int64_t base;     // first element of this env's row in o64 (and in o32 unless base32 >= 0)
   int64_t base32;   // >= 0: o32 is a staging tile (fw_env_kernel, zero-copy host results) and this is the row's offset in it
+  bool commit = true;   // false: the lanes that only accompany a cooperative reset (fw_env_kernel) write nothing
   __device__ __forceinline__ void operator()(int idx, double v) const {
+    if (!commit) return;
     if (o32) o32[(base32 >= 0 ? base32 : base) + idx] = (float)v;
     if (o64) o64[base + idx] = v;
   }
@@ -469,13 +471,17 @@ __device__ __forceinline__ void fw_rot_euler(double phi, double th, double psi, 
 
 // Dryden white noise for sim step s of the episode keyed by eptick (4 streams, already scaled)
 template <bool INL>
-__device__ __forceinline__ void fw_turb_noise(const fw_sim_t& P, uint32_t k0, uint32_t k1, uint32_t genv, uint32_t eptick,
-                                              int s, double (&u)[4]) {
-  FwRng g{k0, k1, genv, eptick};
+__device__ __forceinline__ void fw_turb_noise_g(const fw_sim_t& P, const FwRng& g, int s, double (&u)[4]) {
   fw_normal2_t<INL>(g, FW_RS_TURB, 2u * (uint32_t)s, u[0], u[1]);
   fw_normal2_t<INL>(g, FW_RS_TURB, 2u * (uint32_t)s + 1u, u[2], u[3]);
 #pragma unroll
   for (int j = 0; j < 4; ++j) u[j] *= P.turb_noise_scale;
+}
+template <bool INL>
+__device__ __forceinline__ void fw_turb_noise(const fw_sim_t& P, uint32_t k0, uint32_t k1, uint32_t genv, uint32_t eptick,
+                                              int s, double (&u)[4]) {
+  FwRng g{k0, k1, genv, eptick};
+  fw_turb_noise_g<INL>(P, g, s, u);
 }
 // ... or the caller's samples (PyFly.reset(turbulence_noise=...), fixed_wing.py:287,308): [4, len, n] unscaled standard
 // normals; a step beyond the array wraps around (pyfly: idx % noise.shape[-1])
@@ -657,16 +663,24 @@ __device__ __forceinline__ void fw_metrics_reset(const fw_env_t& E, const FwLayo
 // PyFly.reset + FixedWingAircraft.reset for one env.  init_state rows: FW_N_SV + 3 (wind n,e,d); NaN = sample.
 // SH-templated and out of line: episode ends are rare, so the step path of every instantiation keeps this code out
 // of its straight-line block; inside, a fixed shape still folds (the shape is taken from SH, not from arguments).
-template <class SH>
-__device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
-                                          uint32_t k0, uint32_t k1, uint32_t genv, const double* __restrict__ init_state,
-                                          const double* __restrict__ init_target, int64_t in_stride,
-                                          const FwTurbInject ti, const FwObsWriter& out) {
+// COOP (fw_env_kernel's auto-resets): the WHOLE WARP runs this function for one env - identical inputs, identical control
+// flow, every lane writes the same values to the same state rows (one of the writes lands; CUDA defines that) and only
+// the lane that owns the env writes observations (out.commit).  What it buys: the reset's ~30 Philox blocks are computed
+// once, two per lane, and broadcast by shuffles (philox.cuh, FwRng::coop) instead of one lane computing them in series
+// while 31 wait.
+template <class SH, bool COOP = false>
+__device__ __forceinline__ void fw_reset_env_body(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
+                                                  uint32_t k0, uint32_t k1, uint32_t genv,
+                                                  const double* __restrict__ init_state,
+                                                  const double* __restrict__ init_target, int64_t in_stride,
+                                                  const FwTurbInject ti, const FwObsWriter& out) {
   FW_SHAPE_REFS;
   const uint32_t tick = (uint32_t)c.I(I_TICK);
+  if constexpr (COOP) __syncwarp();     // every lane has read the counter before any lane overwrites it
   c.I(I_TICK) = (int32_t)(tick + 1u);
   c.I(I_EPTICK) = (int32_t)tick;
   FwRng g{k0, k1, genv, tick};
+  if constexpr (COOP) fw_rng_fill_bank(g);
   int dummy = 0;
   auto given = [&](int r, double& v) -> bool {
     if (!init_state) return false;
@@ -717,7 +731,7 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   if (Ps.turbulence) {
     double u0[4];
     if (ti.noise) fw_turb_noise_injected(P, ti, c.env, 0, u0);
-    else fw_turb_noise<SH::fixed>(P, k0, k1, genv, tick, 0, u0);
+    else fw_turb_noise_g<SH::fixed>(P, g, 0, u0);
     for (int j = 0; j < 4; ++j) c.D(D_TU + j) = u0[j];
 #pragma unroll
     for (int f = 0; f < FW_N_FILT; ++f) {
@@ -832,4 +846,12 @@ __device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, 
   c.I(I_LASTK) = 0;
   c.D(D_EPRET) = 0.0;
   if (Ls.met) fw_metrics_reset(E, L, c, gb0);
+}
+// out of line: the explicit-reset kernel (one thread per env)
+template <class SH>
+__device__ __noinline__ void fw_reset_env(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvCtx& c,
+                                          uint32_t k0, uint32_t k1, uint32_t genv, const double* __restrict__ init_state,
+                                          const double* __restrict__ init_target, int64_t in_stride,
+                                          const FwTurbInject ti, const FwObsWriter& out) {
+  fw_reset_env_body<SH, false>(E, P, L, c, k0, k1, genv, init_state, init_target, in_stride, ti, out);
 }

@@ -614,7 +614,7 @@ template <class SH>
 __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P, const FwLayout& L, const FwEnvArgs& a,
                                             int64_t env, const FwEnvPre<fw_env_nz<SH>()>& pre,
                                             double (&m)[FW_N_METRIC_SUMS], int& n_reset, int& attempts, int& accepted,
-                                            int& failed) {
+                                            int& failed, bool& need_reset) {
   FW_SHAPE_REFS;
   FwEnvCtx c{a.d, a.i, L.stride, env};
   fw_commit_step<SH>(P, c, a.cd + env, a.ci + env, L.stride, a.k0, a.k1, a.env_offset + (uint32_t)env, a.ti,
@@ -733,10 +733,8 @@ __device__ __forceinline__ void fw_env_step(const fw_env_t& E, const fw_sim_t& P
     if (term == FW_TERM_STEPS) m[MS_STEPS_TERM] += 1.0;
     if (term == FW_TERM_SUCCESS) m[MS_SUCCESS_TERM] += 1.0;
   }
-  if (do_reset) {
-    n_reset += 1;
-    fw_reset_env<SH>(E, P, L, c, a.k0, a.k1, genv, nullptr, nullptr, 0, FwTurbInject{nullptr, 0, 0}, ow);
-  }
+  if (do_reset) n_reset += 1;
+  need_reset = do_reset;   // the reset itself is run by the whole warp together (fw_env_kernel)
 }
 
 // per-warp sum of the metric contributions, then one atomic per non-zero metric (all 32 lanes must call)
@@ -845,7 +843,29 @@ fw_env_kernel(const __grid_constant__ fw_env_t E, const __grid_constant__ fw_sim
 #pragma unroll
   for (int k = 0; k < FW_N_METRIC_SUMS; ++k) m[k] = 0.0;
   int n_reset = 0, attempts = 0, accepted = 0, failed = 0, nv = 0;
-  if (env < a.n) { fw_env_step<SH>(E, P, L, a, env, pre, m, n_reset, attempts, accepted, failed); nv = 1; }
+  bool need_reset = false;
+  if (env < a.n) { fw_env_step<SH>(E, P, L, a, env, pre, m, n_reset, attempts, accepted, failed, need_reset); nv = 1; }
+  // ---- auto-resets, one env at a time, by the WHOLE warp (env.cuh, fw_reset_env<SH, true>): a reset used to be one lane
+  // running ~4 500 instructions (60 % of them Philox blocks) while 31 lanes waited, and in the stationary episode mix
+  // half of the env blocks contain one (+10 us of mean block run time, profiles/r2_step_timeline.txt).
+  {
+    const unsigned fullm = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned rm = __ballot_sync(fullm, need_reset);
+    while (rm) {
+      const int leader = __ffs((int)rm) - 1;
+      rm &= rm - 1u;
+      const int64_t env_l = __shfl_sync(fullm, env, leader);
+      const int tid_l = (int)(threadIdx.x & ~31u) + leader;
+      FwEnvCtx c{a.d, a.i, L.stride, env_l};
+      FwObsWriter ow{a.stage_obs ? fw_env_tile : a.obs_out, a.obs64_out, env_l * (int64_t)a.obs_dim,
+                     a.stage_obs ? (int64_t)tid_l * a.obs_dim : (int64_t)-1};
+      ow.commit = lane == leader;
+      fw_reset_env_body<SH, true>(E, P, L, c, a.k0, a.k1, a.env_offset + (uint32_t)env_l, nullptr, nullptr, 0,
+                                  FwTurbInject{nullptr, 0, 0}, ow);
+      __syncwarp();
+    }
+  }
   if (a.stage_obs) {
     __syncthreads();
     const int64_t first = (int64_t)blockIdx.x * FW_ENV_BLOCK;

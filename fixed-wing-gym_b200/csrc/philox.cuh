@@ -39,9 +39,63 @@ __device__ __noinline__ void fw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   fw_philox4x32_10_inl(c0, c1, c2, c3, k0, k1, out);
 }
 
+// coop (fw_env_kernel's warp-cooperative auto-reset): ALL 32 lanes of the warp run the reset of ONE env together, so
+// they draw the same (stream, idx) at the same instruction.  The Philox blocks of that (env, tick) are then computed ONCE,
+// two per lane (bank: slots `lane` and `32 + lane` of fw_pc_slot's numbering), and a draw is four shuffles instead of a
+// 90-instruction block: a reset is ~30 draws and was ~60 % Philox.  Same counters, same words, same values.
 struct FwRng {
   uint32_t k0, k1, env, tick;
+  bool coop = false;
+  uint32_t bank[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 };
+#define FW_PC_SLOTS 64
+// (stream, idx) <-> slot: INIT idx = fw_sv id 0..20 | WIND 0..2 | TURB 0..1 | ENV_U 0..13 | ENV_N 0..23; -1: not banked
+__device__ __forceinline__ int fw_pc_slot(uint32_t stream, uint32_t idx) {
+  // branch-free for run-time arguments: first slot and slot count of the stream, one byte each
+  const uint32_t first = (uint32_t)(0x281a181500ull >> (8u * stream)) & 0xffu;    // 0, 21, 24, 26, 40
+  const uint32_t count = (uint32_t)(0x180e020315ull >> (8u * stream)) & 0xffu;    // 21, 3, 2, 14, 24
+  return (stream < 5u && idx < count) ? (int)(first + idx) : -1;
+}
+__device__ __forceinline__ void fw_pc_unslot(int slot, uint32_t& stream, uint32_t& idx) {
+  if (slot < 21) { stream = 0u; idx = (uint32_t)slot; }
+  else if (slot < 24) { stream = 1u; idx = (uint32_t)(slot - 21); }
+  else if (slot < 26) { stream = 2u; idx = (uint32_t)(slot - 24); }
+  else if (slot < 40) { stream = 3u; idx = (uint32_t)(slot - 26); }
+  else { stream = 4u; idx = (uint32_t)(slot - 40); }
+}
+// fill the bank of a cooperative generator (every lane of the warp must call)
+__device__ __forceinline__ void fw_rng_fill_bank(FwRng& g) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    uint32_t stream, idx, w[4];
+    fw_pc_unslot(r * 32 + lane, stream, idx);
+    fw_philox4x32_10_inl(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g.bank[4 * r + k] = w[k];
+  }
+  g.coop = true;
+}
+
+// one Philox block of the generator: from the warp's bank when it holds it (cooperative mode), else computed
+template <bool INL>
+__device__ __forceinline__ void fw_block(const FwRng& g, uint32_t stream, uint32_t idx, uint32_t (&w)[4]) {
+  if (g.coop) {
+    const int s = fw_pc_slot(stream, idx);
+    if (s >= 0) {                       // warp-uniform (all lanes draw the same block)
+      const int src = s & 31;
+      const bool hi = s >= 32;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t v0 = __shfl_sync(0xffffffffu, g.bank[k], src), v1 = __shfl_sync(0xffffffffu, g.bank[4 + k], src);
+        w[k] = hi ? v1 : v0;
+      }
+      return;
+    }
+  }
+  if constexpr (INL) fw_philox4x32_10_inl(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+  else fw_philox4x32_10(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+}
 
 // 53-bit uniform in [0,1) from two words (same construction as numpy's random_sample: (a>>5, b>>6))
 __device__ __forceinline__ double fw_u53(uint32_t a, uint32_t b) {
@@ -51,8 +105,7 @@ __device__ __forceinline__ double fw_u53(uint32_t a, uint32_t b) {
 template <bool INL = false>
 __device__ __forceinline__ double fw_uniform01(const FwRng& g, uint32_t stream, uint32_t idx) {
   uint32_t w[4];
-  if constexpr (INL) fw_philox4x32_10_inl(g.env, g.tick, stream, idx, g.k0, g.k1, w);
-  else fw_philox4x32_10(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+  fw_block<INL>(g, stream, idx, w);
   return fw_u53(w[0], w[1]);
 }
 
@@ -64,7 +117,7 @@ __device__ __forceinline__ double fw_uniform(const FwRng& g, uint32_t stream, ui
 // two standard normals per Philox block (Box-Muller); u1 in (0,1] so the log is finite
 __device__ __forceinline__ void fw_normal2_inl(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
   uint32_t w[4];
-  fw_philox4x32_10_inl(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+  fw_block<true>(g, stream, idx, w);
   double u1 = 1.0 - fw_u53(w[0], w[1]);
   double u2 = fw_u53(w[2], w[3]);
   // branch-free fwmath routines (csrc/fwmath.cuh): 14 observation-noise draws + 4 gust draws per env step make

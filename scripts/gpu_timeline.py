@@ -20,9 +20,9 @@ flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 buf = (ctypes.c_ulonglong * 8)()
 rows = []
 for t in range(40):
-    flush.zero_()
     torch.cuda.synchronize()
     _capi.check(lib.fw_debug_timeline(None, 1))
+    flush.zero_()          # like bench.py: the step is enqueued while the flush runs, so no host launch latency is exposed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     vec.step_tensors(acts[t])
