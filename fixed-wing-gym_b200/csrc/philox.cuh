@@ -47,6 +47,7 @@ struct FwRng {
   uint32_t k0, k1, env, tick;
   bool coop = false;
   uint32_t bank[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  double zbank[4] = {0.0, 0.0, 0.0, 0.0};   // Box-Muller pairs of this lane's two blocks (used for the TURB / ENV_N slots)
 };
 #define FW_PC_SLOTS 64
 // (stream, idx) <-> slot: INIT idx = fw_sv id 0..20 | WIND 0..2 | TURB 0..1 | ENV_U 0..13 | ENV_N 0..23; -1: not banked
@@ -63,20 +64,6 @@ __device__ __forceinline__ void fw_pc_unslot(int slot, uint32_t& stream, uint32_
   else if (slot < 40) { stream = 3u; idx = (uint32_t)(slot - 26); }
   else { stream = 4u; idx = (uint32_t)(slot - 40); }
 }
-// fill the bank of a cooperative generator (every lane of the warp must call)
-__device__ __forceinline__ void fw_rng_fill_bank(FwRng& g) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    uint32_t stream, idx, w[4];
-    fw_pc_unslot(r * 32 + lane, stream, idx);
-    fw_philox4x32_10_inl(g.env, g.tick, stream, idx, g.k0, g.k1, w);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) g.bank[4 * r + k] = w[k];
-  }
-  g.coop = true;
-}
-
 // one Philox block of the generator: from the warp's bank when it holds it (cooperative mode), else computed
 template <bool INL>
 __device__ __forceinline__ void fw_block(const FwRng& g, uint32_t stream, uint32_t idx, uint32_t (&w)[4]) {
@@ -86,10 +73,8 @@ __device__ __forceinline__ void fw_block(const FwRng& g, uint32_t stream, uint32
       const int src = s & 31;
       const bool hi = s >= 32;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t v0 = __shfl_sync(0xffffffffu, g.bank[k], src), v1 = __shfl_sync(0xffffffffu, g.bank[4 + k], src);
-        w[k] = hi ? v1 : v0;
-      }
+      for (int k = 0; k < 4; ++k)       // `hi` is warp-uniform: every lane selects its own word first, then one shuffle
+        w[k] = __shfl_sync(0xffffffffu, hi ? g.bank[4 + k] : g.bank[k], src);
       return;
     }
   }
@@ -115,9 +100,23 @@ __device__ __forceinline__ double fw_uniform(const FwRng& g, uint32_t stream, ui
 }
 
 // two standard normals per Philox block (Box-Muller); u1 in (0,1] so the log is finite
+__device__ __forceinline__ void fw_box_muller(const uint32_t (&w)[4], double& z0, double& z1);
 __device__ __forceinline__ void fw_normal2_inl(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
+  if (g.coop) {                         // cooperative reset: the pair was computed by the lane that holds the block
+    const int s = fw_pc_slot(stream, idx);
+    if (s >= 0) {
+      const int src = s & 31;
+      const bool hi = s >= 32;
+      z0 = __shfl_sync(0xffffffffu, hi ? g.zbank[2] : g.zbank[0], src);
+      z1 = __shfl_sync(0xffffffffu, hi ? g.zbank[3] : g.zbank[1], src);
+      return;
+    }
+  }
   uint32_t w[4];
   fw_block<true>(g, stream, idx, w);
+  fw_box_muller(w, z0, z1);
+}
+__device__ __forceinline__ void fw_box_muller(const uint32_t (&w)[4], double& z0, double& z1) {
   double u1 = 1.0 - fw_u53(w[0], w[1]);
   double u2 = fw_u53(w[2], w[3]);
   // branch-free fwmath routines (csrc/fwmath.cuh): 14 observation-noise draws + 4 gust draws per env step make
@@ -128,6 +127,23 @@ __device__ __forceinline__ void fw_normal2_inl(const FwRng& g, uint32_t stream, 
   z0 = r * c;
   z1 = r * s;
 }
+// fill the bank of a cooperative generator (every lane of the warp must call)
+__device__ __forceinline__ void fw_rng_fill_bank(FwRng& g) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    uint32_t stream, idx, w[4];
+    fw_pc_unslot(r * 32 + lane, stream, idx);
+    fw_philox4x32_10_inl(g.env, g.tick, stream, idx, g.k0, g.k1, w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g.bank[4 * r + k] = w[k];
+    // the normal pair of the block, whatever its stream (one uniform evaluation per round for the whole warp; only the
+    // TURB slots of round 0 and the ENV_N slots of round 1 are ever asked for)
+    fw_box_muller(w, g.zbank[2 * r], g.zbank[2 * r + 1]);
+  }
+  g.coop = true;
+}
+
 __device__ __noinline__ void fw_normal2(const FwRng& g, uint32_t stream, uint32_t idx, double& z0, double& z1) {
   fw_normal2_inl(g, stream, idx, z0, z1);
 }
