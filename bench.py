@@ -544,10 +544,10 @@ def run_gpu_arm(a):
             "env_kernel": {"bound": "hbm", "ms_per_launch": env_ms / max(1, prof_steps),
                            "achieved_gbs": ENV_BYTES_PER_STEP * n / max(1e-9, env_ms / max(1, prof_steps) * 1e-3) / 1e9,
                            "peak_gbs": _measured_peaks().get("hbm_gbs"),
-                           "note": "time between two CUDA events around the launch: includes ~20 us of launch gap / "
-                                   "event cost; on the GPU's own timer the kernel runs 38.5 us alone and sticks out "
-                                   "22.5 us behind the attempt kernel when overlapped "
-                                   "(profiles/r1zz_step_timeline.txt); latency-bound, not bandwidth-bound"},
+                           "note": "time between two CUDA events around the launch of the serialised profiling pass; "
+                                   "in the timed region the kernel runs overlapped with the attempt kernel's tail and its "
+                                   "last block ends ~25 us behind the attempt kernel on the GPU's own timer "
+                                   "(profiles/r2f_step_timeline.txt); latency-bound, not bandwidth-bound"},
             "wall_ms_timed_region": wall_ms,
             "overlap": {"env_kernel": "programmatic dependent launch behind the attempt kernel, per-chunk completion "
                                       "counters", "serial_ms_per_step": (dyn_ms + env_ms) / max(1, prof_steps),
